@@ -1,0 +1,159 @@
+/* sonar_b200 -- C ABI of the B200-native SONAR text-embedding hot path.
+ *
+ * Plain C, no torch / CUDA types in the signatures: device buffers are `void*` /
+ * typed raw pointers, the stream is an opaque `void*` (a `cudaStream_t`).
+ * Every entry point returns 0 on success or a negative code and never throws;
+ * `sb_last_error()` gives the message (thread-local).  No hidden device
+ * allocations happen inside `sb_encoder_forward`; the caller owns all buffers.
+ *
+ * The reference (facebookresearch/SONAR) has NO native interface for this path --
+ * it reaches fairseq2 Python modules.  Each entry point therefore cites the Python
+ * interface it replaces:
+ *
+ *   sb_encoder_create / sb_encoder_forward
+ *       <- SonarTextTransformerEncoderModel.forward(SequenceBatch) -> SonarEncoderOutput
+ *          (sonar/models/sonar_text/model.py:130-143; built by
+ *           SonarTextEncoderFactory.create_model, sonar/models/sonar_text/factory.py:72-120),
+ *          called from TextToEmbeddingModelPipeline.predict via `.map(self.model)`
+ *          (sonar/inference_pipelines/text.py:231-247).
+ *   seq_lens / padded ids layout
+ *       <- Collater(pad_idx) + extract_sequence_batch (text.py:241-242,
+ *          sonar/inference_pipelines/utils.py:18-21): ids int64 [B,S] right-padded,
+ *          PaddingMask(seq_lens).
+ *   sb_pool
+ *       <- SonarTextTransformerEncoderModel.static_pooling (model.py:86-128).
+ *   weight layout
+ *       <- fairseq2 state-dict names mapped in sonar/models/sonar_text/handler.py:71-92
+ *          (nn.Linear [out,in] row-major).
+ */
+#ifndef SONAR_B200_H_
+#define SONAR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_OK 0
+#define SB_ERR_INVALID (-1)  /* bad argument / unsupported shape */
+#define SB_ERR_CUDA (-2)     /* CUDA runtime error */
+#define SB_ERR_DRIVER (-3)   /* driver entry point / tensor-map failure */
+#define SB_ERR_INPUT (-4)    /* device-side input check failed (e.g. token id out of range) */
+
+/* Reference `Pooling` enum values (sonar/models/sonar_text/model.py:23-27). */
+#define SB_POOL_MAX 1
+#define SB_POOL_MEAN 2
+#define SB_POOL_LAST 3
+
+/* GEMM epilogues */
+#define SB_EPI_BIAS 0
+#define SB_EPI_BIAS_RELU 1
+#define SB_EPI_BIAS_RESIDUAL 2
+
+typedef struct SbEncoder SbEncoder;
+
+/* Mirrors the fields of SonarTextEncoderConfig that reach the math
+ * (sonar/models/sonar_text/config.py:14-84). */
+typedef struct SbEncoderConfig {
+  int32_t model_dim;     /* 1024 (multiple of 256, <= 1024; head_dim must be 64) */
+  int32_t num_layers;    /* 24 */
+  int32_t num_heads;     /* 16 */
+  int32_t ffn_inner_dim; /* 8192 (multiple of 256) */
+  int64_t vocab_size;    /* 256206 */
+  int32_t pos_rows;      /* rows of the sinusoidal table = max_seq_len + pad_idx + 1 = 514 */
+  int32_t pooling;       /* SB_POOL_* ; `basic` = SB_POOL_MEAN */
+  float ln_eps;          /* 1e-5 */
+  float embed_scale;     /* sqrt(model_dim) unless no_scale_embedding */
+  int32_t cta_group;     /* 0/2 = paired-CTA tcgen05 tiles (default), 1 = single-CTA */
+  int32_t num_sms;       /* 0 = query the device */
+} SbEncoderConfig;
+
+/* All pointers are DEVICE pointers and stay owned by the caller (must outlive the handle).
+ * Matrices: bf16, row-major [out_features, in_features].  Vectors: fp32. */
+typedef struct SbLayerWeights {
+  const void* wqkv;   /* bf16 [3*D, D] = rows of q_proj | k_proj | v_proj */
+  const float* bqkv;  /* [3*D] */
+  const void* wo;     /* bf16 [D, D]   self_attn.output_proj */
+  const float* bo;    /* [D] */
+  const void* w1;     /* bf16 [F, D]   ffn.inner_proj */
+  const float* b1;    /* [F] */
+  const void* w2;     /* bf16 [D, F]   ffn.output_proj */
+  const float* b2;    /* [D] */
+  const float* ln1_g; /* self_attn_layer_norm */
+  const float* ln1_b;
+  const float* ln2_g; /* ffn_layer_norm */
+  const float* ln2_b;
+} SbLayerWeights;
+
+typedef struct SbEncoderWeights {
+  const void* embed;           /* bf16 [vocab, D]  encoder_frontend.embed.weight */
+  const float* pos_table;      /* fp32 [pos_rows, D]; row t = sinusoid of position t + pad_idx + 1 */
+  const float* final_ln_g;     /* layer_norm.weight */
+  const float* final_ln_b;     /* layer_norm.bias */
+  const SbLayerWeights* layers; /* HOST array of num_layers entries (copied at create) */
+} SbEncoderWeights;
+
+const char* sb_last_error(void);
+int sb_version(void);
+
+int sb_encoder_create(const SbEncoderConfig* cfg, const SbEncoderWeights* w, SbEncoder** out);
+void sb_encoder_destroy(SbEncoder* enc);
+
+/* Bytes of device workspace needed for a batch of <= max_batch sequences holding
+ * <= max_tokens real (unpadded) tokens in total. */
+int sb_encoder_workspace_bytes(const SbEncoder* enc, int32_t max_batch, int64_t max_tokens, size_t* bytes);
+
+/* One pass of the hot path.
+ *   ids            DEVICE int64 [batch, ids_row_stride >= seq_len], right-padded (any pad value)
+ *   seq_lens_host  HOST int32 [batch] true lengths (1..seq_len); NULL = every row is full (no padding_mask)
+ *   out            DEVICE fp32 [batch, model_dim] sentence embeddings
+ *   encoded        DEVICE fp32 [batch, seq_len, model_dim] or NULL (final-LayerNormed states, padded rows zeroed)
+ * Asynchronous on `stream` (does not synchronise). */
+int sb_encoder_forward(SbEncoder* enc, const int64_t* ids, int64_t ids_row_stride, const int32_t* seq_lens_host,
+                       int32_t batch, int32_t seq_len, float* out, float* encoded, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* Same, but `ids_host` / `out_host` are HOST buffers (pinned for full speed); performs the
+ * H2D copy of the ids, the forward and the D2H copy of the embeddings on `stream`, then
+ * synchronises the stream.  `ids_staging` is DEVICE int64 [batch*seq_len], `out_staging`
+ * DEVICE fp32 [batch*model_dim] (caller-owned). */
+int sb_encoder_forward_host(SbEncoder* enc, const int64_t* ids_host, const int32_t* seq_lens_host, int32_t batch,
+                            int32_t seq_len, float* out_host, int64_t* ids_staging, float* out_staging,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* Checks the sticky device-side input flag (token id out of range) of the last forwards;
+ * synchronises `stream`.  Returns SB_OK or SB_ERR_INPUT. */
+int sb_encoder_check_inputs(SbEncoder* enc, void* workspace, void* stream);
+
+/* ---- individual kernels (used by the parity tests and the micro-benchmarks) ---- */
+
+/* C[M,N] = epi(A[M,K] * W[N,K]^T + bias[N]) ; A, W bf16 row-major; C bf16 (out_fp32=0) or fp32;
+ * residual (SB_EPI_BIAS_RESIDUAL) has C's dtype and may alias C.  N % 256 == 0, K % 64 == 0. */
+int sb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int32_t out_fp32,
+                 const float* bias, const void* residual, int64_t ldr, int32_t M, int32_t N, int32_t K, int32_t epi,
+                 int32_t cta_group, void* stream);
+
+/* y[T,D] (bf16) = LayerNorm(x[T,D] fp32) */
+int sb_layernorm(const float* x, const float* gamma, const float* beta, float eps, void* y, int64_t T, int32_t D,
+                 void* stream);
+
+/* packed self-attention: qkv bf16 [T, 3*64*H], cu_seqlens DEVICE int32 [B+1], out bf16 [T, 64*H] */
+int sb_attention(const void* qkv, const int32_t* cu_seqlens, int32_t B, int32_t max_len, int32_t H, void* out,
+                 void* stream);
+
+/* x[cu[b]+t,:] = embed[ids[b,t],:]*scale + pos[t,:] ; err_flag DEVICE int32 (set to 1 on a bad id) */
+int sb_embed(const int64_t* ids, int64_t ids_row_stride, const int32_t* cu_seqlens, int32_t B, int32_t S,
+             const void* embed, int64_t vocab, const float* pos_table, int32_t pos_rows, int32_t D, float scale,
+             float* x, int32_t* err_flag, void* stream);
+
+/* (optional LayerNorm +) pooling of packed rows x fp32 [T,D] -> out fp32 [B,D] */
+int sb_pool(const float* x, const int32_t* cu_seqlens, int32_t B, int32_t D, const float* gamma, const float* beta,
+            float eps, int32_t apply_ln, int32_t pool_mode, float* out, float* encoded_padded, int32_t S_padded,
+            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SONAR_B200_H_ */

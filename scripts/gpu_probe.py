@@ -1,0 +1,175 @@
+"""Bring-up / diagnosis probe for the CUDA kernels (run under gpurun, one stage per process so a
+trapped kernel cannot poison later stages):
+
+    python scripts/gpu_probe.py elementwise | gemm1 | gemm2 | perf | encoder
+"""
+
+import math
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from sonar_b200 import ops  # noqa: E402
+
+DEV = torch.device("cuda:0")
+
+
+def rnd(shape, scale, seed, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(DEV, dtype)
+
+
+def err_map(out, ref, rb=32, cb=64):
+    """coarse map of where the result is wrong: fraction of bad elements per (row block, col block)."""
+    bad = ((out - ref).abs() > (ref.abs() * 0.02 + 0.05)).float()
+    m, n = bad.shape
+    mm, nn = (m // rb) * rb, (n // cb) * cb
+    if mm == 0 or nn == 0:
+        return bad.mean().item()
+    blk = bad[:mm, :nn].view(mm // rb, rb, nn // cb, cb).mean(dim=(1, 3))
+    return blk
+
+
+def stage_elementwise():
+    d = 1024
+    x = rnd((300, d), 3.0, 1) + 0.5
+    g, b = 1 + rnd((d,), 0.1, 2), rnd((d,), 0.1, 3)
+    y = ops.layernorm(x, g, b)
+    ref = torch.nn.functional.layer_norm(x, (d,), g, b, 1e-5)
+    print("layernorm max err", (y.float() - ref).abs().max().item())
+    lens = [5, 128, 1, 77]
+    xx = rnd((sum(lens), d), 2.0, 4)
+    cu = ops.cu_seqlens_of(lens).to(DEV)
+    out = ops.pool_packed(xx, cu, "mean", gamma=g, beta=b)
+    yy = torch.nn.functional.layer_norm(xx, (d,), g, b, 1e-5)
+    refp = torch.stack([yy[int(cu[i]):int(cu[i + 1])].mean(0) for i in range(len(lens))])
+    print("ln_pool max err", (out - refp).abs().max().item())
+    # attention
+    h = 16
+    for lens in ([128] * 3, [1, 17, 64, 65, 130, 514]):
+        t = sum(lens)
+        qkv = rnd((t, 3 * d), 1.0, 5, torch.bfloat16)
+        cu = ops.cu_seqlens_of(lens).to(DEV)
+        o = ops.attention(qkv, cu, max(lens), h)
+        torch.cuda.synchronize()
+        s0, worst = 0, 0.0
+        for n in lens:
+            blk = qkv[s0:s0 + n].float()
+            q, k, v = (blk[:, i * d:(i + 1) * d].view(n, h, 64).transpose(0, 1) for i in range(3))
+            r = torch.nn.functional.scaled_dot_product_attention(q[None], k[None], v[None])[0].transpose(0, 1).reshape(n, d)
+            worst = max(worst, (o[s0:s0 + n].float() - r).abs().max().item())
+            s0 += n
+        print("attention lens", lens, "max err", worst)
+
+
+def stage_gemm(cg):
+    shapes = [(128, 256, 64), (128, 256, 128), (256, 256, 64), (256, 512, 256), (300, 512, 192),
+              (1000, 1024, 1024), (4096, 3072, 1024), (777, 1024, 8192), (8192, 8192, 1024)]
+    for (m, n, k) in shapes:
+        a = rnd((m, k), 1.0, 1, torch.bfloat16)
+        w = rnd((n, k), 1 / math.sqrt(k), 2, torch.bfloat16)
+        bias = rnd((n,), 0.5, 3)
+        ref = a.float() @ w.float().T + bias
+        for od in (torch.bfloat16, torch.float32):
+            out = ops.gemm_bf16(a, w, bias, epilogue="bias", out_dtype=od, cta_group=cg)
+            torch.cuda.synchronize()
+            e = (out.float() - ref).abs().max().item()
+            ok = e < 0.1
+            print(f"gemm cg={cg} {m}x{n}x{k} out={str(od)[6:]} max_err={e:.4g} {'OK' if ok else 'WRONG'}", flush=True)
+            if not ok:
+                em = err_map(out.float(), ref)
+                torch.set_printoptions(linewidth=200, precision=2)
+                print("bad-fraction map (rows=32-row blocks, cols=64-col blocks):\n", em)
+                print("out[0,:8]", out[0, :8].float().tolist(), "\nref[0,:8]", ref[0, :8].tolist())
+                return
+    # epilogues
+    m, n, k = 1500, 1024, 1024
+    a = rnd((m, k), 1.0, 4, torch.bfloat16)
+    w = rnd((n, k), 1 / math.sqrt(k), 5, torch.bfloat16)
+    bias = rnd((n,), 0.5, 6)
+    out = ops.gemm_bf16(a, w, bias, epilogue="relu", cta_group=cg)
+    print("relu max err", (out.float() - torch.relu(a.float() @ w.float().T + bias)).abs().max().item())
+    x = rnd((m, n), 2.0, 7)
+    ref = x + a.float() @ w.float().T + bias
+    ops.gemm_bf16(a, w, bias, epilogue="residual", residual=x, out=x, cta_group=cg)
+    print("residual fp32 in-place max err", (x - ref).abs().max().item())
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for s, e in evs:
+        s.record()
+        fn()
+        e.record()
+    torch.cuda.synchronize()
+    ts = sorted(s.elapsed_time(e) for s, e in evs)
+    return ts[len(ts) // 2], ts[0]
+
+
+def stage_perf():
+    m = 131072
+    for (n, k, epi) in [(3072, 1024, "bias"), (1024, 1024, "residual"), (8192, 1024, "relu"), (1024, 8192, "residual")]:
+        a = rnd((m, k), 1.0, 1, torch.bfloat16)
+        w = rnd((n, k), 1 / math.sqrt(k), 2, torch.bfloat16)
+        bias = rnd((n,), 0.5, 3)
+        fl = 2.0 * m * n * k
+        od = torch.float32 if epi == "residual" else torch.bfloat16
+        out = torch.empty((m, n), dtype=od, device=DEV)
+        res = out if epi == "residual" else None
+        for cg in (1, 2):
+            med, best = timeit(lambda: ops.gemm_bf16(a, w, bias, epilogue=epi, residual=res, out=out, cta_group=cg))
+            print(f"gemm cg={cg} M={m} N={n} K={k} {epi}: median {med:.3f} ms  {fl / med / 1e9:.1f} TFLOP/s (best {fl / best / 1e9:.1f})", flush=True)
+        med, best = timeit(lambda: torch.matmul(a, w.T))
+        print(f"cuBLAS          M={m} N={n} K={k}: median {med:.3f} ms  {fl / med / 1e9:.1f} TFLOP/s (best {fl / best / 1e9:.1f})", flush=True)
+        del a, w, out
+    t, d, h = 131072, 1024, 16
+    x = rnd((t, d), 1.0, 1)
+    g, b = 1 + rnd((d,), 0.1, 2), rnd((d,), 0.1, 3)
+    med, _ = timeit(lambda: ops.layernorm(x, g, b))
+    print(f"layernorm T={t}: {med:.3f} ms  {t * d * 6 / med / 1e6:.0f} GB/s")
+    qkv = rnd((t, 3 * d), 1.0, 5, torch.bfloat16)
+    cu = ops.cu_seqlens_of([128] * (t // 128)).to(DEV)
+    med, _ = timeit(lambda: ops.attention(qkv, cu, 128, h))
+    print(f"attention T={t} S=128: {med:.3f} ms  {t * d * 8 / med / 1e6:.0f} GB/s  {4.0 * t * 128 * d / med / 1e9:.1f} TFLOP/s")
+
+
+def stage_encoder():
+    from oracle.text_encoder import OracleEncoderConfig, OracleTextEncoder, make_synthetic_state_dict
+    from sonar_b200 import B200TextEncoderModel, PaddingMask, SequenceBatch, VocabularyInfo, sonar_text_encoder_config
+    from tests.helpers import parity_metrics
+
+    V = 4096
+    for layers in (1, 4):
+        ocfg = OracleEncoderConfig(vocab_size=V, num_layers=layers)
+        sd = make_synthetic_state_dict(ocfg, seed=1)
+        cfg = sonar_text_encoder_config("basic", num_encoder_layers=layers,
+                                        vocab_info=VocabularyInfo(size=V, unk_idx=1, bos_idx=2, eos_idx=3, pad_idx=1))
+        model = B200TextEncoderModel(cfg, sd, DEV)
+        oracle = OracleTextEncoder(ocfg, sd)
+        lens = [64, 1, 17, 33, 48, 5, 63, 31]
+        g = torch.Generator().manual_seed(0)
+        ids = torch.zeros((len(lens), 64), dtype=torch.int64)
+        for i, n in enumerate(lens):
+            ids[i, :n] = torch.randint(4, V, (n,), generator=g)
+        ref, _ = oracle(ids, torch.tensor(lens))
+        out = model(SequenceBatch(ids.to(DEV), PaddingMask(torch.tensor(lens), 64, lens))).sentence_embeddings
+        torch.cuda.synchronize()
+        print(f"encoder {layers} layers:", parity_metrics(out, ref), flush=True)
+
+
+if __name__ == "__main__":
+    stage = sys.argv[1]
+    t0 = time.time()
+    print(f"== stage {stage} on {torch.cuda.get_device_name(0)}", flush=True)
+    {"elementwise": stage_elementwise, "gemm1": lambda: stage_gemm(1), "gemm2": lambda: stage_gemm(2),
+     "perf": stage_perf, "encoder": stage_encoder}[stage]()
+    torch.cuda.synchronize()
+    print(f"== stage {stage} done in {time.time() - t0:.1f}s", flush=True)

@@ -1,0 +1,16 @@
+"""sonar_b200 -- B200-native (sm_100a) engine behind the SONAR ``inference_pipelines`` API.
+
+Only the text-embedding hot path lives here: host batcher + pipeline mirror
+in Python, all arithmetic in ``lib/libsonar_b200.so`` (``include/sonar_b200.h``).
+"""
+
+__version__ = "0.1.0"
+
+from .sequence import PaddingMask, SequenceBatch, SonarEncoderOutput  # noqa: F401
+from .text_encoder import (  # noqa: F401
+    B200TextEncoderModel,
+    Pooling,
+    SonarTextEncoderConfig,
+    VocabularyInfo,
+    sonar_text_encoder_config,
+)

@@ -1,0 +1,382 @@
+// bf16 x bf16 -> fp32-accumulate GEMM on the 5th-gen tensor cores (tcgen05 + TMEM),
+// fed by TMA, warp-specialised, persistent.  C = epi(A[M,K] · W[N,K]^T + bias[N]).
+//
+// This is the contraction behind every `F.linear` of the SONAR text encoder layer
+// (reference wiring: sonar/models/sonar_text/factory.py:130-153 -- q/k/v/out
+// projections and the 1024->8192->1024 ReLU FFN; nn.Linear weight layout [out,in]).
+//
+// Tile shape per CTA pair (cta_group::2): 256(M) x 256(N) x 64(K) per pipeline stage,
+//   CTA r loads A rows [128r,128r+128) and W rows [128r,128r+128) of the tile;
+//   one tcgen05.mma.cta_group::2 (M=256,N=256,K=16) x4 per stage, issued by ONE thread
+//   of the leader CTA; each CTA's TMEM holds its 128 rows x 256 fp32 columns, double
+//   buffered (2 x 256 = all 512 columns) so the epilogue of tile i overlaps the
+//   mainloop of tile i+1.  cta_group::1 variant: 128 x 256 x 64 per CTA.
+// Warp roles (256 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM alloc/dealloc,
+//   w3 idle, w4-7 epilogue (TMEM -> regs -> bias/ReLU/residual -> swizzled smem -> TMA store).
+// Operand smem layout: K-major, 128-byte rows, SWIZZLE_128B (TMA writes it, UMMA reads it).
+
+#include "common.cuh"
+#include "sonar_b200_internal.h"
+
+namespace sb {
+
+template <int kCtaGroup>
+struct GemmCfg {
+  static constexpr int BLOCK_M = 128;                 // rows per CTA
+  static constexpr int BLOCK_N = 256;                 // UMMA N
+  static constexpr int BLOCK_K = 64;                  // 128 bytes of bf16 = one swizzle atom
+  static constexpr int LOAD_N = BLOCK_N / kCtaGroup;  // W rows each CTA stages
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = LOAD_N * BLOCK_K * 2;
+  static constexpr int STAGES = (kCtaGroup == 2) ? 6 : 4;
+  static constexpr int CD_STAGE_BYTES = 128 * 128;  // 128 rows x 128 B
+  static constexpr int CD_STAGES = 2;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES =
+      STAGES * (A_BYTES + B_BYTES) + CD_STAGES * CD_STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int THREADS = 256;
+};
+
+template <int kCtaGroup, int kEpi, typename OutT>
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                         const __grid_constant__ CUtensorMap tm_c, const float* __restrict__ bias,
+                         const OutT* residual, long long ldr, int M, int N, int K) {
+  using Cfg = GemmCfg<kCtaGroup>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + Cfg::STAGES * Cfg::A_BYTES;
+  uint8_t* smem_cd = smem_b + Cfg::STAGES * Cfg::B_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_cd + Cfg::CD_STAGES * Cfg::CD_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = (cta_rank == 0);
+
+  if (kCtaGroup == 2) cluster_sync_all();  // both CTAs resident before the paired TMEM allocation
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_c);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);   // leader's arrive.expect_tx (+ TMA bytes of both CTAs)
+      mbar_init(&empty_bar[i], 1);  // one tcgen05.commit (multicast to both CTAs)
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);               // one tcgen05.commit
+      mbar_init(&tmem_empty_bar[i], 4 * kCtaGroup);  // one arrive per epilogue warp of every CTA
+    }
+    fence_mbar_init();
+  }
+  if (warp_idx == 2) tmem_alloc<kCtaGroup>(tmem_ptr_smem, Cfg::TMEM_COLS);
+  tc_fence_before();
+  if (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int tile_m = Cfg::BLOCK_M * kCtaGroup;
+  const int num_m_tiles = (M + tile_m - 1) / tile_m;
+  const int num_n_tiles = N / Cfg::BLOCK_N;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int num_kb = K / Cfg::BLOCK_K;
+  const int cluster_id = blockIdx.x / kCtaGroup;
+  const int num_clusters = gridDim.x / kCtaGroup;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
+        const int m0 = m_blk * tile_m + int(cta_rank) * Cfg::BLOCK_M;
+        const int n0 = n_blk * Cfg::BLOCK_N + int(cta_rank) * Cfg::LOAD_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], (Cfg::A_BYTES + Cfg::B_BYTES) * kCtaGroup);
+          if (kCtaGroup == 2) {
+            tma_load_2d_cta2(smem_a + stage * Cfg::A_BYTES, &tm_a, &full_bar[stage], kb * Cfg::BLOCK_K, m0);
+            tma_load_2d_cta2(smem_b + stage * Cfg::B_BYTES, &tm_b, &full_bar[stage], kb * Cfg::BLOCK_K, n0);
+          } else {
+            tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tm_a, &full_bar[stage], kb * Cfg::BLOCK_K, m0);
+            tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tm_b, &full_bar[stage], kb * Cfg::BLOCK_K, n0);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    if (is_leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(Cfg::BLOCK_M * kCtaGroup, Cfg::BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t iter = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
+        const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);  // TMA bytes of both CTAs have landed
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES));
+          const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < Cfg::BLOCK_K / 16; ++k) {
+            // +32 bytes (= 16 bf16) along K inside the 128B swizzle atom -> +2 in the >>4 address field
+            umma_bf16<kCtaGroup>(d_tmem, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc,
+                                 (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit<kCtaGroup>(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (kb == num_kb - 1) umma_commit<kCtaGroup>(&tmem_full_bar[acc]);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp_idx >= 4) {
+    // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
+    const int ew = warp_idx - 4;          // == warp_idx % 4 -> TMEM lane quarter
+    const int row_in_tile = ew * 32 + lane;
+    constexpr int CHUNK_COLS = 128 / int(sizeof(OutT));  // one 128-byte smem row per output row
+    constexpr int NUM_CHUNKS = Cfg::BLOCK_N / CHUNK_COLS;
+    constexpr int SUBS = CHUNK_COLS / 32;
+    uint32_t iter = 0;
+    int cd_stage = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
+      const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
+      const int m0 = m_blk * tile_m + int(cta_rank) * Cfg::BLOCK_M;
+      const int n0 = n_blk * Cfg::BLOCK_N;
+      const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int grow = m0 + row_in_tile;
+#pragma unroll 1
+      for (int c = 0; c < NUM_CHUNKS; ++c) {
+        if (ew == 0 && lane == 0) tma_store_wait_read<Cfg::CD_STAGES - 1>();  // staging buffer free again
+        named_bar_sync(1, 128);
+        uint8_t* cd_row = smem_cd + cd_stage * Cfg::CD_STAGE_BYTES + row_in_tile * 128;
+#pragma unroll
+        for (int s = 0; s < SUBS; ++s) {
+          uint32_t v[32];
+          const int col_in_tile = c * CHUNK_COLS + s * 32;
+          tmem_ld_32x32(tmem_base + (uint32_t(ew * 32) << 16) + acc * Cfg::BLOCK_N + col_in_tile, v);
+          tmem_ld_wait();
+          const int gcol = n0 + col_in_tile;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + gcol + j));
+            f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
+            f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+            f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+          }
+          if constexpr (kEpi == EPI_BIAS_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
+          if constexpr (kEpi == EPI_BIAS_RESIDUAL) {
+            if (grow < M) {
+              const OutT* rp = residual + (long long)grow * ldr + gcol;
+              if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 r4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rp) + j);
+                  f[j + 0] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  const uint4 r8 = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(rp) + j);
+                  const uint32_t w[4] = {r8.x, r8.y, r8.z, r8.w};
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+                    f[j + 2 * q] += __low2float(p);
+                    f[j + 2 * q + 1] += __high2float(p);
+                  }
+                }
+              }
+            }
+          }
+          // 128B-swizzled staging row: logical 16B chunk j lives at physical chunk j ^ (row % 8)
+          if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int phys = q ^ (row_in_tile & 7);
+              *reinterpret_cast<float4*>(cd_row + phys * 16) =
+                  make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int phys = (s * 4 + q) ^ (row_in_tile & 7);
+              *reinterpret_cast<uint4*>(cd_row + phys * 16) =
+                  make_uint4(pack_bf16x2(f[8 * q], f[8 * q + 1]), pack_bf16x2(f[8 * q + 2], f[8 * q + 3]),
+                             pack_bf16x2(f[8 * q + 4], f[8 * q + 5]), pack_bf16x2(f[8 * q + 6], f[8 * q + 7]));
+            }
+          }
+        }
+        if (c == NUM_CHUNKS - 1) {
+          // all TMEM reads of this accumulator are complete -> hand it back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (kCtaGroup == 2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+            else mbar_arrive(&tmem_empty_bar[acc]);
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (ew == 0 && lane == 0) {
+          tma_store_2d(&tm_c, smem_cd + cd_stage * Cfg::CD_STAGE_BYTES, n0 + c * CHUNK_COLS, m0);
+          tma_store_commit();
+        }
+        cd_stage ^= 1;
+      }
+    }
+    if (ew == 0 && lane == 0) tma_store_wait_all<0>();
+  }
+
+  // ===================== teardown =====================
+  tc_fence_before();
+  if (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
+  if (warp_idx == 2) tmem_dealloc<kCtaGroup>(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ----------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess || !p) {
+      set_last_error("cuTensorMapEncodeTiled driver entry point not available");
+      return nullptr;
+    }
+    fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major tensor [rows, cols] with leading dimension ld (elements); box = [box_rows, box_cols];
+// inner box extent must be exactly 128 bytes (SWIZZLE_128B).
+int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld,
+                 int box_rows, int box_cols) {
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  if (!enc) return -3;
+  CUtensorMapDataType dt = (elem_bytes == 2) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (cuuint64_t)elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  if (box_cols * elem_bytes != 128) {
+    set_last_error("make_tmap_2d: inner box must span 128 bytes");
+    return -1;
+  }
+  CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld elem=%d)", (int)r,
+                   rows, cols, ld, elem_bytes);
+    return -3;
+  }
+  return 0;
+}
+
+template <int kCtaGroup, int kEpi, typename OutT>
+static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const float* bias,
+                       const void* residual, long long ldr, int M, int N, int K, int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<kCtaGroup>;
+  auto kern = gemm_bf16_tcgen05_kernel<kCtaGroup, kEpi, OutT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tile_m = Cfg::BLOCK_M * kCtaGroup;
+  const long long num_tiles = (long long)((M + tile_m - 1) / tile_m) * (N / Cfg::BLOCK_N);
+  long long clusters = num_sms / kCtaGroup;
+  if (clusters > num_tiles) clusters = num_tiles;
+  if (clusters < 1) clusters = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * kCtaGroup), 1, 1);
+  cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtaGroup;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, bias, reinterpret_cast<const OutT*>(residual), ldr, M, N, K));
+  return 0;
+}
+
+int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
+  if (g.M <= 0) return 0;
+  if (g.N % 256 != 0 || g.K % 64 != 0 || g.K <= 0 || g.N <= 0) {
+    set_last_error("gemm_bf16: need N %% 256 == 0 and K %% 64 == 0 (got M=%d N=%d K=%d)", g.M, g.N, g.K);
+    return -1;
+  }
+  if (g.epi == EPI_BIAS_RESIDUAL && !g.residual) {
+    set_last_error("gemm_bf16: residual epilogue without residual pointer");
+    return -1;
+  }
+  if (!g.bias) {
+    set_last_error("gemm_bf16: bias pointer is required");
+    return -1;
+  }
+  const int cg = (g.cta_group == 1) ? 1 : 2;
+  const int out_bytes = g.out_fp32 ? 4 : 2;
+  CUtensorMap ta, tb, tc;
+  int rc;
+  if ((rc = make_tmap_2d(&ta, g.A, 2, g.M, g.K, g.lda, 128, 64))) return rc;
+  if ((rc = make_tmap_2d(&tb, g.W, 2, g.N, g.K, g.ldw, 256 / cg, 64))) return rc;
+  if ((rc = make_tmap_2d(&tc, g.C, out_bytes, g.M, g.N, g.ldc, 128, 128 / out_bytes))) return rc;
+  const int sms = g.num_sms > 0 ? g.num_sms : 148;
+
+#define SB_DISPATCH(CG, EPI, T) \
+  return launch_inst<CG, EPI, T>(ta, tb, tc, g.bias, g.residual, g.ldr, g.M, g.N, g.K, sms, stream)
+#define SB_DISPATCH_EPI(CG, T)                                              \
+  switch (g.epi) {                                                          \
+    case EPI_BIAS: SB_DISPATCH(CG, EPI_BIAS, T);                            \
+    case EPI_BIAS_RELU: SB_DISPATCH(CG, EPI_BIAS_RELU, T);                  \
+    case EPI_BIAS_RESIDUAL: SB_DISPATCH(CG, EPI_BIAS_RESIDUAL, T);          \
+    default: set_last_error("gemm_bf16: bad epilogue %d", g.epi); return -1; \
+  }
+  if (cg == 2) {
+    if (g.out_fp32) { SB_DISPATCH_EPI(2, float) } else { SB_DISPATCH_EPI(2, __nv_bfloat16) }
+  } else {
+    if (g.out_fp32) { SB_DISPATCH_EPI(1, float) } else { SB_DISPATCH_EPI(1, __nv_bfloat16) }
+  }
+#undef SB_DISPATCH
+#undef SB_DISPATCH_EPI
+  return -1;
+}
+
+}  // namespace sb

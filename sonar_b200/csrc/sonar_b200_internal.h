@@ -1,0 +1,58 @@
+// Internal (C++) interfaces shared by the sonar_b200 CUDA translation units.
+// The public C ABI is include/sonar_b200.h.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb {
+
+enum EpiMode { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_RESIDUAL = 2 };
+enum PoolMode { POOL_MAX = 1, POOL_MEAN = 2, POOL_LAST = 3 };  // = reference `Pooling` enum values (model.py:23-27)
+
+void set_last_error(const char* fmt, ...);
+
+struct GemmArgs {
+  const __nv_bfloat16* A;  // [M,K] row-major, ld = lda
+  long long lda;
+  const __nv_bfloat16* W;  // [N,K] row-major (nn.Linear layout), ld = ldw
+  long long ldw;
+  void* C;  // [M,N] bf16 or fp32
+  long long ldc;
+  int out_fp32;
+  const float* bias;     // [N] fp32
+  const void* residual;  // [M,N] same dtype as C (may alias C), ld = ldr
+  long long ldr;
+  int M, N, K;
+  int epi;        // EpiMode
+  int cta_group;  // 1 or 2
+  int num_sms;    // 0 -> 148
+};
+
+int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
+
+int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld,
+                 int box_rows, int box_cols);
+
+// x[cu[b]+t, :] = E[ids[b,t], :] * scale + pos[t, :]   (fp32 out)
+int embed_tokens(const int64_t* ids, long long ids_stride, const int32_t* cu_seqlens, int B, int S,
+                 const __nv_bfloat16* embed, long long vocab, const float* pos_table, int pos_rows, int D, float scale,
+                 float* x, int* err_flag, cudaStream_t stream);
+
+// y = LN(x) * gamma + beta, fp32 in, bf16 out, one warp per row
+int layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, __nv_bfloat16* y, long long T,
+                   int D, cudaStream_t stream);
+
+// softmax(q k^T / sqrt(64)) v over packed sequences; qkv [T, 3*D] bf16 (q | k | v), out [T, D] bf16
+int attention_packed(const __nv_bfloat16* qkv, const int32_t* cu_seqlens, int B, int max_len, int H,
+                     __nv_bfloat16* out, cudaStream_t stream);
+
+// optional final LayerNorm + pooling over packed sequences -> out [B, D] fp32;
+// optionally also scatters the (normalised) rows to a padded [B, S, D] fp32 tensor.
+int ln_pool(const float* x, const int32_t* cu_seqlens, int B, int D, const float* gamma, const float* beta,
+            float eps, int apply_ln, int pool_mode, float* out, float* encoded_padded, int S_padded,
+            cudaStream_t stream);
+
+}  // namespace sb

@@ -1,0 +1,184 @@
+"""Drop-in mirror of ``sonar.inference_pipelines.text.TextToEmbeddingModelPipeline``
+(``/root/reference/sonar/inference_pipelines/text.py:140-269``): same constructor and
+``predict`` signature, same argument validation, truncation warning, length-sorted
+dynamic bucketing and output-order restoration -- with the model stage running on the
+B200 engine (``sonar_b200.text_encoder.B200TextEncoderModel``).
+"""
+
+from __future__ import annotations
+
+import os
+import warnings
+from pathlib import Path
+from typing import Dict, Iterable, Iterator, List, Optional, Sequence, Union, cast
+
+import torch
+from torch import Tensor
+
+from ..batching import collate, dynamic_bucket, prefetch, to_sequence_batch
+from ..text_encoder import B200TextEncoderModel, sonar_text_encoder_config
+from .utils import add_progress_bar
+
+Device = Union[str, torch.device]
+CPU = torch.device("cpu")
+
+
+class precision_context:
+    """Same behaviour as the reference context manager (``text.py:36-54``): maps the model
+    dtype to ``torch.set_float32_matmul_precision``.  It has no effect on the sm_100a
+    kernels (bf16 operands, fp32 accumulate) and is kept for API fidelity."""
+
+    dtype_to_precision: Dict[torch.dtype, str] = {
+        torch.bfloat16: "medium",
+        torch.float16: "medium",
+        torch.float32: "high",
+        torch.float64: "highest",
+    }
+
+    def __init__(self, dtype: torch.dtype):
+        self.precision = self.dtype_to_precision.get(dtype, "high")
+
+    def __enter__(self):
+        self.original_precision = torch.get_float32_matmul_precision()
+        if self.precision:
+            torch.set_float32_matmul_precision(self.precision)
+
+    def __exit__(self, exc_type, exc_value, traceback):
+        torch.set_float32_matmul_precision(self.original_precision)
+
+
+def _load_encoder_card(name: str, device: Device) -> B200TextEncoderModel:
+    """Resolve a reference card name (e.g. ``text_sonar_basic_encoder``,
+    ``sonar/cards/text_sonar_basic_encoder.yaml``) to a local fairseq2-layout checkpoint
+    ``$SONAR_B200_CHECKPOINT_DIR/<name>.pt``.  There is no downloader (no network)."""
+    root = os.environ.get("SONAR_B200_CHECKPOINT_DIR")
+    if not root or not (Path(root) / f"{name}.pt").exists():
+        raise FileNotFoundError(
+            f"encoder card {name!r}: set SONAR_B200_CHECKPOINT_DIR to a directory holding {name}.pt "
+            "(fairseq2 state dict under the key 'model'), or pass a B200TextEncoderModel object")
+    arch = "basic"
+    return B200TextEncoderModel.from_checkpoint(Path(root) / f"{name}.pt", sonar_text_encoder_config(arch), device)
+
+
+def _read_text(path: Path) -> Iterator[str]:
+    """``fairseq2.data.text.read_text`` default behaviour: one example per line, line
+    terminators stripped."""
+    with open(path, "r", encoding="utf-8") as f:
+        for line in f:
+            yield line.rstrip("\r\n")
+
+
+class TextToEmbeddingModelPipeline(torch.nn.Module):
+    model: B200TextEncoderModel
+
+    def __init__(
+        self,
+        encoder: Union[str, B200TextEncoderModel],
+        tokenizer,
+        device: Device = CPU,
+        dtype: Optional[torch.dtype] = None,
+    ) -> None:
+        """
+        Args:
+            encoder: card name or model object exposing the reference encoder seam
+                (``.eval()``, ``.dtype``, ``.encoder_frontend.pos_encoder.max_seq_len``,
+                ``__call__(SequenceBatch) -> .sentence_embeddings``)
+            tokenizer: tokenizer object (``create_encoder(lang=, device=)``, ``vocab_info.pad_idx``)
+            device: device the token batches are sent to.  The engine itself is CUDA-only: with the
+                reference's default (CPU) the batches are staged on the host and the model moves them.
+            dtype: dtype of the returned embeddings (default: float32)
+        """
+        super().__init__()
+        if isinstance(encoder, str):
+            encoder = _load_encoder_card(encoder, device if torch.device(device).type == "cuda" else "cuda")
+        if isinstance(tokenizer, str):
+            raise FileNotFoundError(
+                f"tokenizer card {tokenizer!r} cannot be resolved offline; pass a tokenizer object "
+                "(sonar_b200.tokenizer.NllbTokenizer / SyntheticTokenizer)")
+        self.tokenizer = tokenizer
+        self.model = encoder.eval()  # type: ignore
+        self.device = torch.device(device)
+        self.dtype = dtype
+
+    @torch.inference_mode()
+    def predict(
+        self,
+        input: Union[Path, Sequence[str]],
+        source_lang: str,
+        batch_size: Optional[int] = 5,
+        batch_max_tokens: Optional[int] = None,
+        max_seq_len: Optional[int] = None,
+        progress_bar: bool = False,
+        target_device: Optional[Device] = None,
+    ) -> Tensor:
+        """
+        Transform the input texts (from a list of strings or from a text file) into a matrix of their embeddings.
+        The texts are truncated to `max_seq_len` tokens,
+        or, if it is not specified, to the maximum that the model supports.
+        """
+        if batch_max_tokens is None and batch_size is None:
+            raise ValueError("at least one of `batch_size` or `batch_max_tokens` should be provided")
+        if batch_max_tokens is not None and batch_max_tokens <= 0:
+            raise ValueError("`batch_max_tokens` should be strictly positive")
+        if batch_size is not None and batch_size <= 0:
+            raise ValueError("`batch_size` should be strictly positive")
+
+        tokenizer_encoder = self.tokenizer.create_encoder(lang=source_lang, device=self.device)
+        model_max_len = cast(Optional[int], self.model.encoder_frontend.pos_encoder.max_seq_len)
+        if max_seq_len is None:
+            max_seq_len = model_max_len
+        if max_seq_len is not None and model_max_len is not None:
+            if max_seq_len > model_max_len:
+                raise ValueError(
+                    f"max_seq_len cannot be larger than max_seq_len of the encoder model: {model_max_len}")
+
+        n_truncated = 0
+
+        def truncate(x: Tensor) -> Tensor:
+            if max_seq_len is None:
+                return x
+            if x.shape[0] > max_seq_len:
+                nonlocal n_truncated
+                n_truncated += 1
+            return x[:max_seq_len]
+
+        if isinstance(input, (str, Path)):
+            source: Iterable[str] = _read_text(Path(input))
+            sorting_index = None
+        else:
+            # so it should a list
+            sorting_index = torch.argsort(torch.tensor(list(map(len, input))))
+            source = (input[int(i)] for i in sorting_index.tolist())
+
+        pad_idx = self.tokenizer.vocab_info.pad_idx
+        on_cuda = self.device.type == "cuda"
+
+        def batches():
+            tokens = (truncate(tokenizer_encoder(s)) for s in source)
+            for group in dynamic_bucket(tokens, batch_max_tokens or 2**31, len, min_num_examples=1,
+                                        max_num_examples=batch_size or 20_000, drop_remainder=False):
+                ids, lens, ragged = collate(group, pad_idx, pin_memory=True)
+                yield to_sequence_batch(ids, lens, ragged, self.device if on_cuda else CPU)
+
+        out_device = torch.device(target_device) if target_device is not None else self.device
+        pipeline: Iterable = (self.model(b).sentence_embeddings.to(out_device) for b in prefetch(batches(), 2))
+        if progress_bar:
+            pipeline = add_progress_bar(pipeline, inputs=input,
+                                        batch_size=batch_size if batch_max_tokens is None else None)
+
+        with precision_context(self.model.dtype):
+            results: List[Tensor] = list(iter(pipeline))
+
+        if n_truncated:
+            warnings.warn(
+                f"For {n_truncated} input tensors for SONAR text encoder, "
+                f"the length was truncated to {max_seq_len} elements.")
+
+        sentence_embeddings = torch.cat(results, dim=0)
+        if self.dtype is not None:
+            sentence_embeddings = sentence_embeddings.to(self.dtype)
+
+        if sorting_index is not None:
+            reversed_index = torch.argsort(sorting_index)
+            sentence_embeddings = sentence_embeddings[reversed_index.to(sentence_embeddings.device)]
+        return sentence_embeddings

@@ -1,0 +1,90 @@
+"""Tokenizers with the surface the pipelines use (``sonar/inference_pipelines/text.py:199-201,241``):
+``tokenizer.create_encoder(lang=..., device=...) -> callable(str) -> int64[len]`` and
+``tokenizer.vocab_info.pad_idx``.
+
+* ``NllbTokenizer`` wraps a SentencePiece model in the NLLB layout the SONAR cards use
+  (``tokenizer_family: nllb``; ids pad=0 unk=1 bos=2 eos=3, then pieces, then the
+  ``__lang__`` control symbols; source encoding ``[__lang__] + pieces + [</s>]``;
+  SURVEY App. F1).  Needs the ``sentencepiece.bpe.model`` file, which is not available
+  offline; the class exists so real checkpoints work wherever the files do.
+* ``SyntheticTokenizer`` is a dependency-free stand-in (hashes whitespace words into the
+  piece id range) for tests and benchmarks: same control-token layout, deterministic.
+"""
+
+from __future__ import annotations
+
+import zlib
+from typing import Callable, List, Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from .text_encoder import VocabularyInfo
+
+# FLORES-200 language codes in NLLB dictionary order are only needed with a real SPM
+# model; the synthetic tokenizer derives a stable id for any code.
+_NUM_LANG_SLOTS = 202
+
+
+class _TokenEncoder:
+    def __init__(self, fn: Callable[[str], List[int]]) -> None:
+        self._fn = fn
+
+    def __call__(self, text: str) -> Tensor:
+        return torch.tensor(self._fn(text), dtype=torch.int64)
+
+
+class SyntheticTokenizer:
+    """Deterministic word-hash tokenizer with the NLLB id layout (test/bench utility)."""
+
+    def __init__(self, vocab_size: int = 256206, pieces_per_word: int = 1) -> None:
+        if vocab_size < 4 + _NUM_LANG_SLOTS + 8:
+            raise ValueError("vocab too small for the NLLB control-token layout")
+        self.vocab_info = VocabularyInfo(size=vocab_size, unk_idx=1, bos_idx=2, eos_idx=3, pad_idx=0)
+        self._lang_base = vocab_size - _NUM_LANG_SLOTS - 3
+        self._num_pieces = self._lang_base - 4
+        self._ppw = pieces_per_word
+
+    def lang_id(self, lang: str) -> int:
+        return self._lang_base + zlib.crc32(lang.encode("utf-8")) % _NUM_LANG_SLOTS
+
+    def _encode(self, text: str, lang: str) -> List[int]:
+        ids = [self.lang_id(lang)]
+        for w in text.split():
+            for k in range(self._ppw):
+                ids.append(4 + zlib.crc32(f"{k}:{w}".encode("utf-8")) % self._num_pieces)
+        ids.append(self.vocab_info.eos_idx)
+        return ids
+
+    def create_encoder(self, *, task: Optional[str] = None, lang: Optional[str] = None, mode: Optional[str] = None,
+                       device=None, pin_memory: bool = False) -> _TokenEncoder:
+        if lang is None:
+            raise ValueError("`lang` is required")
+        return _TokenEncoder(lambda text: self._encode(text, lang))
+
+
+class NllbTokenizer:
+    """SentencePiece-backed NLLB tokenizer (source mode), ids as in fairseq2's NLLB family."""
+
+    def __init__(self, spm_path: str, langs: Sequence[str], extra_control: Sequence[str] = ("<MINED_DATA>", "<MMT_BT_DATA>", "<SMT_BT_DATA>")) -> None:
+        import sentencepiece as spm  # local import: optional dependency
+
+        self._sp = spm.SentencePieceProcessor(model_file=str(spm_path))
+        n = self._sp.get_piece_size()
+        # fairseq2 appends the control symbols after the SPM pieces (and remaps pad/unk/bos/eos to 0..3)
+        self._lang_ids = {f"__{l}__": n + 1 + i for i, l in enumerate(langs)}
+        size = n + 1 + len(langs) + len(extra_control)
+        self.vocab_info = VocabularyInfo(size=size, unk_idx=1, bos_idx=2, eos_idx=3, pad_idx=0)
+
+    def create_encoder(self, *, task: Optional[str] = None, lang: Optional[str] = None, mode: Optional[str] = None,
+                       device=None, pin_memory: bool = False) -> _TokenEncoder:
+        if lang is None or f"__{lang}__" not in self._lang_ids:
+            raise ValueError(f"`lang` must be one of the tokenizer's languages, got {lang!r}")
+        lang_id = self._lang_ids[f"__{lang}__"]
+        sp = self._sp
+
+        def enc(text: str) -> List[int]:
+            # SPM ids: <unk>=0,<s>=1,</s>=2 then pieces; NLLB/fairseq2 ids: pad0 unk1 bos2 eos3 then pieces (+1)
+            return [lang_id] + [i + 1 for i in sp.encode(text)] + [3]
+
+        return _TokenEncoder(enc)

@@ -1,0 +1,187 @@
+"""Kernel-level parity tests (through the C ABI) against plain fp32 torch references of the
+same op on the same bf16-rounded inputs.  Tolerances are written next to each check."""
+
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(native_lib, cuda_device):
+    from sonar_b200 import ops as _ops
+
+    torch.cuda.set_device(cuda_device)
+    return _ops
+
+
+def _rand(shape, scale, seed, device, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(device=device, dtype=dtype)
+
+
+GEMM_SHAPES = [
+    (128, 256, 64),      # one tile, one k-block
+    (256, 256, 128),     # one paired tile
+    (300, 512, 192),     # M tail inside a tile
+    (1000, 1024, 1024),  # out-proj shape, ragged M
+    (2048, 3072, 1024),  # QKV shape
+    (777, 1024, 8192),   # FFN2 shape (long K), odd M
+    (4096, 8192, 1024),  # FFN1 shape: > 148 tiles -> persistent loop + both TMEM stages
+    (1, 256, 64),        # single row
+]
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
+def test_gemm_bias_bf16(ops, cuda_device, cta_group, m, n, k):
+    a = _rand((m, k), 1.0, 1, cuda_device, torch.bfloat16)
+    w = _rand((n, k), 1.0 / math.sqrt(k), 2, cuda_device, torch.bfloat16)
+    bias = _rand((n,), 0.5, 3, cuda_device)
+    out = ops.gemm_bf16(a, w, bias, epilogue="bias", cta_group=cta_group)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().T + bias
+    # fp32 accumulate; output rounded to bf16 (rel 2^-9) -> allow 1.5 bf16 ulps of |ref| + small abs
+    err = (out.float() - ref).abs()
+    tol = ref.abs() * (1.5 * 2 ** -8) + 2e-2
+    assert bool((err <= tol).all()), f"max err {err.max().item()} at {err.argmax().item()}"
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gemm_relu_bf16(ops, cuda_device, cta_group):
+    m, n, k = 1536, 2048, 1024
+    a = _rand((m, k), 1.0, 4, cuda_device, torch.bfloat16)
+    w = _rand((n, k), 1.0 / math.sqrt(k), 5, cuda_device, torch.bfloat16)
+    bias = _rand((n,), 0.5, 6, cuda_device)
+    out = ops.gemm_bf16(a, w, bias, epilogue="relu", cta_group=cta_group)
+    ref = torch.relu(a.float() @ w.float().T + bias)
+    err = (out.float() - ref).abs()
+    assert bool((err <= ref.abs() * (1.5 * 2 ** -8) + 2e-2).all()), err.max().item()
+    assert float(out.float().min()) >= 0.0
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("m,n,k", [(515, 1024, 1024), (2000, 1024, 8192)])
+def test_gemm_residual_fp32_inplace(ops, cuda_device, cta_group, m, n, k):
+    a = _rand((m, k), 1.0, 7, cuda_device, torch.bfloat16)
+    w = _rand((n, k), 1.0 / math.sqrt(k), 8, cuda_device, torch.bfloat16)
+    bias = _rand((n,), 0.5, 9, cuda_device)
+    x = _rand((m, n), 2.0, 10, cuda_device)
+    ref = x + a.float() @ w.float().T + bias
+    out = ops.gemm_bf16(a, w, bias, epilogue="residual", residual=x, out=x, cta_group=cta_group)  # x += ...
+    assert out.data_ptr() == x.data_ptr()
+    # fp32 output: only accumulation-order differences remain
+    torch.testing.assert_close(x, ref, rtol=1e-4, atol=2e-3)
+
+
+def test_gemm_rejects_bad_shapes(ops, cuda_device):
+    a = torch.zeros((8, 64), dtype=torch.bfloat16, device=cuda_device)
+    w = torch.zeros((100, 64), dtype=torch.bfloat16, device=cuda_device)
+    with pytest.raises(ValueError):
+        ops.gemm_bf16(a, w, torch.zeros(100, device=cuda_device))
+
+
+@pytest.mark.parametrize("t,d", [(1, 1024), (37, 1024), (4096, 1024), (100, 256)])
+def test_layernorm(ops, cuda_device, t, d):
+    x = _rand((t, d), 3.0, 11, cuda_device) + 0.7
+    g = 1.0 + _rand((d,), 0.1, 12, cuda_device)
+    b = _rand((d,), 0.1, 13, cuda_device)
+    y = ops.layernorm(x, g, b, 1e-5)
+    ref = torch.nn.functional.layer_norm(x, (d,), g, b, 1e-5)
+    # bf16 output rounding: half ulp = 2^-9 relative
+    assert bool(((y.float() - ref).abs() <= ref.abs() * 2 ** -8 + 1e-5).all())
+
+
+@pytest.mark.parametrize("lens", [[128] * 4, [1, 2, 17, 64, 65, 128], [200, 129, 514], [33]])
+def test_attention_vs_sdpa(ops, cuda_device, lens):
+    h, hd = 16, 64
+    d = h * hd
+    t = sum(lens)
+    qkv = _rand((t, 3 * d), 1.0, 14, cuda_device, torch.bfloat16)
+    cu = ops.cu_seqlens_of(lens).to(cuda_device)
+    out = ops.attention(qkv, cu, max(lens), h)
+    torch.cuda.synchronize()
+    start = 0
+    for n in lens:
+        blk = qkv[start : start + n].float()
+        q, k, v = (blk[:, i * d : (i + 1) * d].view(n, h, hd).transpose(0, 1) for i in range(3))
+        ref = torch.nn.functional.scaled_dot_product_attention(q[None], k[None], v[None])[0]
+        ref = ref.transpose(0, 1).reshape(n, d)
+        got = out[start : start + n].float()
+        # P is rounded to bf16 before P.V and the output to bf16: ~2^-8 relative of |v|-scale values
+        torch.testing.assert_close(got, ref, rtol=2e-2, atol=2e-2)
+        start += n
+
+
+def test_embed(ops, cuda_device):
+    v, d, s = 1000, 1024, 20
+    lens = [20, 3, 11]
+    table = _rand((v, d), d ** -0.5, 15, cuda_device, torch.bfloat16)
+    pos = _rand((s + 2, d), 1.0, 16, cuda_device)
+    g = torch.Generator().manual_seed(17)
+    ids = torch.randint(0, v, (len(lens), s), generator=g).to(cuda_device)
+    cu = ops.cu_seqlens_of(lens).to(cuda_device)
+    x = ops.embed(ids, cu, table, pos, 32.0, sum(lens))
+    start = 0
+    for b, n in enumerate(lens):
+        ref = table[ids[b, :n]].float() * 32.0 + pos[:n]
+        torch.testing.assert_close(x[start : start + n], ref, rtol=1e-6, atol=1e-6)
+        start += n
+    bad = ids.clone()
+    bad[0, 0] = v
+    with pytest.raises(ValueError):
+        ops.embed(bad, cu, table, pos, 32.0, sum(lens))
+
+
+# ---- reference pooling KATs (tests/unit_tests/test_sonar_pooling.py:16-68) on the GPU kernel;
+#      the 2 feature columns are embedded in the first columns of a D=128 row ----
+def _kat(seqs, device):
+    n, s, f = seqs.shape
+    full = torch.zeros((n, s, 128), device=device)
+    full[:, :, :f] = seqs.to(device)
+    return full
+
+
+@pytest.mark.parametrize("mode,expected", [
+    ("MAX", [[7.0, 4.0], [-1.0, -2.0]]),
+    ("MEAN", [[5.0, 3.0], [-1.0, -2.0]]),
+    ("LAST", [[3.0, 4.0], [-1.0, -2.0]]),
+])
+def test_pooling_kat_with_mask(native_lib, cuda_device, mode, expected):
+    from sonar_b200 import B200TextEncoderModel, PaddingMask, Pooling
+
+    seqs = torch.tensor([[[7, 2], [3, 4], [10, 20]], [[-1, -2], [100, 1000], [-10, -20]]], dtype=torch.float32)
+    pm = PaddingMask(torch.tensor([2, 1]), batch_seq_len=3)
+    out = B200TextEncoderModel.static_pooling(_kat(seqs, cuda_device), pm, getattr(Pooling, mode))
+    torch.testing.assert_close(out[:, :2].cpu(), torch.tensor(expected))
+
+
+def test_pooling_kat_no_mask(native_lib, cuda_device):
+    from sonar_b200 import B200TextEncoderModel, Pooling
+
+    seqs = torch.tensor([[[7, 2], [3, 2], [2, 20]], [[-1, -3], [-4, 2], [-7, -2]]], dtype=torch.float32)
+    x = _kat(seqs, cuda_device)
+    pool = B200TextEncoderModel.static_pooling
+    torch.testing.assert_close(pool(x, None, Pooling.LAST)[:, :2].cpu(), torch.tensor([[2.0, 20], [-7, -2]]))
+    torch.testing.assert_close(pool(x, None, Pooling.MAX)[:, :2].cpu(), torch.tensor([[7.0, 20], [-1, 2]]))
+    torch.testing.assert_close(pool(x, None, Pooling.MEAN)[:, :2].cpu(), torch.tensor([[4.0, 8], [-4, -1]]))
+
+
+def test_ln_pool_matches_torch(ops, cuda_device):
+    d = 1024
+    lens = [5, 128, 1, 77]
+    x = _rand((sum(lens), d), 2.0, 18, cuda_device)
+    g = 1.0 + _rand((d,), 0.1, 19, cuda_device)
+    b = _rand((d,), 0.1, 20, cuda_device)
+    cu = ops.cu_seqlens_of(lens).to(cuda_device)
+    out, enc = ops.pool_packed(x, cu, "mean", gamma=g, beta=b, encoded_seq_len=128)
+    y = torch.nn.functional.layer_norm(x, (d,), g, b, 1e-5)
+    start = 0
+    for i, n in enumerate(lens):
+        ref = y[start : start + n].sum(0) * (1.0 / (torch.tensor(float(n)) + 1e-7)).item()
+        torch.testing.assert_close(out[i], ref, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(enc[i, :n], y[start : start + n], rtol=1e-5, atol=1e-5)
+        assert float(enc[i, n:].abs().max()) == 0.0 if n < 128 else True
+        start += n
