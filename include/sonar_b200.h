@@ -153,6 +153,23 @@ int sb_pool(const float* x, const int32_t* cu_seqlens, int32_t B, int32_t D, con
             float eps, int32_t apply_ln, int32_t pool_mode, float* out, float* encoded_padded, int32_t S_padded,
             void* stream);
 
+/* ---- xsim cosine k-NN / margin mining over sentence embeddings (BASELINE.json config 5) ----
+ * Not a reference interface: the reference only ever does normalize + matmul
+ * (tests/integration_tests/test_text_sonar.py:42,51); algorithm = public LASER xsim. */
+
+int sb_xsim_workspace_bytes(int32_t n, int32_t m, int32_t d, size_t* bytes);
+
+/* k nearest rows of y[m,d] (cosine) for every row of x[n,d]; x, y DEVICE fp32 row-major (raw, un-normalised).
+ * out_val DEVICE fp64 [n,k] exact cosines, out_idx DEVICE int32 [n,k]; sorted by (cosine desc, index asc).
+ * Candidates come from a bf16 tcgen05 GEMM with a fused running top-16, then are re-scored in fp64. */
+int sb_xsim_knn(const float* x, const float* y, int32_t n, int32_t m, int32_t d, int32_t k, double* out_val,
+                int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+
+/* pred[i] = forward candidate of row i with the best margin score.
+ * margin_mode 0 = absolute, 1 = ratio, 2 = distance; val_yx = fp64 [m,k] k-NN cosines of y rows among x. */
+int sb_xsim_margin_predict(const double* val_xy, const int32_t* idx_xy, const double* val_yx, int32_t n, int32_t m,
+                           int32_t k, int32_t margin_mode, int32_t* pred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

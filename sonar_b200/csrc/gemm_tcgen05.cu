@@ -18,6 +18,8 @@
 #include "common.cuh"
 #include "sonar_b200_internal.h"
 
+#include <math_constants.h>
+
 namespace sb {
 
 template <int kCtaGroup>
@@ -38,11 +40,49 @@ struct GemmCfg {
   static constexpr int THREADS = 256;
 };
 
+// Work item w of a cluster -> (m_blk, n_blk).  Default: tiles are dealt round-robin with n fastest, so the
+// clusters running concurrently share A rows through L2 and every weight tile stays L2-resident.
+// Sweep (top-k epilogue): a cluster owns whole m-blocks and walks all n tiles of each, so the running
+// top-k of a row can live in the epilogue thread's registers across the entire sweep.
+template <bool kSweep>
+__device__ __forceinline__ bool tile_of(int w, int cluster_id, int num_clusters, int num_m_tiles, int num_n_tiles,
+                                        int& m_blk, int& n_blk) {
+  if constexpr (kSweep) {
+    m_blk = cluster_id + (w / num_n_tiles) * num_clusters;
+    n_blk = w % num_n_tiles;
+    return m_blk < num_m_tiles;
+  } else {
+    const int tile = cluster_id + w * num_clusters;
+    m_blk = tile / num_n_tiles;
+    n_blk = tile % num_n_tiles;
+    return tile < num_m_tiles * num_n_tiles;
+  }
+}
+
+// insert (v, idx) into a descending list kept in registers; equal values keep the earlier entry first
+template <int KC>
+__device__ __forceinline__ void topk_insert(float (&tv)[KC], int (&ti)[KC], float v, int idx) {
+  float cv = v;
+  int ci = idx;
+#pragma unroll
+  for (int p = 0; p < KC; ++p) {
+    const bool gt = cv > tv[p];
+    const float ov = tv[p];
+    const int oi = ti[p];
+    tv[p] = gt ? cv : ov;
+    ti[p] = gt ? ci : oi;
+    cv = gt ? ov : cv;
+    ci = gt ? oi : ci;
+  }
+}
+
 template <int kCtaGroup, int kEpi, typename OutT>
 __global__ void __launch_bounds__(256, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                          const __grid_constant__ CUtensorMap tm_c, const float* __restrict__ bias,
-                         const OutT* residual, long long ldr, int M, int N, int K) {
+                         const OutT* residual, long long ldr, int M, int N, int K, float* __restrict__ cand_val,
+                         int* __restrict__ cand_idx) {
+  constexpr bool kSweep = (kEpi == EPI_TOPK);
   using Cfg = GemmCfg<kCtaGroup>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -86,8 +126,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 
   const int tile_m = Cfg::BLOCK_M * kCtaGroup;
   const int num_m_tiles = (M + tile_m - 1) / tile_m;
-  const int num_n_tiles = N / Cfg::BLOCK_N;
-  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int num_n_tiles = (N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;  // N tail only with the top-k epilogue
   const int num_kb = K / Cfg::BLOCK_K;
   const int cluster_id = blockIdx.x / kCtaGroup;
   const int num_clusters = gridDim.x / kCtaGroup;
@@ -97,8 +136,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
+      int m_blk, n_blk;
+      for (int w = 0; tile_of<kSweep>(w, cluster_id, num_clusters, num_m_tiles, num_n_tiles, m_blk, n_blk); ++w) {
         const int m0 = m_blk * tile_m + int(cta_rank) * Cfg::BLOCK_M;
         const int n0 = n_blk * Cfg::BLOCK_N + int(cta_rank) * Cfg::LOAD_N;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -122,8 +161,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       constexpr uint32_t idesc = umma_idesc_bf16_f32(Cfg::BLOCK_M * kCtaGroup, Cfg::BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t iter = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
+      int m_blk, n_blk;
+      for (uint32_t iter = 0;
+           tile_of<kSweep>(int(iter), cluster_id, num_clusters, num_m_tiles, num_n_tiles, m_blk, n_blk); ++iter) {
         const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
@@ -153,16 +193,65 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     constexpr int CHUNK_COLS = 128 / int(sizeof(OutT));  // one 128-byte smem row per output row
     constexpr int NUM_CHUNKS = Cfg::BLOCK_N / CHUNK_COLS;
     constexpr int SUBS = CHUNK_COLS / 32;
-    uint32_t iter = 0;
     int cd_stage = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
-      const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
+    int m_blk, n_blk;
+    constexpr int KC = kTopkCandidates;
+    [[maybe_unused]] float tv[KC];
+    [[maybe_unused]] int ti[KC];
+    for (uint32_t iter = 0;
+         tile_of<kSweep>(int(iter), cluster_id, num_clusters, num_m_tiles, num_n_tiles, m_blk, n_blk); ++iter) {
       const int m0 = m_blk * tile_m + int(cta_rank) * Cfg::BLOCK_M;
       const int n0 = n_blk * Cfg::BLOCK_N;
       const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const int grow = m0 + row_in_tile;
+      if constexpr (kEpi == EPI_TOPK) {
+        // ---- running per-row top-KC over the whole sweep of n tiles (no C matrix is ever written) ----
+        if (n_blk == 0) {
+#pragma unroll
+          for (int p = 0; p < KC; ++p) { tv[p] = -CUDART_INF_F; ti[p] = -1; }
+        }
+#pragma unroll 1
+        for (int c = 0; c < Cfg::BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(ew * 32) << 16) + acc * Cfg::BLOCK_N + c * 32, v);
+          tmem_ld_wait();
+          const int gcol = n0 + c * 32;
+          if (gcol + 32 > N) {  // ragged last tile: columns >= N are zero-filled operands, not candidates
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (gcol + j >= N) v[j] = __float_as_uint(-CUDART_INF_F);
+          }
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            float mx = __uint_as_float(v[g8 * 8]);
+#pragma unroll
+            for (int j = 1; j < 8; ++j) mx = fmaxf(mx, __uint_as_float(v[g8 * 8 + j]));
+            if (mx > tv[KC - 1]) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float x = __uint_as_float(v[g8 * 8 + j]);
+                if (x > tv[KC - 1]) topk_insert<KC>(tv, ti, x, gcol + g8 * 8 + j);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kCtaGroup == 2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+          else mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        if (n_blk == num_n_tiles - 1 && grow < M) {
+#pragma unroll
+          for (int p = 0; p < KC; ++p) {
+            cand_val[(long long)grow * KC + p] = tv[p];
+            cand_idx[(long long)grow * KC + p] = ti[p];
+          }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < NUM_CHUNKS; ++c) {
         if (ew == 0 && lane == 0) tma_store_wait_read<Cfg::CD_STAGES - 1>();  // staging buffer free again
@@ -242,7 +331,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (ew == 0 && lane == 0) {
-          tma_store_2d(&tm_c, smem_cd + cd_stage * Cfg::CD_STAGE_BYTES, n0 + c * CHUNK_COLS, m0);
+          if constexpr (kEpi == EPI_BIAS_ACCUM)
+            tma_reduce_add_2d(&tm_c, smem_cd + cd_stage * Cfg::CD_STAGE_BYTES, n0 + c * CHUNK_COLS, m0);
+          else
+            tma_store_2d(&tm_c, smem_cd + cd_stage * Cfg::CD_STAGE_BYTES, n0 + c * CHUNK_COLS, m0);
           tma_store_commit();
         }
         cd_stage ^= 1;
@@ -308,7 +400,8 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long ro
 
 template <int kCtaGroup, int kEpi, typename OutT>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const float* bias,
-                       const void* residual, long long ldr, int M, int N, int K, int num_sms, cudaStream_t stream) {
+                       const void* residual, long long ldr, int M, int N, int K, int num_sms, cudaStream_t stream,
+                       float* cand_val = nullptr, int* cand_idx = nullptr) {
   using Cfg = GemmCfg<kCtaGroup>;
   auto kern = gemm_bf16_tcgen05_kernel<kCtaGroup, kEpi, OutT>;
   static bool attr_set = false;
@@ -317,9 +410,11 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     attr_set = true;
   }
   const int tile_m = Cfg::BLOCK_M * kCtaGroup;
-  const long long num_tiles = (long long)((M + tile_m - 1) / tile_m) * (N / Cfg::BLOCK_N);
+  const long long num_m_tiles = (M + tile_m - 1) / tile_m;
+  const long long num_tiles = num_m_tiles * ((N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N);
   long long clusters = num_sms / kCtaGroup;
   if (clusters > num_tiles) clusters = num_tiles;
+  if (kEpi == EPI_TOPK && clusters > num_m_tiles) clusters = num_m_tiles;  // a cluster owns whole m-blocks
   if (clusters < 1) clusters = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * kCtaGroup), 1, 1);
@@ -333,8 +428,31 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, bias, reinterpret_cast<const OutT*>(residual), ldr, M, N, K));
+  SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, bias, reinterpret_cast<const OutT*>(residual), ldr, M, N, K,
+                                   cand_val, cand_idx));
   return 0;
+}
+
+// Per-row top-kTopkCandidates of A[M,K] . W[N,K]^T (bf16 operands, fp32 accumulate) without materialising
+// the product: cand_val / cand_idx are [M, kTopkCandidates], sorted by value descending.
+int gemm_bf16_topk(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
+                   float* cand_val, int* cand_idx, int cta_group, int num_sms, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return 0;
+  if (K % 64 != 0 || K <= 0) {
+    set_last_error("gemm_bf16_topk: K must be a positive multiple of 64 (got %d)", K);
+    return -1;
+  }
+  const int cg = (cta_group == 1) ? 1 : 2;
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_tmap_2d(&ta, A, 2, M, K, lda, 128, 64))) return rc;
+  if ((rc = make_tmap_2d(&tb, W, 2, N, K, ldw, 256 / cg, 64))) return rc;
+  const int sms = num_sms > 0 ? num_sms : 148;
+  if (cg == 2)
+    return launch_inst<2, EPI_TOPK, float>(ta, tb, ta /*unused*/, nullptr, nullptr, 0, M, N, K, sms, stream, cand_val,
+                                           cand_idx);
+  return launch_inst<1, EPI_TOPK, float>(ta, tb, ta /*unused*/, nullptr, nullptr, 0, M, N, K, sms, stream, cand_val,
+                                         cand_idx);
 }
 
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
@@ -359,15 +477,22 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   if ((rc = make_tmap_2d(&tb, g.W, 2, g.N, g.K, g.ldw, 256 / cg, 64))) return rc;
   if ((rc = make_tmap_2d(&tc, g.C, out_bytes, g.M, g.N, g.ldc, 128, 128 / out_bytes))) return rc;
   const int sms = g.num_sms > 0 ? g.num_sms : 148;
+  int epi = g.epi;
+  if (epi == EPI_BIAS_RESIDUAL && g.out_fp32 && g.residual == g.C && g.ldr == g.ldc) epi = EPI_BIAS_ACCUM;
+  if (epi == EPI_BIAS_ACCUM && !g.out_fp32) {
+    set_last_error("gemm_bf16: accumulate epilogue needs fp32 output");
+    return -1;
+  }
 
 #define SB_DISPATCH(CG, EPI, T) \
   return launch_inst<CG, EPI, T>(ta, tb, tc, g.bias, g.residual, g.ldr, g.M, g.N, g.K, sms, stream)
 #define SB_DISPATCH_EPI(CG, T)                                              \
-  switch (g.epi) {                                                          \
+  switch (epi) {                                                            \
     case EPI_BIAS: SB_DISPATCH(CG, EPI_BIAS, T);                            \
     case EPI_BIAS_RELU: SB_DISPATCH(CG, EPI_BIAS_RELU, T);                  \
     case EPI_BIAS_RESIDUAL: SB_DISPATCH(CG, EPI_BIAS_RESIDUAL, T);          \
-    default: set_last_error("gemm_bf16: bad epilogue %d", g.epi); return -1; \
+    case EPI_BIAS_ACCUM: SB_DISPATCH(CG, EPI_BIAS_ACCUM, float);            \
+    default: set_last_error("gemm_bf16: bad epilogue %d", epi); return -1;  \
   }
   if (cg == 2) {
     if (g.out_fp32) { SB_DISPATCH_EPI(2, float) } else { SB_DISPATCH_EPI(2, __nv_bfloat16) }

@@ -9,7 +9,12 @@
 
 namespace sb {
 
-enum EpiMode { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_RESIDUAL = 2 };
+// EPI_BIAS_ACCUM (internal): C += A.W^T + bias with the add done by TMA reduce-add at L2; chosen
+// automatically for EPI_BIAS_RESIDUAL when the residual aliases a fp32 C (the encoder's x += ... case).
+// Bit-identical to EPI_BIAS_RESIDUAL: both compute fl32(x + fl32(acc + bias)).
+// EPI_TOPK (internal): no C at all -- the epilogue keeps a running per-row top-k of the product (xsim mining).
+enum EpiMode { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_RESIDUAL = 2, EPI_BIAS_ACCUM = 3, EPI_TOPK = 4 };
+constexpr int kTopkCandidates = 16;  // bf16-similarity candidates per row handed to the exact fp64 re-rank
 enum PoolMode { POOL_MAX = 1, POOL_MEAN = 2, POOL_LAST = 3 };  // = reference `Pooling` enum values (model.py:23-27)
 
 void set_last_error(const char* fmt, ...);
@@ -32,6 +37,9 @@ struct GemmArgs {
 };
 
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
+
+int gemm_bf16_topk(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
+                   float* cand_val, int* cand_idx, int cta_group, int num_sms, cudaStream_t stream);
 
 int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld,
                  int box_rows, int box_cols);

@@ -1,0 +1,203 @@
+// xsim cosine k-NN + margin scoring over sentence embeddings (BASELINE.json config 5).
+// Not part of the reference repository (README.md:5 only names the task); algorithm = public LASER
+// xsim.py, restated in oracle/xsim.py.
+//
+// Pipeline for knn(x[n,d], y[m,d], k):
+//   1. l2_normalize: fp32 rows -> unit-norm bf16 rows (+ fp64 norms)                     [HBM-bound]
+//   2. gemm_bf16_topk: tcgen05 GEMM x^ . y^T whose epilogue keeps a running top-16 per row
+//      in registers -- the n x m similarity matrix is never written                      [tensor-bound]
+//   3. exact re-rank of the 16 candidates per row in fp64 from the RAW fp32 embeddings
+//      (cos = <x,y> / (|x||y|)), order (score desc, index asc), keep k                   [gather, L2/HBM]
+// so the final neighbours/scores do not depend on bf16 rounding as long as the true top-k are among the
+// 16 bf16 candidates.
+
+#include "../../include/sonar_b200.h"
+#include "common.cuh"
+#include "sonar_b200_internal.h"
+
+#include <math_constants.h>
+
+namespace sb {
+
+static inline size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// one warp per row: y = x / |x| (bf16), norm (fp64)
+__global__ void __launch_bounds__(256)
+l2_normalize_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xn, double* __restrict__ norm, long long n,
+                    int d) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+  double s = 0.0;
+  for (int c = lane; c < d / 4; c += 32) {
+    const float4 v = xr[c];
+    s += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const double nr = sqrt(s);
+  const float inv = (float)(1.0 / fmax(nr, 1e-30));
+  uint2* out = reinterpret_cast<uint2*>(xn + row * d);
+  for (int c = lane; c < d / 4; c += 32) {
+    const float4 v = xr[c];
+    out[c] = make_uint2(pack_bf16x2(v.x * inv, v.y * inv), pack_bf16x2(v.z * inv, v.w * inv));
+  }
+  if (lane == 0) norm[row] = nr;
+}
+
+// one warp per x row: exact fp64 cosine of the KC candidates, keep the best k by (score desc, index asc)
+template <int KC>
+__global__ void __launch_bounds__(256)
+rerank_kernel(const float* __restrict__ x, const float* __restrict__ y, const double* __restrict__ nx,
+              const double* __restrict__ ny, const int* __restrict__ cand_idx, int n, int m, int d, int k,
+              double* __restrict__ out_val, int* __restrict__ out_idx) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * d);
+  double my_score = -CUDART_INF;
+  int my_idx = 0x7fffffff;
+  for (int c = 0; c < KC; ++c) {
+    const int j = cand_idx[(long long)row * KC + c];
+    double dot = 0.0;
+    if (j >= 0 && j < m) {
+      const float4* yr = reinterpret_cast<const float4*>(y + (long long)j * d);
+      for (int q = lane; q < d / 4; q += 32) {
+        const float4 a = xr[q], b = yr[q];
+        dot += (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (lane == c && j >= 0 && j < m) {
+      my_score = dot / fmax(nx[row] * ny[j], 1e-300);
+      my_idx = j;
+    }
+  }
+  // rank of lane's candidate among the KC (lanes >= KC hold -inf / INT_MAX and rank last)
+  int rank = 0;
+  for (int c = 0; c < KC; ++c) {
+    const double s = __shfl_sync(0xffffffffu, my_score, c);
+    const int i = __shfl_sync(0xffffffffu, my_idx, c);
+    if (s > my_score || (s == my_score && i < my_idx)) ++rank;
+  }
+  if (lane < KC && rank < k) {
+    const bool valid = my_idx != 0x7fffffff;
+    out_val[(long long)row * k + rank] = valid ? my_score : -CUDART_INF;
+    out_idx[(long long)row * k + rank] = valid ? my_idx : -1;
+  }
+}
+
+// one thread per x row: margin scoring over the forward candidates (LASER xsim)
+__global__ void margin_predict_kernel(const double* __restrict__ val_xy, const int* __restrict__ idx_xy,
+                                      const double* __restrict__ val_yx, int n, int m, int k, int mode,
+                                      int* __restrict__ pred) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (mode == 0) {  // absolute: plain top-1 cosine
+    pred[i] = idx_xy[(long long)i * k];
+    return;
+  }
+  double avg_x = 0.0;
+  for (int c = 0; c < k; ++c) avg_x += val_xy[(long long)i * k + c];
+  avg_x /= (double)k;
+  double best = -CUDART_INF;
+  int best_j = -1;
+  for (int c = 0; c < k; ++c) {
+    const int j = idx_xy[(long long)i * k + c];
+    if (j < 0 || j >= m) continue;
+    double avg_y = 0.0;
+    for (int q = 0; q < k; ++q) avg_y += val_yx[(long long)j * k + q];
+    avg_y /= (double)k;
+    const double denom = (avg_x + avg_y) / 2.0;
+    const double cs = val_xy[(long long)i * k + c];
+    const double score = (mode == 1) ? cs / denom : cs - denom;
+    if (score > best) {  // strict: first maximum wins (lowest candidate rank)
+      best = score;
+      best_j = j;
+    }
+  }
+  pred[i] = best_j;
+}
+
+struct XsimWs {
+  __nv_bfloat16* xn;
+  __nv_bfloat16* yn;
+  double* nx;
+  double* ny;
+  float* cand_val;
+  int* cand_idx;
+  size_t bytes;
+};
+
+static XsimWs carve_xsim(int n, int m, int d, void* base) {
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  XsimWs w;
+  w.xn = reinterpret_cast<__nv_bfloat16*>(p + off); off = align_up_sz(off + (size_t)n * d * 2, 1024);
+  w.yn = reinterpret_cast<__nv_bfloat16*>(p + off); off = align_up_sz(off + (size_t)m * d * 2, 1024);
+  w.nx = reinterpret_cast<double*>(p + off); off = align_up_sz(off + (size_t)n * 8, 1024);
+  w.ny = reinterpret_cast<double*>(p + off); off = align_up_sz(off + (size_t)m * 8, 1024);
+  w.cand_val = reinterpret_cast<float*>(p + off); off = align_up_sz(off + (size_t)n * kTopkCandidates * 4, 1024);
+  w.cand_idx = reinterpret_cast<int*>(p + off); off = align_up_sz(off + (size_t)n * kTopkCandidates * 4, 1024);
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+int sb_xsim_workspace_bytes(int32_t n, int32_t m, int32_t d, size_t* bytes) {
+  if (n <= 0 || m <= 0 || d <= 0 || !bytes) { set_last_error("sb_xsim_workspace_bytes: bad argument"); return SB_ERR_INVALID; }
+  *bytes = carve_xsim(n, m, d, nullptr).bytes + 1024;
+  return SB_OK;
+}
+
+int sb_xsim_knn(const float* x, const float* y, int32_t n, int32_t m, int32_t d, int32_t k, double* out_val,
+                int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream_v) {
+  if (!x || !y || !out_val || !out_idx || !workspace) { set_last_error("sb_xsim_knn: null pointer"); return SB_ERR_INVALID; }
+  if (n <= 0 || m <= 0) { set_last_error("sb_xsim_knn: empty input"); return SB_ERR_INVALID; }
+  if (d <= 0 || d % 64 != 0) { set_last_error("sb_xsim_knn: embedding dim must be a multiple of 64 (got %d)", d); return SB_ERR_INVALID; }
+  if (k <= 0 || k > kTopkCandidates) { set_last_error("sb_xsim_knn: k must be in [1, %d]", kTopkCandidates); return SB_ERR_INVALID; }
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023);
+  XsimWs w = carve_xsim(n, m, d, reinterpret_cast<void*>(base));
+  if (base - reinterpret_cast<uintptr_t>(workspace) + w.bytes > workspace_bytes) {
+    set_last_error("sb_xsim_knn: workspace too small");
+    return SB_ERR_INVALID;
+  }
+  int dev = 0, sms = 0;
+  SB_CUDA_CHECK(cudaGetDevice(&dev));
+  SB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  l2_normalize_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(x, w.xn, w.nx, n, d);
+  l2_normalize_kernel<<<(unsigned)((m + 7) / 8), 256, 0, stream>>>(y, w.yn, w.ny, m, d);
+  SB_CUDA_CHECK(cudaGetLastError());
+  int rc = gemm_bf16_topk(w.xn, d, w.yn, d, n, m, d, w.cand_val, w.cand_idx, 2, sms, stream);
+  if (rc) return rc;
+  rerank_kernel<kTopkCandidates><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(x, y, w.nx, w.ny, w.cand_idx, n, m, d, k,
+                                                                             out_val, out_idx);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return SB_OK;
+}
+
+int sb_xsim_margin_predict(const double* val_xy, const int32_t* idx_xy, const double* val_yx, int32_t n, int32_t m,
+                           int32_t k, int32_t margin_mode, int32_t* pred, void* stream_v) {
+  if (!val_xy || !idx_xy || !pred || (margin_mode != 0 && !val_yx)) {
+    set_last_error("sb_xsim_margin_predict: null pointer");
+    return SB_ERR_INVALID;
+  }
+  if (margin_mode < 0 || margin_mode > 2 || n <= 0 || k <= 0) {
+    set_last_error("sb_xsim_margin_predict: bad argument");
+    return SB_ERR_INVALID;
+  }
+  margin_predict_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+      val_xy, idx_xy, val_yx, n, m, k, margin_mode, pred);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return SB_OK;
+}
+
+}  // extern "C"
