@@ -165,11 +165,34 @@ def stage_encoder():
         print(f"encoder {layers} layers:", parity_metrics(out, ref), flush=True)
 
 
+def stage_xsim():
+    import numpy as np
+    from oracle import xsim as ox
+    from sonar_b200 import xsim
+    g = torch.Generator().manual_seed(0)
+    for (n, m, d) in [(300, 1000, 1024), (1000, 777, 1024), (4096, 8192, 1024)]:
+        y = torch.randn((m, d), generator=g)
+        x = torch.randn((n, d), generator=g)
+        val, idx = xsim.knn(x.to(DEV), y.to(DEV), 4)
+        torch.cuda.synchronize()
+        rv, ri = ox.knn(x.numpy(), y.numpy(), 4)
+        same = np.array_equal(idx.cpu().numpy(), ri)
+        print(f"xsim knn {n}x{m}: idx equal={same} max val err={np.abs(val.cpu().numpy() - rv).max():.3e}", flush=True)
+        if not same:
+            bad = (idx.cpu().numpy() != ri).any(1)
+            print("  bad rows", bad.sum(), "first", np.nonzero(bad)[0][:5], idx.cpu().numpy()[bad][:3], ri[bad][:3])
+    n = m = 131072
+    x = torch.randn((n, 1024), device=DEV)
+    y = torch.randn((m, 1024), device=DEV)
+    med, best = timeit(lambda: xsim.knn(x, y, 4), iters=3, warm=1)
+    print(f"xsim knn {n}x{m}: {med:.2f} ms  {n * m / med / 1e6:.2f} Gpairs/s  GEMM-equivalent {2.0 * n * m * 1024 / med / 1e9:.0f} TFLOP/s")
+
+
 if __name__ == "__main__":
     stage = sys.argv[1]
     t0 = time.time()
     print(f"== stage {stage} on {torch.cuda.get_device_name(0)}", flush=True)
     {"elementwise": stage_elementwise, "gemm1": lambda: stage_gemm(1), "gemm2": lambda: stage_gemm(2),
-     "perf": stage_perf, "encoder": stage_encoder}[stage]()
+     "perf": stage_perf, "encoder": stage_encoder, "xsim": stage_xsim}[stage]()
     torch.cuda.synchronize()
     print(f"== stage {stage} done in {time.time() - t0:.1f}s", flush=True)

@@ -156,9 +156,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     }
     __syncwarp();
   } else if (warp_idx == 1) {
-    // ===================== MMA issuer (one thread of the leader CTA) =====================
-    if (is_leader && lane == 0) {
+    // ===================== MMA issuer (leader CTA; whole warp walks the loop, one elected lane issues) ===========
+    // The loop state is kept warp-uniform so the compiler can hold descriptors in uniform registers: the
+    // issue path must stay well under the 512 tensor-core cycles one k-block takes.
+    if (is_leader) {
       constexpr uint32_t idesc = umma_idesc_bf16_f32(Cfg::BLOCK_M * kCtaGroup, Cfg::BLOCK_N);
+      constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO=1024 B, version 1, SWIZZLE_128B
+      const uint32_t a_lo0 = (smem_u32(smem_a) >> 4) & 0x3FFFu;
+      const uint32_t b_lo0 = (smem_u32(smem_b) >> 4) & 0x3FFFu;
       int stage = 0;
       uint32_t phase = 0;
       int m_blk, n_blk;
@@ -171,21 +176,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);  // TMA bytes of both CTAs have landed
           tc_fence_after();
-          const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES));
-          const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES));
+          if (elect_one()) {
+            const uint32_t a_lo = a_lo0 + uint32_t(stage) * (Cfg::A_BYTES >> 4);
+            const uint32_t b_lo = b_lo0 + uint32_t(stage) * (Cfg::B_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < Cfg::BLOCK_K / 16; ++k) {
-            // +32 bytes (= 16 bf16) along K inside the 128B swizzle atom -> +2 in the >>4 address field
-            umma_bf16<kCtaGroup>(d_tmem, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc,
-                                 (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < Cfg::BLOCK_K / 16; ++k) {
+              // +32 bytes (= 16 bf16) along K inside the 128B swizzle atom -> +2 in the >>4 address field
+              const uint64_t a_desc = (uint64_t(desc_hi) << 32) | uint64_t(a_lo + 2 * k);
+              const uint64_t b_desc = (uint64_t(desc_hi) << 32) | uint64_t(b_lo + 2 * k);
+              umma_bf16<kCtaGroup>(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit<kCtaGroup>(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+            if (kb == num_kb - 1) umma_commit<kCtaGroup>(&tmem_full_bar[acc]);
           }
-          umma_commit<kCtaGroup>(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (kb == num_kb - 1) umma_commit<kCtaGroup>(&tmem_full_bar[acc]);
+          __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-    __syncwarp();
   } else if (warp_idx >= 4) {
     // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
     const int ew = warp_idx - 4;          // == warp_idx % 4 -> TMEM lane quarter

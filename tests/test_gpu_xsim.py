@@ -1,0 +1,84 @@
+"""xsim k-NN / margin mining (sb_xsim_knn, sb_xsim_margin_predict) against the float64 NumPy oracle
+(oracle/xsim.py; parity unpinned against the reference, which has no xsim code).  Bar: identical
+neighbour INDICES (bit-exact integer outputs); cosines to 1e-12 (both sides fp64 from the same fp32 data)."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import xsim as oracle_xsim
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n, m, d, seed, noise=0.1):
+    g = torch.Generator().manual_seed(seed)
+    y = torch.randn((m, d), generator=g)
+    x = y[:n].clone() if n <= m else torch.randn((n, d), generator=g)
+    # noisy copies: x_i = y_i + noise * N(0,1) * |y_i| / sqrt(d)
+    x = x + noise * torch.randn(x.shape, generator=g) * x.norm(dim=1, keepdim=True) / d ** 0.5
+    return x.float(), y.float()
+
+
+@pytest.mark.parametrize("n,m,d,k", [(300, 1000, 1024, 4), (1000, 777, 1024, 4), (64, 20, 256, 4),
+                                     (4096, 8192, 1024, 8), (5, 3, 64, 2)])
+def test_knn_matches_oracle(native_lib, cuda_device, n, m, d, k):
+    from sonar_b200 import xsim
+
+    x, y = _data(n, m, d, seed=n + m)
+    val, idx = xsim.knn(x.to(cuda_device), y.to(cuda_device), k)
+    torch.cuda.synchronize()
+    ref_val, ref_idx = oracle_xsim.knn(x.numpy(), y.numpy(), k)
+    kk = min(k, m)
+    assert np.array_equal(idx.cpu().numpy()[:, :kk], ref_idx[:, :kk])
+    np.testing.assert_allclose(val.cpu().numpy()[:, :kk], ref_val[:, :kk], rtol=0, atol=1e-12)
+    if kk < k:  # fewer candidates than k: padded with -1 / -inf
+        assert (idx.cpu().numpy()[:, kk:] == -1).all()
+
+
+def test_knn_hard_near_ties(native_lib, cuda_device):
+    """Clustered data: many neighbours within bf16 resolution of each other -> the exact fp64 re-rank of the
+    16 bf16 candidates must still return the true top-4."""
+    from sonar_b200 import xsim
+
+    g = torch.Generator().manual_seed(7)
+    centers = torch.randn((64, 1024), generator=g)
+    y = centers.repeat_interleave(8, 0) + 0.02 * torch.randn((512, 1024), generator=g)  # clusters of 8
+    x = y + 0.01 * torch.randn(y.shape, generator=g)
+    val, idx = xsim.knn(x.to(cuda_device), y.to(cuda_device), 4)
+    ref_val, ref_idx = oracle_xsim.knn(x.numpy(), y.numpy(), 4)
+    assert np.array_equal(idx.cpu().numpy(), ref_idx)
+
+
+@pytest.mark.parametrize("margin", ["ratio", "distance", "absolute"])
+def test_xsim_matches_oracle(native_lib, cuda_device, margin):
+    from sonar_b200 import xsim
+
+    x, y = _data(2048, 2048, 1024, seed=11, noise=1.0)  # noisy enough that some retrievals fail
+    err, n, pred = xsim.xsim(x.to(cuda_device), y.to(cuda_device), margin=margin, k=4)
+    ref_err, ref_n, ref_pred = oracle_xsim.xsim(x.numpy(), y.numpy(), margin=margin, k=4)
+    assert n == ref_n
+    assert np.array_equal(pred.cpu().numpy(), ref_pred)
+    assert err == ref_err
+
+
+def test_xsim_large_slice_top1(native_lib, cuda_device):
+    """BASELINE.json config 5 parity slice (scaled to what the fp64 oracle finishes in seconds): 16K x 16K."""
+    from sonar_b200 import xsim
+
+    x, y = _data(16384, 16384, 1024, seed=13, noise=0.5)
+    val, idx = xsim.knn(x.to(cuda_device), y.to(cuda_device), 4)
+    ref_val, ref_idx = oracle_xsim.knn(x.numpy(), y.numpy(), 4)
+    assert np.array_equal(idx.cpu().numpy(), ref_idx)
+
+
+def test_xsim_rejects_bad_args(native_lib, cuda_device):
+    from sonar_b200 import xsim
+
+    x = torch.zeros((4, 100), device=cuda_device)
+    with pytest.raises(ValueError):
+        xsim.knn(x, x, 4)  # dim not a multiple of 64
+    with pytest.raises(ValueError):
+        xsim.knn(torch.zeros((4, 64), device=cuda_device), torch.zeros((4, 64), device=cuda_device), 17)
+    with pytest.raises(RuntimeError):
+        xsim.knn(torch.zeros((4, 64)), torch.zeros((4, 64)), 2)
