@@ -139,9 +139,10 @@ int sb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C
 int sb_layernorm(const float* x, const float* gamma, const float* beta, float eps, void* y, int64_t T, int32_t D,
                  void* stream);
 
-/* packed self-attention: qkv bf16 [T, 3*64*H], cu_seqlens DEVICE int32 [B+1], out bf16 [T, 64*H] */
-int sb_attention(const void* qkv, const int32_t* cu_seqlens, int32_t B, int32_t max_len, int32_t H, void* out,
-                 void* stream);
+/* packed self-attention: qkv bf16 [total_tokens, 3*64*H], cu_seqlens DEVICE int32 [B+1], out bf16 [total_tokens, 64*H].
+ * impl 0 = auto (tcgen05 kernel when max_len <= 128, mma.sync flash kernel otherwise), 1 = mma.sync, 2 = tcgen05. */
+int sb_attention(const void* qkv, const int32_t* cu_seqlens, int32_t B, int32_t max_len, int32_t H,
+                 int64_t total_tokens, int32_t impl, void* out, void* stream);
 
 /* x[cu[b]+t,:] = embed[ids[b,t],:]*scale + pos[t,:] ; err_flag DEVICE int32 (set to 1 on a bad id) */
 int sb_embed(const int64_t* ids, int64_t ids_row_stride, const int32_t* cu_seqlens, int32_t B, int32_t S,

@@ -35,6 +35,28 @@ def err_map(out, ref, rb=32, cb=64):
     return blk
 
 
+IMPL = "tcgen05"
+
+
+def stage_attn_tc():
+    """first contact with the tcgen05 attention kernel: small cases, printed errors"""
+    h, d = 16, 1024
+    for lens in ([128], [128] * 3, [64], [1, 17, 64, 65, 100, 128], [128] * 600):
+        t = sum(lens)
+        qkv = rnd((t, 3 * d), 1.0, 5, torch.bfloat16)
+        cu = ops.cu_seqlens_of(lens).to(DEV)
+        o = ops.attention(qkv, cu, max(lens), h, impl="tcgen05")
+        r = ops.attention(qkv, cu, max(lens), h, impl="mma_sync")
+        torch.cuda.synchronize()
+        e = (o.float() - r.float()).abs()
+        print(f"attn_tc lens={lens[:6]}{'...' if len(lens) > 6 else ''} max diff vs mma_sync {e.max().item():.4g} "
+              f"nan={bool(torch.isnan(o.float()).any())}", flush=True)
+        if e.max().item() > 0.05:
+            rows = (e.max(1).values > 0.05).nonzero().flatten()[:10].tolist()
+            cols = (e.max(0).values > 0.05).nonzero().flatten()[:16].tolist()
+            print("  bad rows", rows, "bad cols", cols, "\n  got", o[rows[0], :8].float().tolist(), "\n  ref", r[rows[0], :8].float().tolist())
+
+
 def stage_elementwise():
     d = 1024
     x = rnd((300, d), 3.0, 1) + 0.5
@@ -55,7 +77,7 @@ def stage_elementwise():
         t = sum(lens)
         qkv = rnd((t, 3 * d), 1.0, 5, torch.bfloat16)
         cu = ops.cu_seqlens_of(lens).to(DEV)
-        o = ops.attention(qkv, cu, max(lens), h)
+        o = ops.attention(qkv, cu, max(lens), h, impl=IMPL if max(lens) <= 128 else "auto")
         torch.cuda.synchronize()
         s0, worst = 0, 0.0
         for n in lens:
@@ -137,8 +159,16 @@ def stage_perf():
     print(f"layernorm T={t}: {med:.3f} ms  {t * d * 6 / med / 1e6:.0f} GB/s")
     qkv = rnd((t, 3 * d), 1.0, 5, torch.bfloat16)
     cu = ops.cu_seqlens_of([128] * (t // 128)).to(DEV)
-    med, _ = timeit(lambda: ops.attention(qkv, cu, 128, h))
-    print(f"attention T={t} S=128: {med:.3f} ms  {t * d * 8 / med / 1e6:.0f} GB/s  {4.0 * t * 128 * d / med / 1e9:.1f} TFLOP/s")
+    for impl in ("mma_sync", "tcgen05"):
+        med, _ = timeit(lambda: ops.attention(qkv, cu, 128, h, impl=impl))
+        print(f"attention[{impl}] T={t} S=128: {med:.3f} ms  {t * d * 8 / med / 1e6:.0f} GB/s  {4.0 * t * 128 * d / med / 1e9:.1f} TFLOP/s")
+    lens = torch.randint(16, 129, (t // 72,), generator=torch.Generator().manual_seed(0)).tolist()
+    tt = sum(lens)
+    qkv2 = rnd((tt, 3 * d), 1.0, 6, torch.bfloat16)
+    cu2 = ops.cu_seqlens_of(lens).to(DEV)
+    for impl in ("mma_sync", "tcgen05"):
+        med, _ = timeit(lambda: ops.attention(qkv2, cu2, 128, h, impl=impl))
+        print(f"attention[{impl}] ragged U(16..128) T={tt}: {med:.3f} ms  {tt * d * 8 / med / 1e6:.0f} GB/s")
 
 
 def stage_encoder():
@@ -193,6 +223,6 @@ if __name__ == "__main__":
     t0 = time.time()
     print(f"== stage {stage} on {torch.cuda.get_device_name(0)}", flush=True)
     {"elementwise": stage_elementwise, "gemm1": lambda: stage_gemm(1), "gemm2": lambda: stage_gemm(2),
-     "perf": stage_perf, "encoder": stage_encoder, "xsim": stage_xsim}[stage]()
+     "perf": stage_perf, "encoder": stage_encoder, "xsim": stage_xsim, "attn_tc": stage_attn_tc}[stage]()
     torch.cuda.synchronize()
     print(f"== stage {stage} done in {time.time() - t0:.1f}s", flush=True)

@@ -224,12 +224,18 @@ attention_packed_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
 }  // namespace
 
 int attention_packed(const __nv_bfloat16* qkv, const int32_t* cu_seqlens, int B, int max_len, int H,
-                     __nv_bfloat16* out, cudaStream_t stream) {
+                     long long total_tokens, int impl, int num_sms, __nv_bfloat16* out, cudaStream_t stream) {
   if (B <= 0 || max_len <= 0) return 0;
   if (H <= 0 || H > 65535 || B > 65535) {
     set_last_error("attention_packed: unsupported B=%d H=%d", B, H);
     return -1;
   }
+  if (impl == 2 && max_len > 128) {
+    set_last_error("attention_packed: the tcgen05 kernel handles sequences of at most 128 tokens (max_len=%d)", max_len);
+    return -1;
+  }
+  if (impl == 2 || (impl == 0 && max_len <= 128))
+    return attention_packed_tc(qkv, cu_seqlens, B, H, total_tokens, out, num_sms, stream);
   dim3 grid((unsigned)((max_len + kQBlock - 1) / kQBlock), (unsigned)H, (unsigned)B);
   attention_packed_kernel<<<grid, 256, 0, stream>>>(qkv, cu_seqlens, H, out);
   SB_CUDA_CHECK(cudaGetLastError());

@@ -247,7 +247,7 @@ int sb_encoder_forward(SbEncoder* e, const int64_t* ids, int64_t ids_row_stride,
     g.C = w.qkv; g.ldc = 3 * D; g.out_fp32 = 0; g.bias = L.bqkv; g.residual = nullptr; g.ldr = 0;
     g.N = 3 * D; g.K = D; g.epi = EPI_BIAS;
     if ((rc = gemm_bf16(g, stream))) return rc;
-    if ((rc = attention_packed(w.qkv, w.cu, B, max_len, H, w.h, stream))) return rc;
+    if ((rc = attention_packed(w.qkv, w.cu, B, max_len, H, T, 0, e->num_sms, w.h, stream))) return rc;
     g.A = w.h; g.lda = D; g.W = reinterpret_cast<const __nv_bfloat16*>(L.wo); g.ldw = D;
     g.C = w.x; g.ldc = D; g.out_fp32 = 1; g.bias = L.bo; g.residual = w.x; g.ldr = D;
     g.N = D; g.K = D; g.epi = EPI_BIAS_RESIDUAL;
@@ -327,11 +327,14 @@ int sb_layernorm(const float* x, const float* gamma, const float* beta, float ep
                         reinterpret_cast<cudaStream_t>(stream));
 }
 
-int sb_attention(const void* qkv, const int32_t* cu_seqlens, int32_t B, int32_t max_len, int32_t H, void* out,
-                 void* stream) {
+int sb_attention(const void* qkv, const int32_t* cu_seqlens, int32_t B, int32_t max_len, int32_t H,
+                 int64_t total_tokens, int32_t impl, void* out, void* stream) {
   if (!qkv || !cu_seqlens || !out) { set_last_error("sb_attention: null pointer"); return SB_ERR_INVALID; }
-  return attention_packed(reinterpret_cast<const __nv_bfloat16*>(qkv), cu_seqlens, B, max_len, H,
-                          reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<cudaStream_t>(stream));
+  int dev = 0, sms = 0;
+  SB_CUDA_CHECK(cudaGetDevice(&dev));
+  SB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  return attention_packed(reinterpret_cast<const __nv_bfloat16*>(qkv), cu_seqlens, B, max_len, H, total_tokens, impl,
+                          sms, reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<cudaStream_t>(stream));
 }
 
 int sb_embed(const int64_t* ids, int64_t ids_row_stride, const int32_t* cu_seqlens, int32_t B, int32_t S,

@@ -54,8 +54,11 @@ int layernorm_bf16(const float* x, const float* gamma, const float* beta, float 
                    int D, cudaStream_t stream);
 
 // softmax(q k^T / sqrt(64)) v over packed sequences; qkv [T, 3*D] bf16 (q | k | v), out [T, D] bf16
+// impl: 0 = auto (tcgen05 kernel when max_len <= 128, mma.sync flash kernel otherwise), 1 = mma.sync, 2 = tcgen05
 int attention_packed(const __nv_bfloat16* qkv, const int32_t* cu_seqlens, int B, int max_len, int H,
-                     __nv_bfloat16* out, cudaStream_t stream);
+                     long long total_tokens, int impl, int num_sms, __nv_bfloat16* out, cudaStream_t stream);
+int attention_packed_tc(const __nv_bfloat16* qkv, const int32_t* cu_seqlens, int B, int H, long long total_tokens,
+                        __nv_bfloat16* out, int num_sms, cudaStream_t stream);
 
 // optional final LayerNorm + pooling over packed sequences -> out [B, D] fp32;
 // optionally also scatters the (normalised) rows to a padded [B, S, D] fp32 tensor.

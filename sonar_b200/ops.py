@@ -72,7 +72,10 @@ def cu_seqlens_of(seq_lens) -> Tensor:
     return cu
 
 
-def attention(qkv: Tensor, cu_seqlens: Tensor, max_len: int, num_heads: int) -> Tensor:
+ATTENTION_IMPLS = {"auto": 0, "mma_sync": 1, "tcgen05": 2}
+
+
+def attention(qkv: Tensor, cu_seqlens: Tensor, max_len: int, num_heads: int, impl: str = "auto") -> Tensor:
     """Packed bidirectional MHA: qkv bf16 [T, 3*64*H] -> bf16 [T, 64*H]."""
     _need_cuda(qkv, cu_seqlens)
     assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and cu_seqlens.dtype == torch.int32
@@ -81,7 +84,7 @@ def attention(qkv: Tensor, cu_seqlens: Tensor, max_len: int, num_heads: int) -> 
     assert qkv.shape[1] == 3 * d
     out = torch.empty((t, d), dtype=torch.bfloat16, device=qkv.device)
     rc = _lib.load().sb_attention(qkv.data_ptr(), cu_seqlens.data_ptr(), cu_seqlens.numel() - 1, max_len,
-                                  num_heads, out.data_ptr(), _stream())
+                                  num_heads, t, ATTENTION_IMPLS[impl], out.data_ptr(), _stream())
     _lib.check(rc, "sb_attention")
     return out
 

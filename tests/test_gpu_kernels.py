@@ -94,25 +94,46 @@ def test_layernorm(ops, cuda_device, t, d):
     assert bool(((y.float() - ref).abs() <= ref.abs() * 2 ** -8 + 1e-5).all())
 
 
-@pytest.mark.parametrize("lens", [[128] * 4, [1, 2, 17, 64, 65, 128], [200, 129, 514], [33]])
-def test_attention_vs_sdpa(ops, cuda_device, lens):
+ATTN_CASES = [([128] * 4, "tcgen05"), ([128] * 4, "mma_sync"), ([1, 2, 17, 64, 65, 128], "tcgen05"),
+              ([1, 2, 17, 64, 65, 128], "mma_sync"), ([200, 129, 514], "auto"), ([33], "auto"),
+              ([128] * 700 + [5, 77, 128, 31] * 20, "tcgen05")]  # > 2 x 148 CTAs worth of items: persistent loop
+
+
+@pytest.mark.parametrize("lens,impl", ATTN_CASES)
+def test_attention_vs_sdpa(ops, cuda_device, lens, impl):
     h, hd = 16, 64
     d = h * hd
     t = sum(lens)
     qkv = _rand((t, 3 * d), 1.0, 14, cuda_device, torch.bfloat16)
     cu = ops.cu_seqlens_of(lens).to(cuda_device)
-    out = ops.attention(qkv, cu, max(lens), h)
+    out = ops.attention(qkv, cu, max(lens), h, impl=impl)
     torch.cuda.synchronize()
+    assert bool(torch.isfinite(out.float()).all())
     start = 0
-    for n in lens:
+    for i, n in enumerate(lens):
+        if i >= 12 and i % 97 != 0:  # spot-check the long case
+            start += n
+            continue
         blk = qkv[start : start + n].float()
-        q, k, v = (blk[:, i * d : (i + 1) * d].view(n, h, hd).transpose(0, 1) for i in range(3))
+        q, k, v = (blk[:, j * d : (j + 1) * d].view(n, h, hd).transpose(0, 1) for j in range(3))
         ref = torch.nn.functional.scaled_dot_product_attention(q[None], k[None], v[None])[0]
         ref = ref.transpose(0, 1).reshape(n, d)
         got = out[start : start + n].float()
         # P is rounded to bf16 before P.V and the output to bf16: ~2^-8 relative of |v|-scale values
         torch.testing.assert_close(got, ref, rtol=2e-2, atol=2e-2)
         start += n
+
+
+def test_attention_impls_agree_and_tc_rejects_long(ops, cuda_device):
+    h, d = 16, 1024
+    lens = [128, 90, 3]
+    qkv = _rand((sum(lens), 3 * d), 1.0, 21, cuda_device, torch.bfloat16)
+    cu = ops.cu_seqlens_of(lens).to(cuda_device)
+    a = ops.attention(qkv, cu, 128, h, impl="tcgen05").float()
+    b = ops.attention(qkv, cu, 128, h, impl="mma_sync").float()
+    torch.testing.assert_close(a, b, rtol=2e-2, atol=2e-2)
+    with pytest.raises(ValueError):
+        ops.attention(qkv, cu, 200, h, impl="tcgen05")
 
 
 def test_embed(ops, cuda_device):
