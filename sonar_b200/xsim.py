@@ -73,26 +73,33 @@ def xsim(x: Tensor, y: Tensor, margin: str = "ratio", k: int = 4) -> Tuple[int, 
     return err, n, pred
 
 
-def xsim_distributed(x_shard: Tensor, y_shard: Tensor, margin: str = "ratio", k: int = 4, group=None):
+def xsim_distributed(x_shard: Tensor, y_shard: Tensor, margin: str = "ratio", k: int = 4, group=None,
+                     _knn=None, _margin_predict=None):
     """Every rank holds the same number of rows of x and y (its batch shard of the encoded sentences).
-    -> (global errors, global n, predictions for this rank's rows as GLOBAL y indices)."""
+    -> (global errors, global n, predictions for this rank's rows as GLOBAL y indices).
+
+    ``_knn`` / ``_margin_predict`` exist only so the collective plumbing can be exercised under ``gloo`` on a
+    machine without a GPU (tests inject a checker there); the product path always uses the CUDA kernels."""
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    x_shard, y_shard = _need_cuda_f32(x_shard), _need_cuda_f32(y_shard)
+    if _knn is None:
+        x_shard, y_shard = _need_cuda_f32(x_shard), _need_cuda_f32(y_shard)
+    knn_fn = _knn or knn
+    margin_fn = _margin_predict or margin_predict
     ns, d = x_shard.shape
     x_all = torch.empty((world * ns, d), dtype=torch.float32, device=x_shard.device)
     y_all = torch.empty((world * ns, d), dtype=torch.float32, device=x_shard.device)
     dist.all_gather_into_tensor(x_all, x_shard, group=group)  # the exchange step: [N,1024] on every rank
     dist.all_gather_into_tensor(y_all, y_shard, group=group)
-    val_xy, idx_xy = knn(x_shard, y_all, k)  # this rank's query rows against all of y
+    val_xy, idx_xy = knn_fn(x_shard, y_all, k)  # this rank's query rows against all of y
     val_yx_all = None
     if margin != "absolute":
-        val_yx, _ = knn(y_shard, x_all, k)  # reverse direction for this rank's y rows
+        val_yx, _ = knn_fn(y_shard, x_all, k)  # reverse direction for this rank's y rows
         val_yx_all = torch.empty((world * ns, k), dtype=torch.float64, device=x_shard.device)
         dist.all_gather_into_tensor(val_yx_all, val_yx, group=group)  # tiny: [N,k] fp64
-    pred = margin_predict(val_xy, idx_xy, val_yx_all, world * ns, margin)
+    pred = margin_fn(val_xy, idx_xy, val_yx_all, world * ns, margin)
     target = torch.arange(rank * ns, (rank + 1) * ns, device=pred.device)
     err = (pred.long() != target).sum()
     dist.all_reduce(err, group=group)
