@@ -35,6 +35,12 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) 
   return lo | (hi << 32);
 }
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(kThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* __restrict__ cu, int B, int H,
                     __nv_bfloat16* __restrict__ out) {
@@ -148,38 +154,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* _
       const int len = cu[b + 1] - tok0;  // 1..128 (host guarantees max_len <= 128)
       mbar_wait(bar_s, ph);
       tc_fence_after();
-      // pass 1: row maximum over the valid keys
-      float mx = -CUDART_INF_F;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        if (c * 32 >= len) break;
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
-        tmem_ld_wait();
+      // the whole S row (128 fp32) lives in registers: one batch of TMEM loads, one wait
+      const int nch = (len + 31) >> 5;  // 32-key chunks that hold valid keys (CTA-uniform)
+      uint32_t v[4][32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c * 32 + j < len) mx = fmaxf(mx, __uint_as_float(v[j]));
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_s + lane_base + c * 32, v[c]);  // stale columns are masked below
+      tmem_ld_wait();
+      float mx = -CUDART_INF_F;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c * 32 + 32 > len) {  // chunk reaches past the sentence: keys >= len -> -inf -> probability exactly 0
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j >= len) v[c][j] = __float_as_uint(-CUDART_INF_F);
+        }
+        if (c < nch) {
+          float m0 = __uint_as_float(v[c][0]), m1 = __uint_as_float(v[c][1]);
+#pragma unroll
+          for (int j = 2; j < 32; j += 2) {
+            m0 = fmaxf(m0, __uint_as_float(v[c][j]));
+            m1 = fmaxf(m1, __uint_as_float(v[c][j + 1]));
+          }
+          mx = fmaxf(mx, fmaxf(m0, m1));
+        }
       }
       const float mxs = mx * sl2;
-      // pass 2: p = exp2(s*c - max*c), row sum, bf16 P row -> swizzled K-major smem
-      float sum = 0.f;
+      // p = exp2(s*c - max*c), row sum, bf16 P row -> swizzled K-major smem (zeros beyond the valid chunks)
+      float sum0 = 0.f, sum1 = 0.f;
       uint8_t* prow = sP + row * 128;
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        if (c * 32 < len) {
-          tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
-          tmem_ld_wait();
+        float p[32];
+        if (c < nch) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            p[j] = fast_exp2(fmaf(__uint_as_float(v[c][j]), sl2, -mxs));
+            p[j + 1] = fast_exp2(fmaf(__uint_as_float(v[c][j + 1]), sl2, -mxs));
+            sum0 += p[j];
+            sum1 += p[j + 1];
+          }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0u;
-        }
-        float p[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const bool ok = (c * 32 + j) < len;
-          p[j] = ok ? exp2f(fmaf(__uint_as_float(v[j]), sl2, -mxs)) : 0.f;
-          sum += p[j];
+          for (int j = 0; j < 32; ++j) p[j] = 0.f;
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -189,6 +205,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* _
                          pack_bf16x2(p[8 * q + 4], p[8 * q + 5]), pack_bf16x2(p[8 * q + 6], p[8 * q + 7]));
         }
       }
+      const float sum = sum0 + sum1;
       tc_fence_before();
       fence_proxy_async_smem();  // generic-proxy writes of P -> visible to the tensor core (async proxy)
       __syncwarp();
