@@ -310,9 +310,16 @@ def main():
         flops = 2.0 * T * FFN * D  # algorithmic FLOPs of one launch
         achieved = flops / (kms / 1e3) / 1e12
         peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_gemm_ffn1.json")
+        if os.path.exists(tp) and (B, S) == (BATCH, SEQ):
+            with open(tp) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]  # per launch, from the committed ncu capture
         roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel<cta_group,EPI_BIAS_RELU,bf16> "
                     f"M={T} N={FFN} K={D}", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": f"{peak_kind} bf16_tflops_sustained",
+                    "frac": achieved / peak, "traffic": traffic,
+                    "algorithmic_bytes": 2.0 * T * D + 2.0 * FFN * D + 4.0 * FFN + 2.0 * T * FFN, "peak_source": f"{peak_kind} bf16_tflops_sustained",
                     "ms_per_launch": kms,
                     "whole_step_frac": (value / world) * flops_per_sentence(S) / 1e12 / peak}
         del a, f
