@@ -133,7 +133,28 @@ def dist_env():
     return rank, world, local
 
 
-def cpu_port_throughput(state_dict_cpu, target_seconds: float, sentences_per_step: int = 16):
+def calibrate_cpu_threads() -> int:
+    """Pick the torch intra-op thread count that runs an encoder-layer-shaped fp32 GEMM fastest on this host
+    (more threads than physical cores / NUMA-local memory can be slower); a few seconds."""
+    cores = os.cpu_count() or 1
+    cands = sorted({c for c in (cores, cores // 2, cores // 4, 32, 16, 8) if 1 <= c <= cores}, reverse=True)
+    a = torch.randn(8192, 1024)
+    w = torch.randn(8192, 1024)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        torch.nn.functional.linear(a, w)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.nn.functional.linear(a, w)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
+def cpu_port_throughput(state_dict_cpu, target_seconds: float, sentences_per_step: int = 64):
     """Time the CPU restatement of the reference path (oracle) on a bounded sample of the workload."""
     from oracle.text_encoder import OracleEncoderConfig, OracleTextEncoder
 
@@ -161,13 +182,13 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    calibrate_cpu_threads()
     sd = synthetic_state_dict("cpu", vocab=VOCAB)
     from oracle.text_encoder import OracleEncoderConfig, OracleTextEncoder
 
     torch.set_float32_matmul_precision("high")
     enc = OracleTextEncoder(OracleEncoderConfig(vocab_size=VOCAB, num_layers=LAYERS), sd)
-    per_step = 8
+    per_step = 32
     ids = torch.randint(4, VOCAB, (per_step, SEQ), generator=torch.Generator().manual_seed(0))
     for _ in range(max(args.warmup, 1) if args.warmup < 3 else 3):
         enc(ids, None)
@@ -326,7 +347,7 @@ def main():
 
     cpu_baseline = None
     if sd_cpu is not None:
-        torch.set_num_threads(os.cpu_count() or 1)
+        calibrate_cpu_threads()
         v, n, dt, emb_cpu, ids_cpu = cpu_port_throughput(sd_cpu, args.cpu_seconds)
         got = model(SequenceBatch(ids_cpu.to(dev), None)).sentence_embeddings.cpu().double()
         ref = emb_cpu.double()

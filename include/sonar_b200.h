@@ -154,6 +154,73 @@ int sb_pool(const float* x, const int32_t* cu_seqlens, int32_t B, int32_t D, con
             float eps, int32_t apply_ln, int32_t pool_mode, float* out, float* encoded_padded, int32_t S_padded,
             void* stream);
 
+/* ---- embedding -> text decoder, one incremental step at a time (BASELINE.json config 4) ----
+ * Replaces ConditionalTransformerDecoderModel.decode + project (sonar/nn/conditional_decoder_model.py:60-94,
+ * built by SonarTextDecoderFactory, sonar/models/sonar_text/factory.py:229-315) as driven by fairseq2's
+ * BeamSearchSeq2SeqGenerator inside EmbeddingToTextModelPipeline.predict (sonar/inference_pipelines/text.py:305-346).
+ * State-dict names: sonar/models/sonar_text/handler.py:136-158. */
+typedef struct SbDecoder SbDecoder;
+
+typedef struct SbDecoderConfig {
+  int32_t model_dim;     /* 1024 */
+  int32_t num_layers;    /* 24 */
+  int32_t num_heads;     /* 16 */
+  int32_t ffn_inner_dim; /* 8192 */
+  int32_t input_dim;     /* dimensionality of the sentence embedding; must equal model_dim */
+  int64_t vocab_size;    /* 256206 */
+  int32_t pos_rows;      /* rows of the sinusoidal table (max_seq_len + pad_idx + 1) */
+  int32_t eos_idx;       /* 3 */
+  float ln_eps;          /* 1e-5 */
+  float embed_scale;     /* sqrt(model_dim) */
+} SbDecoderConfig;
+
+/* DEVICE pointers, caller-owned; matrices bf16 [out,in], vectors fp32.  The encoder-decoder attention attends
+ * over ONE key (the sentence embedding), so only its v_proj / output_proj reach the result. */
+typedef struct SbDecoderLayerWeights {
+  const void* wqkv;      /* bf16 [3D, D] self_attn q|k|v */
+  const float* bqkv;
+  const void* wo;        /* self_attn.output_proj */
+  const float* bo;
+  const void* cross_wv;  /* encoder_decoder_attn.v_proj [D, input_dim] */
+  const float* cross_bv;
+  const void* cross_wo;  /* encoder_decoder_attn.output_proj */
+  const float* cross_bo;
+  const void* w1;        /* ffn.inner_proj */
+  const float* b1;
+  const void* w2;        /* ffn.output_proj */
+  const float* b2;
+  const float* ln1_g;    /* self_attn_layer_norm */
+  const float* ln1_b;
+  const float* ln3_g;    /* ffn_layer_norm */
+  const float* ln3_b;
+} SbDecoderLayerWeights;
+
+typedef struct SbDecoderWeights {
+  const void* embed;       /* bf16 [vocab, D] decoder_frontend.embed.weight == final_proj.weight (tied) */
+  const float* pos_table;  /* fp32 [pos_rows, D] */
+  const float* final_ln_g; /* decoder.layer_norm */
+  const float* final_ln_b;
+  const SbDecoderLayerWeights* layers; /* HOST array */
+} SbDecoderWeights;
+
+int sb_decoder_create(const SbDecoderConfig* cfg, const SbDecoderWeights* w, SbDecoder** out);
+void sb_decoder_destroy(SbDecoder* dec);
+/* workspace for num_sentences x beam hypotheses of at most max_len positions (holds the KV caches) */
+int sb_decoder_workspace_bytes(const SbDecoder* dec, int32_t num_sentences, int32_t beam, int32_t max_len, size_t* bytes);
+/* start a batch: embeddings DEVICE fp32 [num_sentences, model_dim]; precomputes the per-layer cross-attention constants */
+int sb_decoder_begin(SbDecoder* dec, const float* embeddings, int32_t num_sentences, int32_t beam, int32_t max_len,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* one decoding step at position t for all R = num_sentences*beam rows (row = sentence*beam + beam_slot):
+ *   tokens  DEVICE int64 [R]           input token of every hypothesis at position t
+ *   table   DEVICE int32 [R, max_len]  table[r, t'] = physical cache row holding position t' < t of hypothesis r
+ *   out_lprob / out_tok DEVICE [R, 16] the 16 most probable next tokens (fp32 log-softmax over the whole vocabulary),
+ *                                      ordered by (log-prob desc, token asc)
+ *   out_eos_lprob DEVICE fp32 [R]      log P(eos) */
+int sb_decoder_step(SbDecoder* dec, const int64_t* tokens, const int32_t* table, int32_t t, int32_t num_sentences,
+                    int32_t beam, int32_t max_len, float* out_lprob, int32_t* out_tok, float* out_eos_lprob,
+                    void* workspace, size_t workspace_bytes, void* stream);
+int sb_decoder_check_inputs(SbDecoder* dec, void* workspace, void* stream);
+
 /* ---- xsim cosine k-NN / margin mining over sentence embeddings (BASELINE.json config 5) ----
  * Not a reference interface: the reference only ever does normalize + matmul
  * (tests/integration_tests/test_text_sonar.py:42,51); algorithm = public LASER xsim. */

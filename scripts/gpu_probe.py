@@ -218,11 +218,75 @@ def stage_xsim():
     print(f"xsim knn {n}x{m}: {med:.2f} ms  {n * m / med / 1e6:.2f} Gpairs/s  GEMM-equivalent {2.0 * n * m * 1024 / med / 1e9:.0f} TFLOP/s")
 
 
+def stage_decoder():
+    from oracle.text_decoder import OracleDecoderConfig, OracleTextDecoder, make_synthetic_decoder_state_dict
+    from sonar_b200 import B200TextDecoderModel, VocabularyInfo, sonar_text_decoder_config
+    V = 4096
+    ocfg = OracleDecoderConfig(vocab_size=V, num_layers=2, max_seq_len=64)
+    sd = make_synthetic_decoder_state_dict(ocfg, seed=2)
+    cfg = sonar_text_decoder_config("basic", num_decoder_layers=2, max_seq_len=64,
+                                    vocab_info=VocabularyInfo(size=V, unk_idx=1, bos_idx=2, eos_idx=3, pad_idx=1))
+    model = B200TextDecoderModel(cfg, sd, DEV)
+    oracle = OracleTextDecoder(ocfg, sd)
+    n, beam, steps = 3, 2, 5
+    emb = torch.randn((n, 1024), generator=torch.Generator().manual_seed(0)) * 0.25
+    toks = torch.randint(4, V, (n * beam, steps), generator=torch.Generator().manual_seed(1))
+    model.begin(emb.to(DEV), beam, 16)
+    r = n * beam
+    table = torch.arange(r, dtype=torch.int32, device=DEV)[:, None].expand(r, 16).contiguous()
+    enc_rows = emb[:, None, :].repeat_interleave(beam, 0)
+    for t in range(steps):
+        lp, tok, eos_lp = model.step(toks[:, t].contiguous().to(DEV), table, t)
+        torch.cuda.synchronize()
+        ref = oracle.step_lprobs(toks[:, :t + 1], enc_rows)
+        d = (lp.cpu() - torch.gather(ref, 1, tok.cpu().long())).abs().max().item()
+        top1 = (tok.cpu()[:, 0].long() == ref.argmax(1)).float().mean().item()
+        print(f"decoder step {t}: max |lprob - oracle| = {d:.4f}  eos err {(eos_lp.cpu() - ref[:, 3]).abs().max().item():.4f} top1 match {top1:.2f}", flush=True)
+    # full-size step timing (config 4: 512 sentences x beam 5, 24 layers, vocab 256206)
+    from bench import synthetic_state_dict  # noqa
+    import time
+    full = sonar_text_decoder_config("basic")
+    g = torch.Generator(device=DEV).manual_seed(3)
+    sdf = {}
+    def rn(*shape, s=0.02):
+        return torch.randn(*shape, generator=g, device=DEV) * s
+    sdf["decoder_frontend.embed.weight"] = rn(256206, 1024, s=1 / 32)
+    for i in range(24):
+        p = f"decoder.layers.{i}."
+        for a in ("self_attn", "encoder_decoder_attn"):
+            for nme in ("q_proj", "k_proj", "v_proj", "output_proj"):
+                sdf[p + f"{a}.{nme}.weight"] = rn(1024, 1024); sdf[p + f"{a}.{nme}.bias"] = rn(1024)
+            sdf[p + f"{a}_layer_norm.weight"] = 1 + rn(1024); sdf[p + f"{a}_layer_norm.bias"] = rn(1024)
+        sdf[p + "ffn.inner_proj.weight"] = rn(8192, 1024); sdf[p + "ffn.inner_proj.bias"] = rn(8192)
+        sdf[p + "ffn.output_proj.weight"] = rn(1024, 8192); sdf[p + "ffn.output_proj.bias"] = rn(1024)
+        sdf[p + "ffn_layer_norm.weight"] = 1 + rn(1024); sdf[p + "ffn_layer_norm.bias"] = rn(1024)
+    sdf["decoder.layer_norm.weight"] = 1 + rn(1024); sdf["decoder.layer_norm.bias"] = rn(1024)
+    big = B200TextDecoderModel(full, sdf, DEV)
+    del sdf
+    n, beam, tmax = 512, 5, 130
+    big.begin(torch.randn((n, 1024), device=DEV) * 0.25, beam, tmax)
+    r = n * beam
+    table = torch.arange(r, dtype=torch.int32, device=DEV)[:, None].expand(r, tmax).contiguous()
+    tk = torch.randint(4, 256000, (r,), device=DEV)
+    for t in (0, 1, 2):
+        big.step(tk, table, t)
+    torch.cuda.synchronize()
+    for t0 in (3, 64, 120):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t in range(t0, t0 + 4):
+            big.step(tk, table, t)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"full-size decoder step at t~{t0}: {e0.elapsed_time(e1) / 4:.2f} ms/step for {r} hypotheses "
+              f"({r / (e0.elapsed_time(e1) / 4) * 1e3:.0f} hyp-tokens/s)", flush=True)
+
+
 if __name__ == "__main__":
     stage = sys.argv[1]
     t0 = time.time()
     print(f"== stage {stage} on {torch.cuda.get_device_name(0)}", flush=True)
     {"elementwise": stage_elementwise, "gemm1": lambda: stage_gemm(1), "gemm2": lambda: stage_gemm(2),
-     "perf": stage_perf, "encoder": stage_encoder, "xsim": stage_xsim, "attn_tc": stage_attn_tc}[stage]()
+     "perf": stage_perf, "encoder": stage_encoder, "xsim": stage_xsim, "attn_tc": stage_attn_tc, "decoder": stage_decoder}[stage]()
     torch.cuda.synchronize()
     print(f"== stage {stage} done in {time.time() - t0:.1f}s", flush=True)

@@ -14,3 +14,4 @@ from .text_encoder import (  # noqa: F401
     VocabularyInfo,
     sonar_text_encoder_config,
 )
+from .text_decoder import B200TextDecoderModel, SonarTextDecoderConfig, sonar_text_decoder_config  # noqa: F401,E402

@@ -37,6 +37,25 @@ class SbEncoderWeights(C.Structure):
                 ("final_ln_b", C.c_void_p), ("layers", C.POINTER(SbLayerWeights))]
 
 
+class SbDecoderConfig(C.Structure):
+    _fields_ = [
+        ("model_dim", C.c_int32), ("num_layers", C.c_int32), ("num_heads", C.c_int32),
+        ("ffn_inner_dim", C.c_int32), ("input_dim", C.c_int32), ("vocab_size", C.c_int64),
+        ("pos_rows", C.c_int32), ("eos_idx", C.c_int32), ("ln_eps", C.c_float), ("embed_scale", C.c_float),
+    ]
+
+
+class SbDecoderLayerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "wqkv", "bqkv", "wo", "bo", "cross_wv", "cross_bv", "cross_wo", "cross_bo", "w1", "b1", "w2", "b2",
+        "ln1_g", "ln1_b", "ln3_g", "ln3_b")]
+
+
+class SbDecoderWeights(C.Structure):
+    _fields_ = [("embed", C.c_void_p), ("pos_table", C.c_void_p), ("final_ln_g", C.c_void_p),
+                ("final_ln_b", C.c_void_p), ("layers", C.POINTER(SbDecoderLayerWeights))]
+
+
 # name -> (restype, argtypes); must list every symbol include/sonar_b200.h declares
 _SIGNATURES = {
     "sb_last_error": (C.c_char_p, []),
@@ -62,6 +81,14 @@ _SIGNATURES = {
                            C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sb_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_float,
                           C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "sb_decoder_create": (C.c_int, [C.POINTER(SbDecoderConfig), C.POINTER(SbDecoderWeights), C.POINTER(C.c_void_p)]),
+    "sb_decoder_destroy": (None, [C.c_void_p]),
+    "sb_decoder_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "sb_decoder_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
+                                   C.c_void_p]),
+    "sb_decoder_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sb_decoder_check_inputs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sb_xsim_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "sb_xsim_knn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

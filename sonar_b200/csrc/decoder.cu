@@ -1,0 +1,465 @@
+// SONAR embedding -> text decoder, one incremental step at a time (BASELINE.json config 4).
+//
+// Reference: ConditionalTransformerDecoderModel.decode/project (sonar/nn/conditional_decoder_model.py:60-94),
+// wiring sonar/models/sonar_text/factory.py:229-315 (pre-LN layers: causal self-attention with a KV cache,
+// encoder-decoder attention, ReLU FFN; final LayerNorm; logits = h . E^T with the tied embedding matrix),
+// driven one token at a time by fairseq2's BeamSearchSeq2SeqGenerator (sonar/inference_pipelines/text.py:305-346).
+//
+// The source is the sentence embedding as a SINGLE encoder position (sonar/models/sonar_translation/model.py:48-53),
+// so every cross-attention softmax is over one key and equals 1: the layer's cross-attention output is the
+// per-sentence constant  c_l = Wo_l (Wv_l e + bv_l) + bo_l  (q/k projections are dead compute).  sb_decoder_begin
+// computes c_l once per sentence with two GEMMs per layer; each step then only adds it.
+//
+// Per step (R = sentences x beam rows, all at the same position t):
+//   x = E[token] * sqrt(d) + pos[t]
+//   24 x { h = LN(x); qkv = h Wqkv^T (tcgen05 GEMM); K/V appended to the cache; attention over positions 0..t
+//          through a per-row ancestry table (beam reordering never moves the cache); x += o Wo^T + bo (TMA reduce-add);
+//          x += c_l[sentence]; h = LN(x); x += W2 relu(W1 h + b1) + b2 }
+//   h = LN_final(x);  logits = h E^T  -- never materialised: the tcgen05 GEMM's sweep epilogue keeps a running
+//   top-16 and an online log-sum-exp per row over all 256 206 columns; a merge kernel turns the per-chunk partials
+//   into the 16 best (log-prob, token) pairs per row plus log P(EOS).
+
+#include "../../include/sonar_b200.h"
+#include "common.cuh"
+#include "sonar_b200_internal.h"
+
+#include <math_constants.h>
+#include <new>
+#include <vector>
+
+namespace sb {
+
+static inline size_t align_up_d(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// x[r,:] = E[token[r],:] * scale + pos[t,:]      (one warp per row)
+__global__ void __launch_bounds__(256)
+decode_embed_kernel(const int64_t* __restrict__ tokens, const __nv_bfloat16* __restrict__ embed, long long vocab,
+                    const float* __restrict__ pos_row, int D, float scale, float* __restrict__ x, int R,
+                    int* __restrict__ err_flag) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  long long id = tokens[r];
+  if (id < 0 || id >= vocab) {
+    if (lane == 0) atomicExch(err_flag, 1);
+    id = 0;
+  }
+  const uint4* erow = reinterpret_cast<const uint4*>(embed + id * (long long)D);
+  const float4* prow = reinterpret_cast<const float4*>(pos_row);
+  float4* xrow = reinterpret_cast<float4*>(x + (long long)r * D);
+  for (int c = lane; c < D / 8; c += 32) {
+    const uint4 e = __ldg(erow + c);
+    const float4 p0 = __ldg(prow + 2 * c), p1 = __ldg(prow + 2 * c + 1);
+    const uint32_t w[4] = {e.x, e.y, e.z, e.w};
+    float f[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+      f[2 * q] = __low2float(v);
+      f[2 * q + 1] = __high2float(v);
+    }
+    xrow[2 * c] = make_float4(fmaf(f[0], scale, p0.x), fmaf(f[1], scale, p0.y), fmaf(f[2], scale, p0.z), fmaf(f[3], scale, p0.w));
+    xrow[2 * c + 1] = make_float4(fmaf(f[4], scale, p1.x), fmaf(f[5], scale, p1.y), fmaf(f[6], scale, p1.z), fmaf(f[7], scale, p1.w));
+  }
+}
+
+// x[r,:] += c[r / beam, :]   (fp32, one warp per row)
+__global__ void __launch_bounds__(256)
+add_sentence_const_kernel(float* __restrict__ x, const float* __restrict__ c, int R, int beam, int D) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  float4* xr = reinterpret_cast<float4*>(x + (long long)r * D);
+  const float4* cr = reinterpret_cast<const float4*>(c + (long long)(r / beam) * D);
+  for (int q = lane; q < D / 4; q += 32) {
+    float4 a = xr[q];
+    const float4 b = __ldg(cr + q);
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    xr[q] = a;
+  }
+}
+
+// fp32 [n, D] -> bf16 (plain cast; A operand of the cross-attention constant GEMMs)
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    *reinterpret_cast<uint2*>(out + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  } else {
+    for (long long j = i; j < n; ++j) out[j] = __float2bfloat16_rn(in[j]);
+  }
+}
+
+// Incremental causal self-attention: one warp per (row, head).  Appends this step's K/V to the cache at
+// position t (physical row r) and attends over positions 0..t, where position t' < t of hypothesis r lives in
+// physical cache row table[r, t'] (its ancestor at that step).
+__global__ void __launch_bounds__(128)
+decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ kcache,
+                        __nv_bfloat16* __restrict__ vcache, const int32_t* __restrict__ table, int t, int Tmax, int H,
+                        __nv_bfloat16* __restrict__ out) {
+  const int r = blockIdx.y;
+  const int h = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (h >= H) return;
+  const int D = H * 64;
+  const __nv_bfloat16* row = qkv + (long long)r * 3 * D + h * 64 + lane * 2;
+  const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(row);
+  const __nv_bfloat162 k2 = *reinterpret_cast<const __nv_bfloat162*>(row + D);
+  const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(row + 2 * D);
+  const long long own = ((long long)r * Tmax + t) * D + h * 64 + lane * 2;
+  *reinterpret_cast<__nv_bfloat162*>(kcache + own) = k2;
+  *reinterpret_cast<__nv_bfloat162*>(vcache + own) = v2;
+  const float q0 = __low2float(q2), q1 = __high2float(q2);
+  const float sl2 = 0.125f * 1.4426950408889634f;
+  float m = -CUDART_INF_F, l = 0.f, a0 = 0.f, a1 = 0.f;
+  const int32_t* trow = table + (long long)r * Tmax;
+  for (int tp = 0; tp <= t; ++tp) {
+    __nv_bfloat162 kk, vv;
+    if (tp == t) {
+      kk = k2;
+      vv = v2;
+    } else {
+      const long long off = ((long long)trow[tp] * Tmax + tp) * D + h * 64 + lane * 2;
+      kk = *reinterpret_cast<const __nv_bfloat162*>(kcache + off);
+      vv = *reinterpret_cast<const __nv_bfloat162*>(vcache + off);
+    }
+    const float s = warp_sum(q0 * __low2float(kk) + q1 * __high2float(kk));
+    const float mn = fmaxf(m, s);
+    const float corr = exp2f((m - mn) * sl2);
+    const float p = exp2f((s - mn) * sl2);
+    l = l * corr + p;
+    a0 = a0 * corr + p * __low2float(vv);
+    a1 = a1 * corr + p * __high2float(vv);
+    m = mn;
+  }
+  const float inv = 1.0f / l;
+  *reinterpret_cast<uint32_t*>(out + (long long)r * D + h * 64 + lane * 2) = pack_bf16x2(a0 * inv, a1 * inv);
+}
+
+// Merge the per-chunk partials of the vocabulary GEMM: one warp per row.
+//   lse = log sum_j exp(logit_j) over all columns; out: 16 best (logit - lse, token), order (value desc, token asc);
+//   eos_lprob = <h, E[eos]> - lse (needed when the generator must force EOS and EOS is not among the 16).
+template <int KC>
+__global__ void __launch_bounds__(256)
+vocab_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, const float* __restrict__ lse_part,
+                   int n_chunks, const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ embed, int D,
+                   int eos_idx, int R, float* __restrict__ out_lprob, int* __restrict__ out_tok,
+                   float* __restrict__ out_eos) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  // ---- log-sum-exp ----
+  float M = -CUDART_INF_F;
+  for (int c = lane; c < n_chunks; c += 32) M = fmaxf(M, lse_part[((long long)r * n_chunks + c) * 2]);
+  M = warp_max(M);
+  float S = 0.f;
+  for (int c = lane; c < n_chunks; c += 32) {
+    const float mc = lse_part[((long long)r * n_chunks + c) * 2];
+    const float sc = lse_part[((long long)r * n_chunks + c) * 2 + 1];
+    if (mc > -CUDART_INF_F) S += sc * __expf(mc - M);
+  }
+  S = warp_sum(S);
+  const float lse = M + logf(S);
+  // ---- top-KC of the n_chunks*KC candidates: every lane keeps a strided slice, then KC rounds of warp arg-max ----
+  const int total = n_chunks * KC;
+  const float* cv = cand_val + (long long)r * total;
+  const int* ci = cand_idx + (long long)r * total;
+  unsigned long long taken = 0ull;  // lane-local bitmap over its slice (slice <= 64 entries: n_chunks <= 128)
+  for (int k = 0; k < KC; ++k) {
+    float bv = -CUDART_INF_F;
+    int bi = 0x7fffffff, bpos = -1;
+    int s = 0;
+    for (int p = lane; p < total; p += 32, ++s) {
+      if (taken & (1ull << s)) continue;
+      const float v = cv[p];
+      const int i = ci[p];
+      if (i < 0) continue;
+      if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; bpos = s; }
+    }
+    // warp arg-max by (value desc, token asc)
+    float wv = bv;
+    int wi = bi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+      if (ov > wv || (ov == wv && oi < wi)) { wv = ov; wi = oi; }
+    }
+    if (bpos >= 0 && bv == wv && bi == wi) taken |= (1ull << bpos);  // token ids are unique -> exactly one lane
+    if (lane == 0) {
+      const bool valid = wi != 0x7fffffff;
+      out_lprob[(long long)r * KC + k] = valid ? (wv - lse) : -CUDART_INF_F;
+      out_tok[(long long)r * KC + k] = valid ? wi : -1;
+    }
+  }
+  // ---- log P(EOS) ----
+  float dot = 0.f;
+  const __nv_bfloat16* hr = h + (long long)r * D;
+  const __nv_bfloat16* er = embed + (long long)eos_idx * D;
+  for (int q = lane * 2; q < D; q += 64) {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(hr + q);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(er + q);
+    dot += __low2float(a) * __low2float(b) + __high2float(a) * __high2float(b);
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) out_eos[r] = dot - lse;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+struct SbDecoder {
+  SbDecoderConfig cfg;
+  const void* embed;
+  const float* pos_table;
+  const float* final_ln_g;
+  const float* final_ln_b;
+  std::vector<SbDecoderLayerWeights> layers;
+  int num_sms;
+};
+
+namespace {
+
+struct DecWs {
+  int32_t* err_flag;
+  float* x;               // [R, D] fp32 residual stream of the current step
+  __nv_bfloat16* h;       // [R, D]
+  __nv_bfloat16* qkv;     // [R, 3D]
+  __nv_bfloat16* f;       // [R, F]
+  float* cross;           // [L, N, D] per-sentence cross-attention constants
+  __nv_bfloat16* ebf;     // [N, D] bf16 sentence embeddings
+  __nv_bfloat16* vtmp;    // [N, D]
+  float* cand_val;        // [R, n_chunks, 16]
+  int* cand_idx;
+  float* lse_part;        // [R, n_chunks, 2]
+  __nv_bfloat16* kcache;  // [L, R, Tmax, D]
+  __nv_bfloat16* vcache;
+  int n_chunks;
+  size_t bytes;
+};
+
+DecWs carve_dec(const SbDecoder* d, int N, int beam, int Tmax, void* base) {
+  const size_t D = d->cfg.model_dim, F = d->cfg.ffn_inner_dim, L = d->cfg.num_layers;
+  const size_t R = (size_t)N * beam;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  DecWs w;
+  auto take = [&](size_t bytes) { uint8_t* q = p + off; off = align_up_d(off + bytes, 1024); return q; };
+  w.n_chunks = gemm_topk_chunks((int)R, (int)d->cfg.vocab_size, 2, d->num_sms);
+  w.err_flag = reinterpret_cast<int32_t*>(take(256));
+  w.x = reinterpret_cast<float*>(take(R * D * 4));
+  w.h = reinterpret_cast<__nv_bfloat16*>(take(R * D * 2));
+  w.qkv = reinterpret_cast<__nv_bfloat16*>(take(R * 3 * D * 2));
+  w.f = reinterpret_cast<__nv_bfloat16*>(take(R * F * 2));
+  w.cross = reinterpret_cast<float*>(take(L * (size_t)N * D * 4));
+  w.ebf = reinterpret_cast<__nv_bfloat16*>(take((size_t)N * D * 2));
+  w.vtmp = reinterpret_cast<__nv_bfloat16*>(take((size_t)N * D * 2));
+  w.cand_val = reinterpret_cast<float*>(take(R * w.n_chunks * kTopkCandidates * 4));
+  w.cand_idx = reinterpret_cast<int*>(take(R * w.n_chunks * kTopkCandidates * 4));
+  w.lse_part = reinterpret_cast<float*>(take(R * w.n_chunks * 2 * 4));
+  w.kcache = reinterpret_cast<__nv_bfloat16*>(take(L * R * (size_t)Tmax * D * 2));
+  w.vcache = reinterpret_cast<__nv_bfloat16*>(take(L * R * (size_t)Tmax * D * 2));
+  w.bytes = off;
+  return w;
+}
+
+int check_ws(const SbDecoder* d, int N, int beam, int Tmax, void* workspace, size_t workspace_bytes, DecWs* out) {
+  if (!d || !workspace) { set_last_error("sb_decoder: null argument"); return SB_ERR_INVALID; }
+  if (N <= 0 || beam <= 0 || Tmax <= 0 || Tmax > d->cfg.pos_rows) {
+    set_last_error("sb_decoder: bad N=%d beam=%d max_len=%d (position table has %d rows)", N, beam, Tmax, d->cfg.pos_rows);
+    return SB_ERR_INVALID;
+  }
+  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023);
+  *out = carve_dec(d, N, beam, Tmax, reinterpret_cast<void*>(base));
+  if (base - reinterpret_cast<uintptr_t>(workspace) + out->bytes > workspace_bytes) {
+    set_last_error("sb_decoder: workspace too small (%zu given, %zu needed)", workspace_bytes,
+                   (size_t)(base - reinterpret_cast<uintptr_t>(workspace)) + out->bytes);
+    return SB_ERR_INVALID;
+  }
+  if (out->n_chunks > 128) { set_last_error("sb_decoder: vocabulary split into too many chunks"); return SB_ERR_INVALID; }
+  return SB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sb_decoder_create(const SbDecoderConfig* cfg, const SbDecoderWeights* w, SbDecoder** out) {
+  if (!cfg || !w || !out) { set_last_error("sb_decoder_create: null argument"); return SB_ERR_INVALID; }
+  *out = nullptr;
+  const int D = cfg->model_dim, H = cfg->num_heads, F = cfg->ffn_inner_dim;
+  if (D <= 0 || D % 256 != 0 || D > 1024 || H <= 0 || D != H * 64 || F <= 0 || F % 256 != 0) {
+    set_last_error("sb_decoder_create: need model_dim %% 256 == 0 (<= 1024), head_dim 64, ffn %% 256 == 0");
+    return SB_ERR_INVALID;
+  }
+  if (cfg->input_dim != D) {
+    set_last_error("sb_decoder_create: input_dim (%d) must equal model_dim (%d)", cfg->input_dim, D);
+    return SB_ERR_INVALID;
+  }
+  if (cfg->num_layers < 0 || cfg->pos_rows <= 0 || cfg->vocab_size <= 0 || cfg->eos_idx < 0 ||
+      cfg->eos_idx >= cfg->vocab_size) {
+    set_last_error("sb_decoder_create: bad num_layers / pos_rows / vocab_size / eos_idx");
+    return SB_ERR_INVALID;
+  }
+  if (!w->embed || !w->pos_table || !w->final_ln_g || !w->final_ln_b || (cfg->num_layers > 0 && !w->layers)) {
+    set_last_error("sb_decoder_create: missing weight pointer");
+    return SB_ERR_INVALID;
+  }
+  int dev = 0, n_gpu = 0;
+  if (cudaGetDeviceCount(&n_gpu) != cudaSuccess || n_gpu == 0) {
+    set_last_error("sb_decoder_create: no CUDA device (this engine has no CPU path)");
+    return SB_ERR_CUDA;
+  }
+  SB_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  SB_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_last_error("sb_decoder_create: sm_100a kernels need a B200-class GPU (found sm_%d%d)", prop.major, prop.minor);
+    return SB_ERR_CUDA;
+  }
+  SbDecoder* d = new (std::nothrow) SbDecoder();
+  if (!d) { set_last_error("out of host memory"); return SB_ERR_INVALID; }
+  d->cfg = *cfg;
+  d->embed = w->embed;
+  d->pos_table = w->pos_table;
+  d->final_ln_g = w->final_ln_g;
+  d->final_ln_b = w->final_ln_b;
+  d->layers.assign(w->layers, w->layers + cfg->num_layers);
+  for (int i = 0; i < cfg->num_layers; ++i) {
+    const SbDecoderLayerWeights& l = d->layers[i];
+    const void* ptrs[] = {l.wqkv, l.bqkv, l.wo, l.bo, l.cross_wv, l.cross_bv, l.cross_wo, l.cross_bo, l.w1, l.b1,
+                          l.w2, l.b2, l.ln1_g, l.ln1_b, l.ln3_g, l.ln3_b};
+    for (const void* q : ptrs)
+      if (!q) {
+        set_last_error("sb_decoder_create: layer %d has a null weight pointer", i);
+        delete d;
+        return SB_ERR_INVALID;
+      }
+  }
+  d->num_sms = prop.multiProcessorCount;
+  *out = d;
+  return SB_OK;
+}
+
+void sb_decoder_destroy(SbDecoder* d) { delete d; }
+
+int sb_decoder_workspace_bytes(const SbDecoder* d, int32_t num_sentences, int32_t beam, int32_t max_len, size_t* bytes) {
+  if (!d || !bytes || num_sentences <= 0 || beam <= 0 || max_len <= 0) {
+    set_last_error("sb_decoder_workspace_bytes: bad argument");
+    return SB_ERR_INVALID;
+  }
+  *bytes = carve_dec(d, num_sentences, beam, max_len, nullptr).bytes + 1024;
+  return SB_OK;
+}
+
+int sb_decoder_begin(SbDecoder* d, const float* embeddings, int32_t N, int32_t beam, int32_t max_len, void* workspace,
+                     size_t workspace_bytes, void* stream_v) {
+  DecWs w;
+  int rc = check_ws(d, N, beam, max_len, workspace, workspace_bytes, &w);
+  if (rc) return rc;
+  if (!embeddings) { set_last_error("sb_decoder_begin: null embeddings"); return SB_ERR_INVALID; }
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const int D = d->cfg.model_dim;
+  SB_CUDA_CHECK(cudaMemsetAsync(w.err_flag, 0, sizeof(int32_t), stream));
+  const long long n = (long long)N * D;
+  cast_bf16_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, stream>>>(embeddings, w.ebf, n);
+  SB_CUDA_CHECK(cudaGetLastError());
+  GemmArgs g;
+  g.cta_group = 2;
+  g.num_sms = d->num_sms;
+  g.M = N;
+  g.K = D;
+  g.N = D;
+  g.lda = D;
+  g.ldw = D;
+  g.ldc = D;
+  g.residual = nullptr;
+  g.ldr = 0;
+  g.epi = EPI_BIAS;
+  for (int li = 0; li < d->cfg.num_layers; ++li) {
+    const SbDecoderLayerWeights& L = d->layers[li];
+    // v = e Wv^T + bv  (bf16), c = v Wo^T + bo (fp32)
+    g.A = w.ebf; g.W = reinterpret_cast<const __nv_bfloat16*>(L.cross_wv); g.C = w.vtmp; g.out_fp32 = 0; g.bias = L.cross_bv;
+    if ((rc = gemm_bf16(g, stream))) return rc;
+    g.A = w.vtmp; g.W = reinterpret_cast<const __nv_bfloat16*>(L.cross_wo); g.C = w.cross + (size_t)li * N * D; g.out_fp32 = 1;
+    g.bias = L.cross_bo;
+    if ((rc = gemm_bf16(g, stream))) return rc;
+  }
+  return SB_OK;
+}
+
+int sb_decoder_step(SbDecoder* d, const int64_t* tokens, const int32_t* table, int32_t t, int32_t N, int32_t beam,
+                    int32_t max_len, float* out_lprob, int32_t* out_tok, float* out_eos_lprob, void* workspace,
+                    size_t workspace_bytes, void* stream_v) {
+  DecWs w;
+  int rc = check_ws(d, N, beam, max_len, workspace, workspace_bytes, &w);
+  if (rc) return rc;
+  if (!tokens || !table || !out_lprob || !out_tok || !out_eos_lprob) { set_last_error("sb_decoder_step: null pointer"); return SB_ERR_INVALID; }
+  if (t < 0 || t >= max_len) { set_last_error("sb_decoder_step: position %d outside [0,%d)", t, max_len); return SB_ERR_INVALID; }
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const int D = d->cfg.model_dim, F = d->cfg.ffn_inner_dim, H = d->cfg.num_heads;
+  const int R = N * beam;
+  if (R > 65535) { set_last_error("sb_decoder_step: too many rows (%d)", R); return SB_ERR_INVALID; }
+  const unsigned row_blocks = (unsigned)((R + 7) / 8);
+  decode_embed_kernel<<<row_blocks, 256, 0, stream>>>(tokens, reinterpret_cast<const __nv_bfloat16*>(d->embed),
+                                                      d->cfg.vocab_size, d->pos_table + (size_t)t * D, D,
+                                                      d->cfg.embed_scale, w.x, R, w.err_flag);
+  SB_CUDA_CHECK(cudaGetLastError());
+  GemmArgs g;
+  g.cta_group = 2;
+  g.num_sms = d->num_sms;
+  g.M = R;
+  const size_t layer_stride = (size_t)R * max_len * D;
+  for (int li = 0; li < d->cfg.num_layers; ++li) {
+    const SbDecoderLayerWeights& L = d->layers[li];
+    if ((rc = layernorm_bf16(w.x, L.ln1_g, L.ln1_b, d->cfg.ln_eps, w.h, R, D, stream))) return rc;
+    g.A = w.h; g.lda = D; g.W = reinterpret_cast<const __nv_bfloat16*>(L.wqkv); g.ldw = D;
+    g.C = w.qkv; g.ldc = 3 * D; g.out_fp32 = 0; g.bias = L.bqkv; g.residual = nullptr; g.ldr = 0;
+    g.N = 3 * D; g.K = D; g.epi = EPI_BIAS;
+    if ((rc = gemm_bf16(g, stream))) return rc;
+    decode_attention_kernel<<<dim3((unsigned)((H + 3) / 4), (unsigned)R), 128, 0, stream>>>(
+        w.qkv, w.kcache + li * layer_stride, w.vcache + li * layer_stride, table, t, max_len, H, w.h);
+    SB_CUDA_CHECK(cudaGetLastError());
+    g.A = w.h; g.lda = D; g.W = reinterpret_cast<const __nv_bfloat16*>(L.wo); g.ldw = D;
+    g.C = w.x; g.ldc = D; g.out_fp32 = 1; g.bias = L.bo; g.residual = w.x; g.ldr = D;
+    g.N = D; g.K = D; g.epi = EPI_BIAS_RESIDUAL;
+    if ((rc = gemm_bf16(g, stream))) return rc;
+    add_sentence_const_kernel<<<row_blocks, 256, 0, stream>>>(w.x, w.cross + (size_t)li * N * D, R, beam, D);
+    SB_CUDA_CHECK(cudaGetLastError());
+    if ((rc = layernorm_bf16(w.x, L.ln3_g, L.ln3_b, d->cfg.ln_eps, w.h, R, D, stream))) return rc;
+    g.A = w.h; g.lda = D; g.W = reinterpret_cast<const __nv_bfloat16*>(L.w1); g.ldw = D;
+    g.C = w.f; g.ldc = F; g.out_fp32 = 0; g.bias = L.b1; g.residual = nullptr; g.ldr = 0;
+    g.N = F; g.K = D; g.epi = EPI_BIAS_RELU;
+    if ((rc = gemm_bf16(g, stream))) return rc;
+    g.A = w.f; g.lda = F; g.W = reinterpret_cast<const __nv_bfloat16*>(L.w2); g.ldw = F;
+    g.C = w.x; g.ldc = D; g.out_fp32 = 1; g.bias = L.b2; g.residual = w.x; g.ldr = D;
+    g.N = D; g.K = F; g.epi = EPI_BIAS_RESIDUAL;
+    if ((rc = gemm_bf16(g, stream))) return rc;
+  }
+  if ((rc = layernorm_bf16(w.x, d->final_ln_g, d->final_ln_b, d->cfg.ln_eps, w.h, R, D, stream))) return rc;
+  if ((rc = gemm_bf16_topk(w.h, D, reinterpret_cast<const __nv_bfloat16*>(d->embed), D, R, (int)d->cfg.vocab_size, D,
+                           w.cand_val, w.cand_idx, w.lse_part, w.n_chunks, 2, d->num_sms, stream)))
+    return rc;
+  vocab_merge_kernel<kTopkCandidates><<<row_blocks, 256, 0, stream>>>(
+      w.cand_val, w.cand_idx, w.lse_part, w.n_chunks, w.h, reinterpret_cast<const __nv_bfloat16*>(d->embed), D,
+      d->cfg.eos_idx, R, out_lprob, out_tok, out_eos_lprob);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return SB_OK;
+}
+
+int sb_decoder_check_inputs(SbDecoder* d, void* workspace, void* stream_v) {
+  if (!d || !workspace) { set_last_error("sb_decoder_check_inputs: null argument"); return SB_ERR_INVALID; }
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023);
+  int32_t flag = 0;
+  SB_CUDA_CHECK(cudaMemcpyAsync(&flag, reinterpret_cast<void*>(base), sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  SB_CUDA_CHECK(cudaStreamSynchronize(stream));
+  if (flag != 0) {
+    set_last_error("token id outside [0, vocab_size) fed to the decoder");
+    return SB_ERR_INPUT;
+  }
+  return SB_OK;
+}
+
+}  // extern "C"

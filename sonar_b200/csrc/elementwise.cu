@@ -22,7 +22,7 @@ static constexpr int kMaxVec = 8;  // float4 per lane -> D <= 1024
 __global__ void __launch_bounds__(256)
 embed_kernel(const int64_t* __restrict__ ids, long long ids_stride, const int32_t* __restrict__ cu, int S,
              const __nv_bfloat16* __restrict__ embed, long long vocab, const float* __restrict__ pos_table, int D,
-             float scale, float* __restrict__ x, int* __restrict__ err_flag) {
+             float scale, float* __restrict__ x, int* __restrict__ err_flag, int pos_offset) {
   const int b = blockIdx.x;
   const int pos = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -35,7 +35,7 @@ embed_kernel(const int64_t* __restrict__ ids, long long ids_stride, const int32_
     id = 0;
   }
   const uint4* erow = reinterpret_cast<const uint4*>(embed + id * (long long)D);
-  const float4* prow = reinterpret_cast<const float4*>(pos_table + (long long)pos * D);
+  const float4* prow = reinterpret_cast<const float4*>(pos_table + (long long)(pos + pos_offset) * D);
   float4* xrow = reinterpret_cast<float4*>(x + (long long)(start + pos) * D);
   for (int c = lane; c < D / 8; c += 32) {
     const uint4 e = __ldg(erow + c);
@@ -60,13 +60,16 @@ embed_kernel(const int64_t* __restrict__ ids, long long ids_stride, const int32_
 
 int embed_tokens(const int64_t* ids, long long ids_stride, const int32_t* cu_seqlens, int B, int S,
                  const __nv_bfloat16* embed, long long vocab, const float* pos_table, int pos_rows, int D, float scale,
-                 float* x, int* err_flag, cudaStream_t stream) {
+                 float* x, int* err_flag, cudaStream_t stream, int pos_offset) {
   if (B <= 0 || S <= 0) return 0;
   if (D % 8 != 0) { set_last_error("embed_tokens: D must be a multiple of 8"); return -1; }
-  if (S > pos_rows) { set_last_error("embed_tokens: S=%d exceeds the position table (%d rows)", S, pos_rows); return -1; }
+  if (S + pos_offset > pos_rows || pos_offset < 0) {
+    set_last_error("embed_tokens: positions [%d,%d) exceed the position table (%d rows)", pos_offset, S + pos_offset, pos_rows);
+    return -1;
+  }
   dim3 grid((unsigned)B, (unsigned)((S + 7) / 8), 1);
   embed_kernel<<<grid, 256, 0, stream>>>(ids, ids_stride, cu_seqlens, S, embed, vocab, pos_table, D, scale, x,
-                                         err_flag);
+                                         err_flag, pos_offset);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

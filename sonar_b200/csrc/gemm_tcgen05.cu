@@ -40,24 +40,48 @@ struct GemmCfg {
   static constexpr int THREADS = 256;
 };
 
-// Work item w of a cluster -> (m_blk, n_blk).  Default: tiles are dealt round-robin with n fastest, so the
-// clusters running concurrently share A rows through L2 and every weight tile stays L2-resident.
-// Sweep (top-k epilogue): a cluster owns whole m-blocks and walks all n tiles of each, so the running
-// top-k of a row can live in the epilogue thread's registers across the entire sweep.
+// Tile scheduler shared by the three warp roles (each role walks an identical copy).
+// Default: tiles are dealt round-robin with n fastest, so the clusters running concurrently share A rows
+// through L2 and every weight tile stays L2-resident.
+// Sweep (top-k epilogue): a work item is (m-block, n-chunk); the cluster walks all n tiles of the chunk so the
+// running top-k / log-sum-exp of a row lives in the epilogue thread's registers for the whole item.  Items of one
+// m-block sit next to each other, and the same chunk of different m-blocks runs concurrently on different
+// clusters, so W streams through L2 once.
 template <bool kSweep>
-__device__ __forceinline__ bool tile_of(int w, int cluster_id, int num_clusters, int num_m_tiles, int num_n_tiles,
-                                        int& m_blk, int& n_blk) {
-  if constexpr (kSweep) {
-    m_blk = cluster_id + (w / num_n_tiles) * num_clusters;
-    n_blk = w % num_n_tiles;
-    return m_blk < num_m_tiles;
-  } else {
-    const int tile = cluster_id + w * num_clusters;
-    m_blk = tile / num_n_tiles;
-    n_blk = tile % num_n_tiles;
-    return tile < num_m_tiles * num_n_tiles;
+struct TileSched {
+  int num_m_tiles, num_n_tiles, cluster_id, num_clusters, n_chunks, tiles_per_chunk;
+  int i = 0, j = 0;
+  __device__ __forceinline__ bool next(int& m_blk, int& n_blk, int& chunk, bool& first, bool& last) {
+    if constexpr (!kSweep) {
+      const int tile = cluster_id + i * num_clusters;
+      ++i;
+      if (tile >= num_m_tiles * num_n_tiles) return false;
+      m_blk = tile / num_n_tiles;
+      n_blk = tile % num_n_tiles;
+      chunk = 0;
+      first = last = true;
+      return true;
+    } else {
+      for (;;) {
+        const int item = cluster_id + i * num_clusters;
+        if (item >= num_m_tiles * n_chunks) return false;
+        m_blk = item / n_chunks;
+        chunk = item % n_chunks;
+        const int n_begin = chunk * tiles_per_chunk;
+        const int cnt = min(tiles_per_chunk, num_n_tiles - n_begin);
+        if (j < cnt) {
+          n_blk = n_begin + j;
+          first = (j == 0);
+          last = (j == cnt - 1);
+          ++j;
+          return true;
+        }
+        j = 0;
+        ++i;
+      }
+    }
   }
-}
+};
 
 // insert (v, idx) into a descending list kept in registers; equal values keep the earlier entry first
 template <int KC>
@@ -81,7 +105,7 @@ __global__ void __launch_bounds__(256, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                          const __grid_constant__ CUtensorMap tm_c, const float* __restrict__ bias,
                          const OutT* residual, long long ldr, int M, int N, int K, float* __restrict__ cand_val,
-                         int* __restrict__ cand_idx) {
+                         int* __restrict__ cand_idx, float* __restrict__ lse_part, int n_chunks) {
   constexpr bool kSweep = (kEpi == EPI_TOPK);
   using Cfg = GemmCfg<kCtaGroup>;
   extern __shared__ uint8_t smem_raw[];
@@ -130,14 +154,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   const int num_kb = K / Cfg::BLOCK_K;
   const int cluster_id = blockIdx.x / kCtaGroup;
   const int num_clusters = gridDim.x / kCtaGroup;
+  TileSched<kSweep> sched{num_m_tiles, num_n_tiles, cluster_id, num_clusters, n_chunks,
+                          (num_n_tiles + n_chunks - 1) / n_chunks};
+  int m_blk, n_blk, chunk;
+  bool first_in_item, last_in_item;
 
   if (warp_idx == 0) {
     // ===================== TMA producer (one thread) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int m_blk, n_blk;
-      for (int w = 0; tile_of<kSweep>(w, cluster_id, num_clusters, num_m_tiles, num_n_tiles, m_blk, n_blk); ++w) {
+      while (sched.next(m_blk, n_blk, chunk, first_in_item, last_in_item)) {
         const int m0 = m_blk * tile_m + int(cta_rank) * Cfg::BLOCK_M;
         const int n0 = n_blk * Cfg::BLOCK_N + int(cta_rank) * Cfg::LOAD_N;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -166,9 +193,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       const uint32_t b_lo0 = (smem_u32(smem_b) >> 4) & 0x3FFFu;
       int stage = 0;
       uint32_t phase = 0;
-      int m_blk, n_blk;
-      for (uint32_t iter = 0;
-           tile_of<kSweep>(int(iter), cluster_id, num_clusters, num_m_tiles, num_n_tiles, m_blk, n_blk); ++iter) {
+      for (uint32_t iter = 0; sched.next(m_blk, n_blk, chunk, first_in_item, last_in_item); ++iter) {
         const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
@@ -202,12 +227,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     constexpr int NUM_CHUNKS = Cfg::BLOCK_N / CHUNK_COLS;
     constexpr int SUBS = CHUNK_COLS / 32;
     int cd_stage = 0;
-    int m_blk, n_blk;
     constexpr int KC = kTopkCandidates;
     [[maybe_unused]] float tv[KC];
     [[maybe_unused]] int ti[KC];
-    for (uint32_t iter = 0;
-         tile_of<kSweep>(int(iter), cluster_id, num_clusters, num_m_tiles, num_n_tiles, m_blk, n_blk); ++iter) {
+    [[maybe_unused]] float run_max = -CUDART_INF_F, run_sum = 0.f;  // online log-sum-exp of the row (optional)
+    for (uint32_t iter = 0; sched.next(m_blk, n_blk, chunk, first_in_item, last_in_item); ++iter) {
       const int m0 = m_blk * tile_m + int(cta_rank) * Cfg::BLOCK_M;
       const int n0 = n_blk * Cfg::BLOCK_N;
       const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
@@ -216,9 +240,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       const int grow = m0 + row_in_tile;
       if constexpr (kEpi == EPI_TOPK) {
         // ---- running per-row top-KC over the whole sweep of n tiles (no C matrix is ever written) ----
-        if (n_blk == 0) {
+        if (first_in_item) {
 #pragma unroll
           for (int p = 0; p < KC; ++p) { tv[p] = -CUDART_INF_F; ti[p] = -1; }
+          run_max = -CUDART_INF_F;
+          run_sum = 0.f;
         }
 #pragma unroll 1
         for (int c = 0; c < Cfg::BLOCK_N / 32; ++c) {
@@ -230,6 +256,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (gcol + j >= N) v[j] = __float_as_uint(-CUDART_INF_F);
+          }
+          if (lse_part != nullptr) {  // online log-sum-exp over every column of the row (fp32, like log_softmax)
+            float cm = __uint_as_float(v[0]);
+#pragma unroll
+            for (int j = 1; j < 32; ++j) cm = fmaxf(cm, __uint_as_float(v[j]));
+            if (cm > run_max) {
+              run_sum *= __expf(run_max - cm);  // exp(-inf) = 0 on the first chunk
+              run_max = cm;
+            }
+            if (run_max > -CUDART_INF_F) {
+              float cs = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) cs += __expf(__uint_as_float(v[j]) - run_max);
+              run_sum += cs;
+            }
           }
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
@@ -251,11 +292,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           if (kCtaGroup == 2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
           else mbar_arrive(&tmem_empty_bar[acc]);
         }
-        if (n_blk == num_n_tiles - 1 && grow < M) {
+        if (last_in_item && grow < M) {
+          const long long slot = (long long)grow * n_chunks + chunk;
 #pragma unroll
           for (int p = 0; p < KC; ++p) {
-            cand_val[(long long)grow * KC + p] = tv[p];
-            cand_idx[(long long)grow * KC + p] = ti[p];
+            cand_val[slot * KC + p] = tv[p];
+            cand_idx[slot * KC + p] = ti[p];
+          }
+          if (lse_part != nullptr) {
+            lse_part[slot * 2] = run_max;
+            lse_part[slot * 2 + 1] = run_sum;
           }
         }
         continue;
@@ -409,7 +455,8 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long ro
 template <int kCtaGroup, int kEpi, typename OutT>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const float* bias,
                        const void* residual, long long ldr, int M, int N, int K, int num_sms, cudaStream_t stream,
-                       float* cand_val = nullptr, int* cand_idx = nullptr) {
+                       float* cand_val = nullptr, int* cand_idx = nullptr, float* lse_part = nullptr,
+                       int n_chunks = 1) {
   using Cfg = GemmCfg<kCtaGroup>;
   auto kern = gemm_bf16_tcgen05_kernel<kCtaGroup, kEpi, OutT>;
   static bool attr_set = false;
@@ -422,7 +469,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   const long long num_tiles = num_m_tiles * ((N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N);
   long long clusters = num_sms / kCtaGroup;
   if (clusters > num_tiles) clusters = num_tiles;
-  if (kEpi == EPI_TOPK && clusters > num_m_tiles) clusters = num_m_tiles;  // a cluster owns whole m-blocks
+  if (kEpi == EPI_TOPK && clusters > num_m_tiles * n_chunks) clusters = num_m_tiles * n_chunks;  // whole items
   if (clusters < 1) clusters = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * kCtaGroup), 1, 1);
@@ -437,17 +484,38 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, bias, reinterpret_cast<const OutT*>(residual), ldr, M, N, K,
-                                   cand_val, cand_idx));
+                                   cand_val, cand_idx, lse_part, n_chunks));
   return 0;
 }
 
+// Number of n-chunks the top-k sweep is split into so that (m-blocks x chunks) fills the clusters.
+int gemm_topk_chunks(int M, int N, int cta_group, int num_sms) {
+  const int cg = (cta_group == 1) ? 1 : 2;
+  const int clusters = (num_sms > 0 ? num_sms : 148) / cg;
+  const int num_m_tiles = (M + 128 * cg - 1) / (128 * cg);
+  const int num_n_tiles = (N + 255) / 256;
+  int want = clusters / num_m_tiles;
+  if (want < 1) want = 1;
+  if (want > num_n_tiles) want = num_n_tiles;
+  const int tpc = (num_n_tiles + want - 1) / want;
+  return (num_n_tiles + tpc - 1) / tpc;  // every chunk non-empty
+}
+
 // Per-row top-kTopkCandidates of A[M,K] . W[N,K]^T (bf16 operands, fp32 accumulate) without materialising
-// the product: cand_val / cand_idx are [M, kTopkCandidates], sorted by value descending.
+// the product.  Outputs are per (row, chunk): cand_val / cand_idx [M, n_chunks, kTopkCandidates] sorted by value
+// descending, and (optional) lse_part [M, n_chunks, 2] = (max, sum exp(v - max)) over the chunk's columns.
 int gemm_bf16_topk(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
-                   float* cand_val, int* cand_idx, int cta_group, int num_sms, cudaStream_t stream) {
+                   float* cand_val, int* cand_idx, float* lse_part, int n_chunks, int cta_group, int num_sms,
+                   cudaStream_t stream) {
   if (M <= 0 || N <= 0) return 0;
   if (K % 64 != 0 || K <= 0) {
     set_last_error("gemm_bf16_topk: K must be a positive multiple of 64 (got %d)", K);
+    return -1;
+  }
+  const int num_n_tiles = (N + 255) / 256;
+  if (n_chunks < 1 || n_chunks > num_n_tiles ||
+      ((num_n_tiles + n_chunks - 1) / n_chunks) * (n_chunks - 1) >= num_n_tiles) {
+    set_last_error("gemm_bf16_topk: invalid n_chunks=%d for %d n-tiles", n_chunks, num_n_tiles);
     return -1;
   }
   const int cg = (cta_group == 1) ? 1 : 2;
@@ -458,9 +526,9 @@ int gemm_bf16_topk(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W
   const int sms = num_sms > 0 ? num_sms : 148;
   if (cg == 2)
     return launch_inst<2, EPI_TOPK, float>(ta, tb, ta /*unused*/, nullptr, nullptr, 0, M, N, K, sms, stream, cand_val,
-                                           cand_idx);
+                                           cand_idx, lse_part, n_chunks);
   return launch_inst<1, EPI_TOPK, float>(ta, tb, ta /*unused*/, nullptr, nullptr, 0, M, N, K, sms, stream, cand_val,
-                                         cand_idx);
+                                         cand_idx, lse_part, n_chunks);
 }
 
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {

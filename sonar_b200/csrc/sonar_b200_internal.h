@@ -38,8 +38,10 @@ struct GemmArgs {
 
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
 
+int gemm_topk_chunks(int M, int N, int cta_group, int num_sms);
 int gemm_bf16_topk(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
-                   float* cand_val, int* cand_idx, int cta_group, int num_sms, cudaStream_t stream);
+                   float* cand_val, int* cand_idx, float* lse_part, int n_chunks, int cta_group, int num_sms,
+                   cudaStream_t stream);
 
 int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld,
                  int box_rows, int box_cols);
@@ -47,7 +49,7 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long ro
 // x[cu[b]+t, :] = E[ids[b,t], :] * scale + pos[t, :]   (fp32 out)
 int embed_tokens(const int64_t* ids, long long ids_stride, const int32_t* cu_seqlens, int B, int S,
                  const __nv_bfloat16* embed, long long vocab, const float* pos_table, int pos_rows, int D, float scale,
-                 float* x, int* err_flag, cudaStream_t stream);
+                 float* x, int* err_flag, cudaStream_t stream, int pos_offset = 0);
 
 // y = LN(x) * gamma + beta, fp32 in, bf16 out, one warp per row
 int layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, __nv_bfloat16* y, long long T,

@@ -176,7 +176,7 @@ int sb_xsim_knn(const float* x, const float* y, int32_t n, int32_t m, int32_t d,
   l2_normalize_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(x, w.xn, w.nx, n, d);
   l2_normalize_kernel<<<(unsigned)((m + 7) / 8), 256, 0, stream>>>(y, w.yn, w.ny, m, d);
   SB_CUDA_CHECK(cudaGetLastError());
-  int rc = gemm_bf16_topk(w.xn, d, w.yn, d, n, m, d, w.cand_val, w.cand_idx, 2, sms, stream);
+  int rc = gemm_bf16_topk(w.xn, d, w.yn, d, n, m, d, w.cand_val, w.cand_idx, nullptr, 1, 2, sms, stream);
   if (rc) return rc;
   rerank_kernel<kTopkCandidates><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(x, y, w.nx, w.ny, w.cand_idx, n, m, d, k,
                                                                              out_val, out_idx);

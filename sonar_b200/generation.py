@@ -1,0 +1,219 @@
+"""Beam search over the B200 decoder -- the part of fairseq2's ``BeamSearchSeq2SeqGenerator`` [fs2] that
+``EmbeddingToTextModelPipeline.predict`` drives (``sonar/inference_pipelines/text.py:315-333``), with the same
+constructor keywords (``beam_size=5, min_gen_len=1, max_gen_len=(1,128), max_seq_len, normalize_scores=True,
+len_penalty=1.0, unk_penalty=0.0``).
+
+All bookkeeping is vectorised ``torch`` on the device (a few [N, 2*beam] tensors per step) with NO host
+synchronisation inside the loop except an "all sentences finished" check every few steps; the model step itself is
+one C-ABI call.  Ordering rule everywhere: score descending, then (beam * vocab + token) ascending -- the rule the
+oracle (``oracle/text_decoder.py::beam_search_step``) defines.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+from torch import Tensor
+
+from .text_decoder import TOPK, B200TextDecoderModel
+
+NEG_INF = float("-inf")
+
+
+@dataclass
+class Hypothesis:
+    seq: Tensor            # generated tokens (prompt stripped unless echo_prompt), final EOS included
+    score: Optional[float]
+
+
+@dataclass
+class Seq2SeqGeneratorOutput:
+    hypotheses: List[List[Hypothesis]]
+
+
+def select_candidates(total: Tensor, tok: Tensor, vocab: int, k: int):
+    """total fp32 [N, B, C] candidate scores, tok int64 [N, B, C] -> the k best per sentence as
+    (score [N,k], beam [N,k], token [N,k]) ordered by (score desc, beam*vocab+token asc)."""
+    n, b, c = total.shape
+    flat = total.reshape(n, b * c)
+    beam_id = torch.arange(b, device=total.device)[None, :, None].expand(n, b, c).reshape(n, b * c)
+    ftok = tok.reshape(n, b * c)
+    key2 = beam_id * vocab + ftok
+    o1 = torch.argsort(key2, dim=1, stable=True)
+    o2 = torch.argsort(torch.gather(flat, 1, o1), dim=1, descending=True, stable=True)[:, :k]
+    sel = torch.gather(o1, 1, o2)
+    return torch.gather(flat, 1, sel), torch.gather(beam_id, 1, sel), torch.gather(ftok, 1, sel)
+
+
+class BeamSearchSeq2SeqGenerator:
+    def __init__(self, model: B200TextDecoderModel, *, beam_size: int = 5, min_gen_len: int = 1,
+                 max_gen_len: Tuple[int, int] = (1, 128), max_seq_len: Optional[int] = None, echo_prompt: bool = False,
+                 normalize_scores: bool = True, temperature: float = 1.0, unk_penalty: float = 0.0,
+                 len_penalty: float = 1.0, pad_idx: int = 0, sync_every: int = 8) -> None:
+        if beam_size < 1:
+            raise ValueError("`beam_size` must be greater than or equal to 1")
+        if 2 * beam_size > TOPK:
+            raise ValueError(f"`beam_size` must be <= {TOPK // 2 - 1} (the decoder step returns the top-{TOPK} tokens per row)")
+        if min_gen_len < 1:
+            raise ValueError("`min_gen_len` must be greater than or equal to 1")
+        if temperature != 1.0:
+            raise NotImplementedError("temperature != 1.0")
+        self.model = model
+        self.beam_size = beam_size
+        self.min_gen_len = min_gen_len
+        self.max_gen_len = max_gen_len
+        self.max_seq_len = max_seq_len
+        self.echo_prompt = echo_prompt
+        self.normalize_scores = normalize_scores
+        self.unk_penalty = unk_penalty
+        self.len_penalty = len_penalty
+        self.pad_idx = pad_idx
+        self.sync_every = sync_every
+
+    @torch.inference_mode()
+    def __call__(self, source_seqs: Tensor, source_padding_mask, prompt_seqs: Tensor, prompt_padding_mask=None
+                 ) -> Seq2SeqGeneratorOutput:
+        m = self.model
+        dev = m.device
+        vi = m.target_vocab_info
+        eos, unk, pad, V = vi.eos_idx, vi.unk_idx, self.pad_idx, vi.size
+        if source_seqs.dim() == 2:
+            source_seqs = source_seqs[:, None, :]  # DummyEncoderModel + encode(): [N,1,D] (model.py:48-53)
+        N = source_seqs.shape[0]
+        B = self.beam_size
+        R = N * B
+        prompt = prompt_seqs.to(dev).long()
+        if prompt.dim() == 1:
+            prompt = prompt[None].expand(N, -1)
+        P = prompt.shape[1]
+        model_max = m.max_target_seq_len
+        max_total = min(self.max_seq_len or model_max, model_max)
+        src_len = source_seqs.shape[1]
+        max_gen = min(int(self.max_gen_len[0] * src_len + self.max_gen_len[1]), max_total - P)
+        if max_gen < 1:
+            raise ValueError("`max_seq_len` leaves no room to generate after the prompt")
+        min_gen = min(self.min_gen_len, max_gen)
+        Tmax = P + max_gen
+        m.begin(source_seqs[:, 0], B, Tmax)
+
+        ar_n = torch.arange(N, device=dev)
+        seqs = torch.full((N, B, Tmax), pad, dtype=torch.int64, device=dev)
+        seqs[:, :, :P] = prompt[:, None, :]
+        table = torch.arange(R, device=dev, dtype=torch.int32)[:, None].expand(R, Tmax).contiguous()
+        cum = torch.zeros((N, B), dtype=torch.float32, device=dev)
+        alive = torch.ones((N, B), dtype=torch.bool, device=dev)
+        done = torch.zeros((N,), dtype=torch.bool, device=dev)
+        CAP = 2 * B
+        fin_score = torch.full((N, CAP + 1), NEG_INF, dtype=torch.float32, device=dev)
+        fin_seq = torch.full((N, CAP + 1, Tmax), pad, dtype=torch.int64, device=dev)
+        fin_len = torch.zeros((N, CAP + 1), dtype=torch.int64, device=dev)
+        fin_count = torch.zeros((N,), dtype=torch.int64, device=dev)
+        rank = torch.arange(2 * B, device=dev)[None, :]
+
+        # prefill: every prompt position but the last only feeds the KV cache
+        for p in range(P - 1):
+            m.step(seqs[:, :, p].reshape(R).contiguous(), table, p)
+
+        tokens = seqs[:, :, P - 1].reshape(R).contiguous()
+        for g in range(max_gen):
+            t = P - 1 + g  # position of the input token; the new token lands at t + 1
+            lp, tok, eos_lp = m.step(tokens, table, t)
+            lp = lp.view(N, B, TOPK)
+            tok = tok.view(N, B, TOPK).long()
+            lp = lp.masked_fill((tok < 0) | (tok == pad), NEG_INF)
+            if self.unk_penalty:
+                lp = torch.where(tok == unk, lp - self.unk_penalty, lp)
+            if g < min_gen:
+                lp = lp.masked_fill(tok == eos, NEG_INF)
+            if g >= max_gen - 1:  # the last allowed token must be EOS
+                lp = torch.full_like(lp, NEG_INF)
+                lp[:, :, 0] = eos_lp.view(N, B)
+                tok = tok.clone()
+                tok[:, :, 0] = eos
+            total = (cum[:, :, None] + lp).masked_fill(~alive[:, :, None], NEG_INF)
+            if g == 0:
+                total[:, 1:, :] = NEG_INF  # all beams are copies of the prompt
+            c_score, c_beam, c_tok = select_candidates(total, tok, V, 2 * B)
+
+            valid = c_score > NEG_INF
+            is_eos = (c_tok == eos) & valid
+            # ---- finalise EOS candidates ranked inside the beam ----
+            fin_mask = is_eos & (rank < B) & ~done[:, None]
+            fin_pos = fin_count[:, None] + torch.cumsum(fin_mask, 1) - 1
+            fin_ok = fin_mask & (fin_pos < CAP)
+            dest = torch.where(fin_ok, fin_pos, torch.full_like(fin_pos, CAP))
+            gen_len = g + 1
+            fscore = c_score / (float(gen_len) ** self.len_penalty) if self.normalize_scores else c_score
+            fin_score.scatter_(1, dest, torch.where(fin_ok, fscore, torch.full_like(fscore, NEG_INF)))
+            cand_seqs = torch.gather(seqs, 1, c_beam[:, :, None].expand(N, 2 * B, Tmax)).clone()
+            cand_seqs[:, :, t + 1] = c_tok
+            fin_seq.scatter_(1, dest[:, :, None].expand(N, 2 * B, Tmax), cand_seqs)
+            fin_len.scatter_(1, dest, torch.full_like(dest, t + 2))
+            fin_score[:, CAP] = NEG_INF
+            fin_count = fin_count + fin_mask.sum(1)
+            # ---- next beam: the first B non-EOS candidates ----
+            keep = valid & ~is_eos & ~done[:, None]
+            kpos = torch.cumsum(keep, 1) - 1
+            keep_ok = keep & (kpos < B)
+            kdest = torch.where(keep_ok, kpos, torch.full_like(kpos, B))
+            new_cum = torch.full((N, B + 1), NEG_INF, dtype=torch.float32, device=dev).scatter_(
+                1, kdest, torch.where(keep_ok, c_score, torch.full_like(c_score, NEG_INF)))[:, :B]
+            new_alive = torch.zeros((N, B + 1), dtype=torch.bool, device=dev).scatter_(1, kdest, keep_ok)[:, :B]
+            new_src = torch.zeros((N, B + 1), dtype=torch.int64, device=dev).scatter_(1, kdest, c_beam)[:, :B]
+            new_tok = torch.full((N, B + 1), pad, dtype=torch.int64, device=dev).scatter_(1, kdest, c_tok)[:, :B]
+            new_src = torch.where(new_alive, new_src, torch.zeros_like(new_src))
+            new_tok = torch.where(new_alive, new_tok, torch.full_like(new_tok, pad))
+            done = done | (fin_count >= B)
+            new_alive = new_alive & ~done[:, None]
+            seqs = torch.gather(seqs, 1, new_src[:, :, None].expand(N, B, Tmax)).clone()
+            seqs[:, :, t + 1] = new_tok
+            src_row = (ar_n[:, None] * B + new_src).reshape(R)
+            table = table.index_select(0, src_row).contiguous()
+            table[:, t] = src_row.to(torch.int32)
+            cum, alive = new_cum, new_alive
+            tokens = new_tok.reshape(R).contiguous()
+            if (g + 1) % self.sync_every == 0 and bool(done.all()):
+                break
+
+        m.check_inputs()
+        # ---- best-first hypotheses (score desc, earlier-finished first on ties) ----
+        order = torch.argsort(fin_score[:, :CAP], dim=1, descending=True, stable=True)[:, :B]
+        s_sorted = torch.gather(fin_score[:, :CAP], 1, order).cpu()
+        l_sorted = torch.gather(fin_len[:, :CAP], 1, order).cpu()
+        q_sorted = torch.gather(fin_seq[:, :CAP], 1, order[:, :, None].expand(N, B, Tmax)).cpu()
+        out: List[List[Hypothesis]] = []
+        start = 0 if self.echo_prompt else P
+        for i in range(N):
+            hyps = []
+            for j in range(B):
+                sc = float(s_sorted[i, j])
+                if sc == NEG_INF:
+                    continue
+                hyps.append(Hypothesis(seq=q_sorted[i, j, start : int(l_sorted[i, j])].clone(), score=sc))
+            out.append(hyps)
+        return Seq2SeqGeneratorOutput(out)
+
+
+class SequenceToTextConverter:
+    """fairseq2 ``SequenceToTextConverter`` [fs2] as used at ``text.py:322-333``: prompt = the tokenizer's target-mode
+    prefix (``[</s>, __lang__]``), output = decoded best hypothesis per input."""
+
+    def __init__(self, generator: BeamSearchSeq2SeqGenerator, tokenizer, task: str, target_lang: Optional[str] = None):
+        self.generator = generator
+        enc = tokenizer.create_encoder(task=task, lang=target_lang, mode="target", device=generator.model.device)
+        prefix = getattr(enc, "prefix_indices", None)
+        if prefix is None:
+            raise ValueError("the tokenizer's target-mode encoder must expose `prefix_indices`")
+        self.prompt = prefix.to(torch.int64)
+        self.text_decoder = tokenizer.create_decoder()
+
+    def batch_convert(self, source_seqs: Tensor, source_padding_mask=None):
+        out = self.generator(source_seqs, source_padding_mask, self.prompt, None)
+        texts = []
+        for i, hyps in enumerate(out.hypotheses):
+            if not hyps:
+                raise RuntimeError(f"the generator returned no hypothesis at index {i}")
+            texts.append(self.text_decoder(hyps[0].seq))
+        return texts, out

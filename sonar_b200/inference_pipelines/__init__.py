@@ -1,1 +1,6 @@
-from .text import TextToEmbeddingModelPipeline, precision_context  # noqa: F401
+from .text import (  # noqa: F401
+    EmbeddingToTextModelPipeline,
+    TextToEmbeddingModelPipeline,
+    TextToTextModelPipeline,
+    precision_context,
+)

@@ -16,6 +16,9 @@ import torch
 from torch import Tensor
 
 from ..batching import collate, dynamic_bucket, prefetch, to_sequence_batch
+from ..batching import bucket
+from ..generation import BeamSearchSeq2SeqGenerator, SequenceToTextConverter
+from ..text_decoder import B200TextDecoderModel, sonar_text_decoder_config
 from ..text_encoder import B200TextEncoderModel, sonar_text_encoder_config
 from .utils import add_progress_bar
 
@@ -182,3 +185,74 @@ class TextToEmbeddingModelPipeline(torch.nn.Module):
             reversed_index = torch.argsort(sorting_index)
             sentence_embeddings = sentence_embeddings[reversed_index.to(sentence_embeddings.device)]
         return sentence_embeddings
+
+
+def _load_decoder_card(name: str, device: Device) -> B200TextDecoderModel:
+    root = os.environ.get("SONAR_B200_CHECKPOINT_DIR")
+    if not root or not (Path(root) / f"{name}.pt").exists():
+        raise FileNotFoundError(
+            f"decoder card {name!r}: set SONAR_B200_CHECKPOINT_DIR to a directory holding {name}.pt "
+            "(fairseq2 state dict under the key 'model'), or pass a B200TextDecoderModel object")
+    return B200TextDecoderModel.from_checkpoint(Path(root) / f"{name}.pt", sonar_text_decoder_config("basic"), device)
+
+
+class EmbeddingToTextModelPipeline(torch.nn.Module):
+    """Mirror of ``sonar.inference_pipelines.text.EmbeddingToTextModelPipeline`` (``text.py:272-346``): sentence
+    embeddings -> text with beam search.  ``self.model`` is the B200 decoder itself: the reference wraps it as
+    ``SonarEncoderDecoderModel(DummyEncoderModel, decoder)`` whose ``encode`` only un-squeezes the embedding to
+    ``[N,1,D]`` (``sonar/models/sonar_translation/model.py:48-53,81-95``); the generator here does that reshape."""
+
+    model: B200TextDecoderModel
+
+    def __init__(self, decoder: Union[str, B200TextDecoderModel], tokenizer, device: Device = CPU,
+                 dtype: Optional[torch.dtype] = None) -> None:
+        super().__init__()
+        if isinstance(decoder, str):
+            decoder = _load_decoder_card(decoder, device if torch.device(device).type == "cuda" else "cuda")
+        if isinstance(tokenizer, str):
+            raise FileNotFoundError(f"tokenizer card {tokenizer!r} cannot be resolved offline; pass a tokenizer object")
+        self.device = torch.device(device)
+        self.tokenizer = tokenizer
+        self.model = decoder.eval()  # type: ignore
+
+    @torch.inference_mode()
+    def predict(self, inputs: Tensor, target_lang: str, batch_size: int = 5, progress_bar: bool = False,
+                sampler=None, **generator_kwargs) -> List[str]:
+        if sampler is not None:
+            raise NotImplementedError("SamplingSeq2SeqGenerator is not part of the B200 path; use beam search")
+        generator_kwargs.setdefault("pad_idx", self.tokenizer.vocab_info.pad_idx)
+        generator = BeamSearchSeq2SeqGenerator(self.model, **generator_kwargs)
+        converter = SequenceToTextConverter(generator, self.tokenizer, task="translation", target_lang=target_lang)
+
+        def _do_translate(src_tensors: List[Tensor]) -> List[str]:
+            texts, _ = converter.batch_convert(torch.stack(src_tensors).to(self.model.device), None)
+            return texts
+
+        pipeline: Iterable = (_do_translate(b) for b in bucket(list(inputs), batch_size))
+        if progress_bar:
+            pipeline = add_progress_bar(pipeline, inputs=inputs, batch_size=batch_size)
+        with precision_context(self.model.dtype):
+            results: List[List[str]] = list(iter(pipeline))
+        return [x for y in results for x in y]
+
+
+class TextToTextModelPipeline(torch.nn.Module):
+    """Mirror of ``TextToTextModelPipeline`` (``text.py:57-137``): encode with the B200 encoder, decode with the B200
+    decoder.  ``max_seq_len`` is clamped to the decoder's position table like the reference (``:102-107``)."""
+
+    def __init__(self, encoder: Union[str, B200TextEncoderModel], decoder: Union[str, B200TextDecoderModel], tokenizer,
+                 device: Device = CPU, dtype: Optional[torch.dtype] = None) -> None:
+        super().__init__()
+        self.t2vec = TextToEmbeddingModelPipeline(encoder, tokenizer, device=device, dtype=None)
+        self.vec2text = EmbeddingToTextModelPipeline(decoder, tokenizer, device=device, dtype=None)
+        self.tokenizer = tokenizer
+
+    @torch.inference_mode()
+    def predict(self, input: Union[Path, Sequence[str]], source_lang: str, target_lang: str, batch_size: int = 5,
+                progress_bar: bool = False, **generator_kwargs) -> List[str]:
+        generator_kwargs = generator_kwargs or {}
+        model_max_seq_len = self.vec2text.model.decoder_frontend.pos_encoder.max_seq_len
+        generator_kwargs["max_seq_len"] = min(model_max_seq_len, generator_kwargs.get("max_seq_len", model_max_seq_len))
+        emb = self.t2vec.predict(input, source_lang=source_lang, batch_size=batch_size, progress_bar=progress_bar)
+        return self.vec2text.predict(emb, target_lang=target_lang, batch_size=batch_size, progress_bar=progress_bar,
+                                     **generator_kwargs)

@@ -27,11 +27,25 @@ _NUM_LANG_SLOTS = 202
 
 
 class _TokenEncoder:
-    def __init__(self, fn: Callable[[str], List[int]]) -> None:
+    """``prefix_indices`` / ``suffix_indices`` mirror fairseq2's text encoders: in NLLB *target* mode the prefix is
+    ``[</s>, __lang__]`` -- the decoder prompt ``SequenceToTextConverter`` feeds the generator."""
+
+    def __init__(self, fn: Callable[[str], List[int]], prefix: Optional[List[int]] = None,
+                 suffix: Optional[List[int]] = None) -> None:
         self._fn = fn
+        self.prefix_indices = torch.tensor(prefix, dtype=torch.int64) if prefix is not None else None
+        self.suffix_indices = torch.tensor(suffix, dtype=torch.int64) if suffix is not None else None
 
     def __call__(self, text: str) -> Tensor:
         return torch.tensor(self._fn(text), dtype=torch.int64)
+
+
+class _TokenDecoder:
+    def __init__(self, fn: Callable[[List[int]], str]) -> None:
+        self._fn = fn
+
+    def __call__(self, ids: Tensor) -> str:
+        return self._fn([int(i) for i in ids.tolist()])
 
 
 class SyntheticTokenizer:
@@ -60,7 +74,20 @@ class SyntheticTokenizer:
                        device=None, pin_memory: bool = False) -> _TokenEncoder:
         if lang is None:
             raise ValueError("`lang` is required")
-        return _TokenEncoder(lambda text: self._encode(text, lang))
+        eos = self.vocab_info.eos_idx
+        if mode == "target":  # [</s>, __lang__] pieces... </s>
+            return _TokenEncoder(lambda text: [eos] + self._encode(text, lang), prefix=[eos, self.lang_id(lang)],
+                                 suffix=[eos])
+        return _TokenEncoder(lambda text: self._encode(text, lang), prefix=[self.lang_id(lang)], suffix=[eos])
+
+    def create_decoder(self) -> "_TokenDecoder":
+        """ids -> text; control symbols are dropped, every piece id prints as ``t<id>`` (the hash is one-way)."""
+        lo, hi = 4, self._lang_base
+
+        def dec(ids: List[int]) -> str:
+            return " ".join(f"t{i}" for i in ids if lo <= i < hi)
+
+        return _TokenDecoder(dec)
 
 
 class NllbTokenizer:
@@ -87,4 +114,15 @@ class NllbTokenizer:
             # SPM ids: <unk>=0,<s>=1,</s>=2 then pieces; NLLB/fairseq2 ids: pad0 unk1 bos2 eos3 then pieces (+1)
             return [lang_id] + [i + 1 for i in sp.encode(text)] + [3]
 
-        return _TokenEncoder(enc)
+        if mode == "target":
+            return _TokenEncoder(lambda text: [3] + enc(text), prefix=[3, lang_id], suffix=[3])
+        return _TokenEncoder(enc, prefix=[lang_id], suffix=[3])
+
+    def create_decoder(self) -> "_TokenDecoder":
+        sp = self._sp
+        n = sp.get_piece_size()
+
+        def dec(ids: List[int]) -> str:
+            return sp.decode([i - 1 for i in ids if 4 <= i <= n])
+
+        return _TokenDecoder(dec)

@@ -1,0 +1,123 @@
+"""CUDA decoder (sb_decoder_begin / sb_decoder_step through B200TextDecoderModel) against the fp32 CPU oracle
+(oracle/text_decoder.py) on shared seeded synthetic weights -- BASELINE.json config 4 at sizes the oracle finishes
+in seconds.  bf16 operands vs the fp32 oracle: log-probabilities agree to 3e-2 absolute (logit scale ~1; stated per
+check); the beam-search BOOKKEEPING is held to exact equality in tests/test_oracle_decoder.py (CPU)."""
+
+import math
+
+import pytest
+import torch
+
+from oracle.text_decoder import (BeamSearchConfig, OracleDecoderConfig, OracleTextDecoder, beam_search,
+                                 make_synthetic_decoder_state_dict)
+
+pytestmark = pytest.mark.gpu
+
+VOCAB = 4096
+
+
+@pytest.fixture(scope="module")
+def small(native_lib, cuda_device):
+    from sonar_b200 import B200TextDecoderModel, VocabularyInfo, sonar_text_decoder_config
+
+    ocfg = OracleDecoderConfig(vocab_size=VOCAB, num_layers=2, max_seq_len=64)
+    sd = make_synthetic_decoder_state_dict(ocfg, seed=2)
+    sd["decoder_frontend.embed.weight"] *= 3.0  # peakier next-token distributions
+    sd["final_proj.weight"] = sd["decoder_frontend.embed.weight"]
+    cfg = sonar_text_decoder_config("basic", num_decoder_layers=2, max_seq_len=64,
+                                    vocab_info=VocabularyInfo(size=VOCAB, unk_idx=1, bos_idx=2, eos_idx=3, pad_idx=1))
+    return OracleTextDecoder(ocfg, sd), B200TextDecoderModel(cfg, sd, cuda_device)
+
+
+def _emb(n, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn((n, 1024), generator=g) * 0.25 / math.sqrt(1024) * 32.0
+
+
+def test_teacher_forced_steps_match_oracle(small, cuda_device):
+    oracle, model = small
+    n, beam, steps = 3, 2, 9
+    emb = _emb(n)
+    g = torch.Generator().manual_seed(1)
+    toks = torch.randint(4, VOCAB, (n * beam, steps), generator=g)
+    model.begin(emb.to(cuda_device), beam, 16)
+    r = n * beam
+    table = torch.arange(r, dtype=torch.int32, device=cuda_device)[:, None].expand(r, 16).contiguous()
+    enc_rows = emb[:, None, :].repeat_interleave(beam, 0)
+    for t in range(steps):
+        lp, tok, eos_lp = model.step(toks[:, t].contiguous().to(cuda_device), table, t)
+        ref = oracle.step_lprobs(toks[:, : t + 1], enc_rows)  # [R, V] fp32
+        lp, tok, eos_lp = lp.cpu(), tok.cpu().long(), eos_lp.cpu()
+        # the returned candidates carry the right log-probs ...
+        torch.testing.assert_close(lp, torch.gather(ref, 1, tok), rtol=0, atol=3e-2)
+        torch.testing.assert_close(eos_lp, ref[:, 3], rtol=0, atol=3e-2)
+        # ... are sorted, normalised over the WHOLE vocabulary, and contain the oracle's arg-max
+        assert bool((lp[:, :-1] >= lp[:, 1:]).all())
+        assert bool((tok == ref.argmax(1, keepdim=True)).any(1).all())
+        # the 16th-best oracle value bounds what may be missing from the candidate list
+        kth = ref.topk(16, dim=1).values[:, -1:]
+        assert bool((lp[:, -1:] >= kth - 6e-2).all())
+
+
+def test_beam_reordering_through_the_ancestry_table(small, cuda_device):
+    """Hypothesis r continues from a DIFFERENT physical row: results must equal decoding that token history directly."""
+    oracle, model = small
+    n, beam = 2, 3
+    r = n * beam
+    emb = _emb(n, seed=4)
+    g = torch.Generator().manual_seed(2)
+    hist = torch.randint(4, VOCAB, (r, 3), generator=g)
+    model.begin(emb.to(cuda_device), beam, 8)
+    table = torch.arange(r, dtype=torch.int32, device=cuda_device)[:, None].expand(r, 8).contiguous()
+    for t in range(2):
+        model.step(hist[:, t].contiguous().to(cuda_device), table, t)
+    src = torch.tensor([1, 1, 0, 5, 3, 3])  # new row r descends from old row src[r] (within its sentence)
+    table2 = table.index_select(0, src.to(cuda_device)).contiguous()
+    table2[:, 1] = src.to(cuda_device).to(torch.int32)
+    table2[:, 0] = src.to(cuda_device).to(torch.int32)
+    new_tok = hist[:, 2]
+    lp, tok, _ = model.step(new_tok.contiguous().to(cuda_device), table2, 2)
+    seqs = torch.cat([hist[src, :2], new_tok[:, None]], 1)
+    ref = oracle.step_lprobs(seqs, emb[:, None, :].repeat_interleave(beam, 0))
+    torch.testing.assert_close(lp.cpu(), torch.gather(ref, 1, tok.cpu().long()), rtol=0, atol=3e-2)
+
+
+def test_generation_is_near_optimal_and_scores_are_honest(small, cuda_device):
+    from sonar_b200.generation import BeamSearchSeq2SeqGenerator
+
+    oracle, model = small
+    n, beam, max_gen = 6, 4, 8
+    emb = _emb(n, seed=7)
+    prompt = torch.tensor([3, 4000])
+    gen = BeamSearchSeq2SeqGenerator(model, beam_size=beam, max_gen_len=(0, max_gen), pad_idx=0)
+    out = gen(emb.to(cuda_device), None, prompt, None)
+    enc1 = emb[:, None, :]
+    ref = beam_search(lambda toks: oracle.step_lprobs(toks, enc1.repeat_interleave(beam, 0)), prompt, n,
+                      BeamSearchConfig(beam_size=beam, max_gen_len=max_gen, pad_idx=0))
+    exact = 0
+    for i in range(n):
+        hyps = out.hypotheses[i]
+        assert len(hyps) >= 1 and int(hyps[0].seq[-1]) == 3  # ends with EOS
+        for h in hyps:  # reported score == oracle score of that very sequence (teacher forced), within bf16 tolerance
+            seq = torch.cat([prompt, h.seq])
+            lps = torch.log_softmax(oracle.logits(seq[None, :-1], enc1[i : i + 1])[0].float(), -1)
+            s = sum(float(lps[p, seq[p + 1]]) for p in range(len(prompt) - 1, len(seq) - 1)) / len(h.seq)
+            assert abs(s - h.score) <= 3e-2, (i, s, h.score)
+        assert hyps[0].score >= ref[i][0][0] - 5e-2  # as good as the oracle's best hypothesis
+        exact += int(hyps[0].seq.tolist() == ref[i][0][1])
+    print("best-hypothesis exact matches vs fp32 oracle:", exact, "/", n)
+
+
+def test_embedding_to_text_pipeline(small, cuda_device):
+    from sonar_b200.inference_pipelines import EmbeddingToTextModelPipeline
+    from sonar_b200.tokenizer import SyntheticTokenizer
+
+    _, model = small
+    pipe = EmbeddingToTextModelPipeline(model, SyntheticTokenizer(vocab_size=VOCAB), device=cuda_device)
+    emb = _emb(7, seed=9)
+    texts = pipe.predict(emb, target_lang="fra_Latn", batch_size=3, max_seq_len=12)
+    assert len(texts) == 7 and all(isinstance(t, str) for t in texts)
+    again = pipe.predict(emb, target_lang="fra_Latn", batch_size=7, max_seq_len=12)
+    assert texts == again  # batch composition does not change the result
+    with pytest.raises(ValueError):
+        pipe.predict(emb, target_lang="fra_Latn", max_seq_len=2)  # no room after the 2-token prompt

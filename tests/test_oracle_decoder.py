@@ -1,0 +1,113 @@
+"""CPU tests for the decoder row (BASELINE.json config 4):
+* the oracle decoder against the committed HuggingFace M2M100Decoder golden (independent implementation);
+* the PRODUCT beam-search bookkeeping (sonar_b200/generation.py, pure torch host logic) against the oracle's
+  sequential restatement, by driving it with a stand-in model whose step() serves the oracle's log-probs through the
+  same top-16 + ancestry-table interface the CUDA decoder has."""
+
+import math
+import os
+
+import pytest
+import torch
+
+from oracle.text_decoder import (BeamSearchConfig, OracleDecoderConfig, OracleTextDecoder, beam_search,
+                                 make_synthetic_decoder_state_dict)
+from sonar_b200.generation import BeamSearchSeq2SeqGenerator, select_candidates
+from sonar_b200.text_encoder import VocabularyInfo
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "m2m100_decoder_small.pt")
+
+
+def test_oracle_decoder_matches_m2m100_golden():
+    g = torch.load(GOLDEN, weights_only=True)
+    dec = OracleTextDecoder(OracleDecoderConfig(**g["config"]), g["state_dict"])
+    torch.testing.assert_close(dec.hidden(g["tokens"], g["encoder_output"]), g["hidden"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(dec.logits(g["tokens"], g["encoder_output"]), g["logits"], rtol=1e-5, atol=2e-5)
+
+
+def test_cross_attention_over_one_key_is_a_constant():
+    """The identity the CUDA decoder relies on: with a single encoder position the cross-attention output does not
+    depend on the query (softmax over one key == 1)."""
+    cfg = OracleDecoderConfig(model_dim=64, vocab_size=50, num_layers=1, num_heads=1, ffn_inner_dim=128)
+    sd = make_synthetic_decoder_state_dict(cfg, seed=3, weight_std=0.3)
+    dec = OracleTextDecoder(cfg, sd)
+    enc = torch.randn(2, 1, 64)
+    p = "decoder.layers.0.encoder_decoder_attn."
+    a = dec._mha(p, torch.randn(2, 5, 64), enc, None)
+    const = torch.nn.functional.linear(
+        torch.nn.functional.linear(enc, sd[p + "v_proj.weight"], sd[p + "v_proj.bias"]),
+        sd[p + "output_proj.weight"], sd[p + "output_proj.bias"])
+    torch.testing.assert_close(a, const.expand(2, 5, 64), rtol=1e-5, atol=1e-5)
+
+
+def test_select_candidates_order_with_ties():
+    total = torch.tensor([[[0.5, 0.5, -1.0], [0.5, float("-inf"), 0.2]]])  # [1, 2 beams, 3]
+    tok = torch.tensor([[[7, 3, 9], [2, 5, 7]]])
+    s, b, t = select_candidates(total, tok, vocab=10, k=4)
+    # score desc, then beam*V+token asc: (0.5,b0,t3) (0.5,b0,t7) (0.5,b1,t2) (0.2,b1,t7)
+    assert t.tolist() == [[3, 7, 2, 7]] and b.tolist() == [[0, 0, 1, 1]]
+    assert s.tolist() == [[0.5, 0.5, 0.5, pytest.approx(0.2)]]
+
+
+class _OracleBackedModel:
+    """Serves oracle log-probs through the CUDA decoder's interface (top-16 per row + ancestry table)."""
+
+    def __init__(self, dec: OracleTextDecoder, vocab: VocabularyInfo, max_len: int):
+        self.dec, self.target_vocab_info, self.max_target_seq_len = dec, vocab, max_len
+        self.device = torch.device("cpu")
+
+    def begin(self, emb, beam, max_len):
+        self.enc = emb.reshape(emb.shape[0], 1, -1).repeat_interleave(beam, 0)
+        self.hist = {}
+
+    def step(self, tokens, table, t):
+        self.hist[t] = tokens.clone()
+        r = tokens.shape[0]
+        seq = torch.stack([self.hist[tp][table[:, tp].long()] for tp in range(t)] + [tokens], 1) if t > 0 else tokens[:, None]
+        lp = self.dec.step_lprobs(seq, self.enc)
+        order = torch.argsort(-lp, dim=1, stable=True)[:, :16]  # value desc, token asc
+        return torch.gather(lp, 1, order), order.to(torch.int32), lp[:, self.target_vocab_info.eos_idx].clone()
+
+    def check_inputs(self):
+        pass
+
+
+@pytest.mark.parametrize("beam,min_len,max_len,unk_pen", [(1, 1, 6, 0.0), (3, 1, 7, 0.0), (5, 2, 9, 0.5), (4, 1, 3, 0.0)])
+def test_product_beam_search_equals_oracle(beam, min_len, max_len, unk_pen):
+    torch.manual_seed(0)
+    v = 40
+    cfg = OracleDecoderConfig(model_dim=32, vocab_size=v, num_layers=1, num_heads=2, ffn_inner_dim=64, max_seq_len=32)
+    sd = make_synthetic_decoder_state_dict(cfg, seed=5, weight_std=0.4)
+    sd["decoder_frontend.embed.weight"] *= 6.0  # peaky distributions so EOS actually gets chosen
+    sd["final_proj.weight"] = sd["decoder_frontend.embed.weight"]
+    dec = OracleTextDecoder(cfg, sd)
+    n = 4
+    emb = torch.randn(n, 32)
+    prompt = torch.tensor([3, 17])
+    vocab = VocabularyInfo(size=v, unk_idx=1, bos_idx=2, eos_idx=3, pad_idx=1)
+    gen = BeamSearchSeq2SeqGenerator(_OracleBackedModel(dec, vocab, 32), beam_size=beam, min_gen_len=min_len,
+                                     max_gen_len=(0, max_len), unk_penalty=unk_pen, pad_idx=0, sync_every=2)
+    out = gen(emb, None, prompt, None)
+
+    bcfg = BeamSearchConfig(beam_size=beam, min_gen_len=min_len, max_gen_len=max_len, unk_penalty=unk_pen,
+                            pad_idx=0, unk_idx=1, eos_idx=3)
+    enc_rows = emb[:, None, :].repeat_interleave(beam, 0)
+    ref = beam_search(lambda toks: dec.step_lprobs(toks, enc_rows), prompt, n, bcfg)
+    for i in range(n):
+        got = [(h.score, h.seq.tolist()) for h in out.hypotheses[i]]
+        exp = ref[i]
+        assert [g[1] for g in got] == [e[1] for e in exp], (i, got, exp)
+        for (gs, _), (es, _) in zip(got, exp):
+            assert math.isclose(gs, es, rel_tol=1e-5, abs_tol=1e-5)
+
+
+def test_generator_argument_validation():
+    class M:
+        pass
+
+    with pytest.raises(ValueError):
+        BeamSearchSeq2SeqGenerator(M(), beam_size=0)
+    with pytest.raises(ValueError):
+        BeamSearchSeq2SeqGenerator(M(), beam_size=9)  # 2*beam must fit the 16 candidates per row
+    with pytest.raises(ValueError):
+        BeamSearchSeq2SeqGenerator(M(), min_gen_len=0)
