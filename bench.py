@@ -188,7 +188,7 @@ def run_reference(args):
 
     torch.set_float32_matmul_precision("high")
     enc = OracleTextEncoder(OracleEncoderConfig(vocab_size=VOCAB, num_layers=LAYERS), sd)
-    per_step = 32
+    per_step = 16
     ids = torch.randint(4, VOCAB, (per_step, SEQ), generator=torch.Generator().manual_seed(0))
     for _ in range(max(args.warmup, 1) if args.warmup < 3 else 3):
         enc(ids, None)

@@ -93,6 +93,13 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __
 // Incremental causal self-attention: one warp per (row, head).  Appends this step's K/V to the cache at
 // position t (physical row r) and attends over positions 0..t, where position t' < t of hypothesis r lives in
 // physical cache row table[r, t'] (its ancestor at that step).
+//   phase 1: lanes are parallel over keys (each lane owns keys lane, lane+32, ... and does the full 64-dim dot
+//            against q held in registers) -- no shuffles inside the loop;
+//   phase 2: one warp max / sum for the softmax;
+//   phase 3: lanes are parallel over the 64 output dims (2 each); each key's probability and cache row are
+//            broadcast with one shuffle, V rows are read fully coalesced.
+constexpr int kMaxKeyIters = 16;  // positions <= 512 (the decoder's position table)
+
 __global__ void __launch_bounds__(128)
 decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ kcache,
                         __nv_bfloat16* __restrict__ vcache, const int32_t* __restrict__ table, int t, int Tmax, int H,
@@ -102,35 +109,80 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
   const int lane = threadIdx.x & 31;
   if (h >= H) return;
   const int D = H * 64;
-  const __nv_bfloat16* row = qkv + (long long)r * 3 * D + h * 64 + lane * 2;
-  const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(row);
-  const __nv_bfloat162 k2 = *reinterpret_cast<const __nv_bfloat162*>(row + D);
-  const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(row + 2 * D);
-  const long long own = ((long long)r * Tmax + t) * D + h * 64 + lane * 2;
-  *reinterpret_cast<__nv_bfloat162*>(kcache + own) = k2;
-  *reinterpret_cast<__nv_bfloat162*>(vcache + own) = v2;
-  const float q0 = __low2float(q2), q1 = __high2float(q2);
-  const float sl2 = 0.125f * 1.4426950408889634f;
-  float m = -CUDART_INF_F, l = 0.f, a0 = 0.f, a1 = 0.f;
-  const int32_t* trow = table + (long long)r * Tmax;
-  for (int tp = 0; tp <= t; ++tp) {
-    __nv_bfloat162 kk, vv;
-    if (tp == t) {
-      kk = k2;
-      vv = v2;
-    } else {
-      const long long off = ((long long)trow[tp] * Tmax + tp) * D + h * 64 + lane * 2;
-      kk = *reinterpret_cast<const __nv_bfloat162*>(kcache + off);
-      vv = *reinterpret_cast<const __nv_bfloat162*>(vcache + off);
+  const __nv_bfloat16* row = qkv + (long long)r * 3 * D + h * 64;
+  // append this step's K / V (2 dims per lane) to the cache
+  {
+    const __nv_bfloat162 k2 = *reinterpret_cast<const __nv_bfloat162*>(row + D + lane * 2);
+    const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(row + 2 * D + lane * 2);
+    const long long own = ((long long)r * Tmax + t) * D + h * 64 + lane * 2;
+    *reinterpret_cast<__nv_bfloat162*>(kcache + own) = k2;
+    *reinterpret_cast<__nv_bfloat162*>(vcache + own) = v2;
+  }
+  float q[64];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + c * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+      q[c * 8 + 2 * e] = __low2float(b);
+      q[c * 8 + 2 * e + 1] = __high2float(b);
     }
-    const float s = warp_sum(q0 * __low2float(kk) + q1 * __high2float(kk));
-    const float mn = fmaxf(m, s);
-    const float corr = exp2f((m - mn) * sl2);
-    const float p = exp2f((s - mn) * sl2);
-    l = l * corr + p;
-    a0 = a0 * corr + p * __low2float(vv);
-    a1 = a1 * corr + p * __high2float(vv);
-    m = mn;
+  }
+  __syncwarp();  // the row written above is read back below by a single lane
+  const int nk = t + 1;
+  const int32_t* trow = table + (long long)r * Tmax;
+  float sc[kMaxKeyIters];
+  int prow[kMaxKeyIters];
+  float m = -CUDART_INF_F;
+#pragma unroll
+  for (int i = 0; i < kMaxKeyIters; ++i) {
+    sc[i] = -CUDART_INF_F;
+    prow[i] = r;
+    const int tp = i * 32 + lane;
+    if (i * 32 < nk && tp < nk) {
+      prow[i] = (tp == t) ? r : trow[tp];
+      const uint4* kp = reinterpret_cast<const uint4*>(kcache + ((long long)prow[i] * Tmax + tp) * D + h * 64);
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 u = kp[c];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+          d0 = fmaf(q[c * 8 + 2 * e], __low2float(b), d0);
+          d1 = fmaf(q[c * 8 + 2 * e + 1], __high2float(b), d1);
+        }
+      }
+      sc[i] = d0 + d1;
+      m = fmaxf(m, sc[i]);
+    }
+  }
+  m = warp_max(m);
+  const float sl2 = 0.125f * 1.4426950408889634f;
+  float l = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxKeyIters; ++i) {
+    sc[i] = exp2f((sc[i] - m) * sl2);  // exp2(-inf) = 0 for the slots without a key
+    l += sc[i];
+  }
+  l = warp_sum(l);
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxKeyIters; ++i) {
+    if (i * 32 < nk) {
+      const int cnt = min(32, nk - i * 32);
+      for (int j = 0; j < cnt; ++j) {
+        const float p = __shfl_sync(0xffffffffu, sc[i], j);
+        const int pr = __shfl_sync(0xffffffffu, prow[i], j);
+        const __nv_bfloat162 vv = *reinterpret_cast<const __nv_bfloat162*>(
+            vcache + ((long long)pr * Tmax + (i * 32 + j)) * D + h * 64 + lane * 2);
+        a0 = fmaf(p, __low2float(vv), a0);
+        a1 = fmaf(p, __high2float(vv), a1);
+      }
+    }
   }
   const float inv = 1.0f / l;
   *reinterpret_cast<uint32_t*>(out + (long long)r * D + h * 64 + lane * 2) = pack_bf16x2(a0 * inv, a1 * inv);
@@ -397,6 +449,7 @@ int sb_decoder_step(SbDecoder* d, const int64_t* tokens, const int32_t* table, i
   if (rc) return rc;
   if (!tokens || !table || !out_lprob || !out_tok || !out_eos_lprob) { set_last_error("sb_decoder_step: null pointer"); return SB_ERR_INVALID; }
   if (t < 0 || t >= max_len) { set_last_error("sb_decoder_step: position %d outside [0,%d)", t, max_len); return SB_ERR_INVALID; }
+  if (max_len > 32 * kMaxKeyIters) { set_last_error("sb_decoder_step: max_len %d > %d", max_len, 32 * kMaxKeyIters); return SB_ERR_INVALID; }
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   const int D = d->cfg.model_dim, F = d->cfg.ffn_inner_dim, H = d->cfg.num_heads;
   const int R = N * beam;
