@@ -221,6 +221,19 @@ int sb_decoder_step(SbDecoder* dec, const int64_t* tokens, const int32_t* table,
                     void* workspace, size_t workspace_bytes, void* stream);
 int sb_decoder_check_inputs(SbDecoder* dec, void* workspace, void* stream);
 
+/* ---- speech feature frontend (BASELINE.json config 3, rows a9/a10) ----
+ * Replaces fairseq2n WaveformToFbankConverter(num_mel_bins=80, waveform_scale=2**15, channel_last=True,
+ * standardize=True) + Collater(pad_value=0, pad_to_multiple=2) (sonar/inference_pipelines/speech.py:120-127,139,
+ * 283-290,444).  16 kHz mono input. */
+size_t sb_fbank_tables_bytes(void);
+/* fills a HOST buffer of sb_fbank_tables_bytes() (window, FFT twiddles, mel filters); upload it to the device once */
+int sb_fbank_build_tables(void* host_buf);
+/* waves DEVICE fp32 packed samples in [-1,1]; wave_offsets DEVICE int64 [B+1]; frame_offsets DEVICE int32 [B+1]
+ * (cumulative frame counts, frames_b = 1 + (samples_b - 400) / 160); tables DEVICE (see above);
+ * raw_out DEVICE fp32 [total_frames, 80] scratch; out DEVICE fp32 [B, padded_frames, 80] standardised, zero padded */
+int sb_fbank(const float* waves, const int64_t* wave_offsets, const int32_t* frame_offsets, int32_t B,
+             int32_t total_frames, const void* tables, float* raw_out, float* out, int32_t padded_frames, void* stream);
+
 /* ---- xsim cosine k-NN / margin mining over sentence embeddings (BASELINE.json config 5) ----
  * Not a reference interface: the reference only ever does normalize + matmul
  * (tests/integration_tests/test_text_sonar.py:42,51); algorithm = public LASER xsim. */

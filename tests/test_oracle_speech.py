@@ -1,0 +1,44 @@
+"""CPU: the speech-frontend oracle (oracle/speech_frontend.py) against the committed torchaudio Kaldi-fbank golden
+(tests/golden/fbank_golden.pt, make_fbank_golden.py), and the host-built filterbank tables of the CUDA library."""
+
+import os
+
+import torch
+
+from oracle.speech_frontend import (collate_fbank, fbank, mel_banks, num_frames, povey_window, standardize,
+                                    waveform_to_fbank)
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "fbank_golden.pt")
+
+
+def test_oracle_fbank_matches_torchaudio_golden():
+    g = torch.load(GOLDEN, weights_only=True)
+    for w, raw, std in zip(g["waveforms"], g["fbank_raw"], g["fbank_standardized"]):
+        f = fbank(w)
+        assert f.shape == raw.shape == (num_frames(w.numel()), 80)
+        torch.testing.assert_close(f, raw, rtol=0, atol=5e-4)          # log-mel, fp32 FFT round-off
+        torch.testing.assert_close(standardize(f), std, rtol=0, atol=5e-4)
+
+
+def test_frame_count_and_collate():
+    assert num_frames(160000) == 998 and num_frames(400) == 1 and num_frames(399) == 0  # 10 s -> 998
+    feats = [waveform_to_fbank(torch.randn(3000) * 0.1), waveform_to_fbank(torch.randn(1760) * 0.1)]
+    batch, lens = collate_fbank(feats)
+    assert lens == [17, 9] and batch.shape == (2, 18, 80)  # pad_to_multiple=2
+    assert float(batch[0, 17].abs().max()) == 0.0 and float(batch[1, 9:].abs().max()) == 0.0
+
+
+def test_native_tables_match_oracle(native_lib):
+    n = native_lib.sb_fbank_tables_bytes()
+    buf = torch.empty(n, dtype=torch.uint8)
+    assert native_lib.sb_fbank_build_tables(buf.data_ptr()) == 0
+    f, ints = buf.view(torch.float32), buf.view(torch.int32)
+    torch.testing.assert_close(f[:400], povey_window(), rtol=0, atol=1e-7)
+    off = 400 + 2 * 128 + 2 * 256
+    lo, ln = ints[off : off + 80], ints[off + 80 : off + 160]
+    w = f[off + 160 : off + 160 + 80 * 64].view(80, 64)
+    mb = mel_banks()
+    for m in range(80):
+        dense = torch.zeros(257)
+        dense[lo[m] : lo[m] + ln[m]] = w[m, : ln[m]]
+        torch.testing.assert_close(dense, mb[m], rtol=0, atol=1e-7)
