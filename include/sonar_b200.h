@@ -51,6 +51,7 @@ extern "C" {
 #define SB_EPI_BIAS 0
 #define SB_EPI_BIAS_RELU 1
 #define SB_EPI_BIAS_RESIDUAL 2
+#define SB_EPI_BIAS_SILU 5
 
 typedef struct SbEncoder SbEncoder;
 
@@ -233,6 +234,79 @@ int sb_fbank_build_tables(void* host_buf);
  * raw_out DEVICE fp32 [total_frames, 80] scratch; out DEVICE fp32 [B, padded_frames, 80] standardised, zero padded */
 int sb_fbank(const float* waves, const int64_t* wave_offsets, const int32_t* frame_offsets, int32_t B,
              int32_t total_frames, const void* tables, float* raw_out, float* out, int32_t padded_frames, void* stream);
+
+/* ---- speech encoder: w2v-BERT Conformer stack + attention pooler (BASELINE.json config 3, rows a11/a12) ----
+ * Replaces SonarSpeechEncoderModel.forward (sonar/models/sonar_speech/model.py:59-77; factory.py:53-152;
+ * sonar/nn/encoder_pooler.py:70-83); parameter names per sonar/models/sonar_speech/handler.py:63-100. */
+typedef struct SbSpeechEncoder SbSpeechEncoder;
+
+typedef struct SbSpeechConfig {
+  int32_t model_dim;            /* 1024 */
+  int32_t num_layers;           /* 24 Conformer blocks */
+  int32_t num_heads;            /* 16 */
+  int32_t ffn_inner_dim;        /* 4096 */
+  int32_t conv_kernel;          /* 31 */
+  int32_t pooler_layers;        /* 3 (english) / 6 (non_english) */
+  int32_t pooler_ffn_inner_dim; /* 4096 */
+  float ln_eps;                 /* 1e-5 */
+} SbSpeechConfig;
+
+/* every field is a DEVICE pointer (matrices bf16 [out,in]; vectors fp32) */
+typedef struct SbConformerLayerWeights {
+  const float* ffn1_ln_g; const float* ffn1_ln_b;
+  const void* ffn1_w1; const float* ffn1_b1; const void* ffn1_w2 /* x0.5 */; const float* ffn1_b2 /* x0.5 */;
+  const float* attn_ln_g; const float* attn_ln_b;
+  const void* wqkv; const float* bqkv; const void* wo; const float* bo;
+  const void* wr;            /* self_attn.sdpa.r_proj.weight */
+  const float* u_bias;       /* [H*64] */
+  const float* v_bias;
+  const float* conv_ln_g; const float* conv_ln_b;
+  const void* pw1;           /* conv.pointwise_conv1 [2D, D] */
+  const float* dw;           /* conv.depthwise_conv  fp32 [D, 31] */
+  const float* bn_scale;     /* gamma / sqrt(running_var + eps) */
+  const float* bn_shift;     /* beta - running_mean * bn_scale */
+  const void* pw2;           /* conv.pointwise_conv2 [D, D] */
+  const float* ffn2_ln_g; const float* ffn2_ln_b;
+  const void* ffn2_w1; const float* ffn2_b1; const void* ffn2_w2 /* x0.5 */; const float* ffn2_b2 /* x0.5 */;
+  const float* ln_g; const float* ln_b;   /* the block's final layer_norm */
+} SbConformerLayerWeights;
+
+typedef struct SbPoolerLayerWeights {
+  const void* sa_wv; const float* sa_bv; const void* sa_wo; const float* sa_bo;
+  const float* sa_ln_g; const float* sa_ln_b;
+  const void* ca_wq; const float* ca_bq;
+  const void* ca_wkv /* [2D, D] = k_proj | v_proj */; const float* ca_bkv;
+  const void* ca_wo; const float* ca_bo;
+  const float* ca_ln_g; const float* ca_ln_b;
+  const void* w1; const float* b1; const void* w2; const float* b2;
+  const float* ffn_ln_g; const float* ffn_ln_b;
+} SbPoolerLayerWeights;
+
+typedef struct SbSpeechWeights {
+  const float* front_ln_g;  /* encoder_frontend.post_extract_layer_norm [160] */
+  const float* front_ln_b;
+  const void* front_w;      /* encoder_frontend.model_dim_proj, bf16 [D, 192] (columns 160..191 zero) */
+  const float* front_b;
+  const float* final_ln_g;  /* layer_norm (re-homed stack LayerNorm) */
+  const float* final_ln_b;
+  const float* pooler_q0;   /* fp32 [D] = embed[bos] * sqrt(D) + pos[0] */
+  const void* proj_w;       /* encoder_pooler.projection_out.weight bf16 [D, D] */
+  const float* zeros;       /* fp32 zeros, >= max(2D, relpos rows) entries (bias of the bias-free projections) */
+  const SbConformerLayerWeights* layers; /* HOST arrays */
+  const SbPoolerLayerWeights* pooler;
+} SbSpeechWeights;
+
+int sb_speech_encoder_create(const SbSpeechConfig* cfg, const SbSpeechWeights* w, SbSpeechEncoder** out);
+void sb_speech_encoder_destroy(SbSpeechEncoder* enc);
+int sb_speech_encoder_workspace_bytes(const SbSpeechEncoder* enc, int32_t batch, int64_t total_positions,
+                                      int32_t max_positions, size_t* bytes);
+/* fbank DEVICE fp32 [batch, padded_frames, 80] (sb_fbank output); cu_dev DEVICE int32 [batch+1] cumulative positions,
+ * lens_host HOST int32 [batch] positions per utterance (= frames // 2); relpos_table DEVICE bf16 [relpos_rows, D] with
+ * relpos_rows = roundup(2*max_len - 1, 256), row k = sinusoid of relative position (max_len - 1 - k), zero rows after
+ * 2*max_len - 1; out DEVICE fp32 [batch, D]; encoded_packed DEVICE fp32 [total_positions, D] or NULL. */
+int sb_speech_encoder_forward(SbSpeechEncoder* enc, const float* fbank, int32_t padded_frames, const int32_t* cu_dev,
+                              const int32_t* lens_host, int32_t batch, const void* relpos_table, int32_t relpos_rows,
+                              float* out, float* encoded_packed, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- xsim cosine k-NN / margin mining over sentence embeddings (BASELINE.json config 5) ----
  * Not a reference interface: the reference only ever does normalize + matmul

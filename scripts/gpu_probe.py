@@ -282,11 +282,54 @@ def stage_decoder():
               f"({r / (e0.elapsed_time(e1) / 4) * 1e3:.0f} hyp-tokens/s)", flush=True)
 
 
+def stage_speech():
+    from oracle.speech_encoder import OracleSpeechConfig, OracleSpeechEncoder, make_synthetic_speech_state_dict
+    from oracle.speech_frontend import collate_fbank, waveform_to_fbank
+    from sonar_b200 import B200SpeechEncoderModel, PaddingMask, SequenceBatch, sonar_speech_encoder_config
+    from sonar_b200.speech_frontend import WaveformToFbank
+    from tests.helpers import parity_metrics
+    g = torch.Generator().manual_seed(3)
+    waves = [(torch.randn(n, generator=g) * 0.1).clamp(-1, 1) for n in (16000, 9000, 48000)]
+    out, frames = WaveformToFbank(DEV)([w.to(DEV) for w in waves])
+    ref, rl = collate_fbank([waveform_to_fbank(w) for w in waves])
+    print("fbank frames", frames, rl, "max err", (out.cpu() - ref).abs().max().item(), flush=True)
+    frames = [300, 131, 64, 2]
+    fb = torch.zeros((len(frames), 300, 80))
+    for i, n in enumerate(frames):
+        fb[i, :n] = torch.randn((n, 80), generator=g)
+    for (nl, npool) in ((0, 0), (1, 0), (1, 1), (2, 2)):
+        ocfg = OracleSpeechConfig(num_layers=nl, pooler_layers=npool)
+        sd = make_synthetic_speech_state_dict(ocfg, seed=3)
+        model = B200SpeechEncoderModel(sonar_speech_encoder_config("english", num_encoder_layers=nl, num_decoder_layers=npool), sd, DEV)
+        oracle = OracleSpeechEncoder(ocfg, sd)
+        remb, renc, lens = oracle(fb, frames)
+        model.return_encoded_seqs = True
+        o = model(SequenceBatch(fb.to(DEV), PaddingMask(torch.tensor(frames), 300, frames)))
+        torch.cuda.synchronize()
+        st, worst = 0, 0.0
+        for i, n in enumerate(lens):
+            got, exp = o.encoded_seqs[st:st + n].cpu(), renc[i, :n]
+            worst = max(worst, float((got - exp).norm() / exp.norm()))
+            st += n
+        print(f"speech layers={nl} pooler={npool}: encoded rel-L2 max {worst:.4g}; emb", parity_metrics(o.sentence_embeddings, remb), flush=True)
+    # timing at config-3 scale: 64 x 10 s utterances, full 24+3 layers
+    ocfg = OracleSpeechConfig()
+    sd = make_synthetic_speech_state_dict(ocfg, seed=3)
+    model = B200SpeechEncoderModel(sonar_speech_encoder_config("english"), sd, DEV)
+    wv = [(torch.randn(160000, generator=g) * 0.05).clamp(-1, 1).to(DEV) for _ in range(64)]
+    conv = WaveformToFbank(DEV)
+    def run():
+        fbk, fr = conv(wv)
+        return model(SequenceBatch(fbk, PaddingMask(torch.tensor(fr), fbk.shape[1], fr))).sentence_embeddings
+    med, best = timeit(run, iters=3, warm=1)
+    print(f"speech encoder 64 x 10 s (fbank + 24 Conformer + 3 pooler layers): {med:.1f} ms -> {64 / med * 1e3:.0f} utt/s", flush=True)
+
+
 if __name__ == "__main__":
     stage = sys.argv[1]
     t0 = time.time()
     print(f"== stage {stage} on {torch.cuda.get_device_name(0)}", flush=True)
     {"elementwise": stage_elementwise, "gemm1": lambda: stage_gemm(1), "gemm2": lambda: stage_gemm(2),
-     "perf": stage_perf, "encoder": stage_encoder, "xsim": stage_xsim, "attn_tc": stage_attn_tc, "decoder": stage_decoder}[stage]()
+     "perf": stage_perf, "encoder": stage_encoder, "xsim": stage_xsim, "attn_tc": stage_attn_tc, "decoder": stage_decoder, "speech": stage_speech}[stage]()
     torch.cuda.synchronize()
     print(f"== stage {stage} done in {time.time() - t0:.1f}s", flush=True)

@@ -15,3 +15,4 @@ from .text_encoder import (  # noqa: F401
     sonar_text_encoder_config,
 )
 from .text_decoder import B200TextDecoderModel, SonarTextDecoderConfig, sonar_text_decoder_config  # noqa: F401,E402
+from .speech_encoder import B200SpeechEncoderModel, SonarSpeechEncoderConfig, sonar_speech_encoder_config  # noqa: F401,E402

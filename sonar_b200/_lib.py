@@ -56,6 +56,34 @@ class SbDecoderWeights(C.Structure):
                 ("final_ln_b", C.c_void_p), ("layers", C.POINTER(SbDecoderLayerWeights))]
 
 
+class SbSpeechConfig(C.Structure):
+    _fields_ = [("model_dim", C.c_int32), ("num_layers", C.c_int32), ("num_heads", C.c_int32),
+                ("ffn_inner_dim", C.c_int32), ("conv_kernel", C.c_int32), ("pooler_layers", C.c_int32),
+                ("pooler_ffn_inner_dim", C.c_int32), ("ln_eps", C.c_float)]
+
+
+CONFORMER_FIELDS = ("ffn1_ln_g", "ffn1_ln_b", "ffn1_w1", "ffn1_b1", "ffn1_w2", "ffn1_b2", "attn_ln_g", "attn_ln_b",
+                    "wqkv", "bqkv", "wo", "bo", "wr", "u_bias", "v_bias", "conv_ln_g", "conv_ln_b", "pw1", "dw",
+                    "bn_scale", "bn_shift", "pw2", "ffn2_ln_g", "ffn2_ln_b", "ffn2_w1", "ffn2_b1", "ffn2_w2", "ffn2_b2",
+                    "ln_g", "ln_b")
+POOLER_FIELDS = ("sa_wv", "sa_bv", "sa_wo", "sa_bo", "sa_ln_g", "sa_ln_b", "ca_wq", "ca_bq", "ca_wkv", "ca_bkv",
+                 "ca_wo", "ca_bo", "ca_ln_g", "ca_ln_b", "w1", "b1", "w2", "b2", "ffn_ln_g", "ffn_ln_b")
+
+
+class SbConformerLayerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in CONFORMER_FIELDS]
+
+
+class SbPoolerLayerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in POOLER_FIELDS]
+
+
+class SbSpeechWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("front_ln_g", "front_ln_b", "front_w", "front_b", "final_ln_g", "final_ln_b",
+                                          "pooler_q0", "proj_w", "zeros")] + \
+               [("layers", C.POINTER(SbConformerLayerWeights)), ("pooler", C.POINTER(SbPoolerLayerWeights))]
+
+
 # name -> (restype, argtypes); must list every symbol include/sonar_b200.h declares
 _SIGNATURES = {
     "sb_last_error": (C.c_char_p, []),
@@ -93,6 +121,12 @@ _SIGNATURES = {
     "sb_fbank_build_tables": (C.c_int, [C.c_void_p]),
     "sb_fbank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                            C.c_void_p, C.c_int32, C.c_void_p]),
+    "sb_speech_encoder_create": (C.c_int, [C.POINTER(SbSpeechConfig), C.POINTER(SbSpeechWeights), C.POINTER(C.c_void_p)]),
+    "sb_speech_encoder_destroy": (None, [C.c_void_p]),
+    "sb_speech_encoder_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.POINTER(C.c_size_t)]),
+    "sb_speech_encoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                            C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                            C.c_void_p]),
     "sb_xsim_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "sb_xsim_knn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -1,0 +1,620 @@
+// SONAR speech encoder on sm_100a (BASELINE.json config 3):
+//   w2v-BERT frontend (stack 2 fbank frames -> LN(160) -> Linear 160->1024)
+//   -> 24 Conformer blocks -> model.layer_norm -> attention pooler (1 BOS query, POST-LN decoder layers) -> [B,1024]
+// following SonarSpeechEncoderModel.forward (sonar/models/sonar_speech/model.py:59-77), factory.py:53-152,
+// nn/encoder_pooler.py:70-83; parameter names per sonar_speech/handler.py:63-100.
+//
+// Every Linear / pointwise conv is the tcgen05 GEMM of gemm_tcgen05.cu (SiLU / ReLU / bias / x += epilogues; the
+// macaron 0.5 is folded into the FFN output weights on the host, BatchNorm is folded to scale+shift).  Tokens are
+// PACKED (row = cu[b] + t), so padded positions never exist: the reference zeroes them before the depthwise conv and
+// masks them in the softmax; here they are simply out of range.
+//
+// Relative-position attention (Transformer-XL):  score(i,j) = ((q_i+u).k_j + (q_i+v).p_{i-j}) / 8
+//   = (q_i.k_j + u.k_j + q_i.p_{i-j} + v.p_{i-j}) / 8.  p = r_proj(R) is one small GEMM per layer; the term
+//   q_i.p_r + v.p_r for ALL r is one K=64 GEMM per head whose bias vector is v.p_r (written to `bd`, bf16); the
+//   flash kernel then adds bd[i, S-1-i+j] and u.k_j (computed from the K tile in shared memory) to q_i.k_j.
+
+#include "../../include/sonar_b200.h"
+#include "common.cuh"
+#include "sonar_b200_internal.h"
+
+#include <math_constants.h>
+#include <new>
+#include <vector>
+
+namespace sb {
+namespace {
+
+inline size_t align_up_c(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+constexpr int kFeat = 160, kFeatPad = 192;
+
+// ---------------------------------------------------------------------------------------------
+// frontend: row (b,t) = LN(fbank[b, 2t:2t+2, :]) -> bf16 [T, 192] (cols 160..191 zero)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+frontend_ln_kernel(const float* __restrict__ fbank, int Tpad, const int32_t* __restrict__ cu,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   __nv_bfloat16* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int t = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int start = cu[b], len = cu[b + 1] - start;
+  if (t >= len) return;
+  const float* src = fbank + ((long long)b * Tpad + 2 * t) * 80;
+  float v[5];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) { v[i] = src[i * 32 + lane]; s += v[i]; }
+  const float mean = warp_sum(s) / float(kFeat);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) { const float d = v[i] - mean; q += d * d; }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / float(kFeat) + eps);
+  __nv_bfloat16* o = out + (long long)(start + t) * kFeatPad;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int n = i * 32 + lane;
+    o[n] = __float2bfloat16_rn((v[i] - mean) * rstd * gamma[n] + beta[n]);
+  }
+  o[kFeat + lane] = __float2bfloat16_rn(0.f);
+}
+
+// vp[h, n] = sum_d v_bias[h, d] * p[n, h*64 + d]      (one warp per (n, h))
+__global__ void __launch_bounds__(256)
+relpos_bias_kernel(const __nv_bfloat16* __restrict__ p, const float* __restrict__ v_bias, int Npad, int H,
+                   float* __restrict__ vp) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int h = blockIdx.y, lane = threadIdx.x & 31;
+  if (n >= Npad) return;
+  const __nv_bfloat162 pv = *reinterpret_cast<const __nv_bfloat162*>(p + (long long)n * H * 64 + h * 64 + lane * 2);
+  const float s = warp_sum(v_bias[h * 64 + lane * 2] * __low2float(pv) + v_bias[h * 64 + lane * 2 + 1] * __high2float(pv));
+  if (lane == 0) vp[(long long)h * Npad + n] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// relative-position flash attention over packed sequences (mma.sync m16n8k16, online softmax)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src, bool ok) {
+  const int sz = ok ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void ldsm4(uint32_t a, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t a, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t toff(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+
+__global__ void __launch_bounds__(256)
+attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu, int H,
+                        const float* __restrict__ u_bias, const __nv_bfloat16* __restrict__ bd, int Npad, int S_center,
+                        __nv_bfloat16* __restrict__ out) {
+  __shared__ __align__(128) uint8_t sQ[128 * 128];
+  __shared__ __align__(128) uint8_t sK[64 * 128];
+  __shared__ __align__(128) uint8_t sV[64 * 128];
+  __shared__ float s_u[64];
+  __shared__ float s_kb[64];
+  const int qblk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int start = cu[b], len = cu[b + 1] - start;
+  const int q0 = qblk * 128;
+  if (q0 >= len) return;
+  const int D = H * 64;
+  const long long rs = 3ll * D;
+  const __nv_bfloat16* qbase = qkv + (long long)start * rs + h * 64;
+  const __nv_bfloat16* kbase = qbase + D;
+  const __nv_bfloat16* vbase = qbase + 2 * D;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sQa = smem_u32(sQ), sKa = smem_u32(sK), sVa = smem_u32(sV);
+  if (tid < 64) s_u[tid] = u_bias[h * 64 + tid];
+  for (int i = tid; i < 128 * 8; i += 256) {
+    const int r = i >> 3, c = i & 7;
+    const bool ok = (q0 + r) < len;
+    cp16(sQa + toff(r, c), qbase + (long long)(ok ? q0 + r : 0) * rs + c * 8, ok);
+  }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  uint32_t qf[4][4];
+  {
+    const int r = warp * 16 + (lane & 15);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) ldsm4(sQa + toff(r, kk * 2 + (lane >> 4)), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
+  }
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+  float m_run[2] = {-CUDART_INF_F, -CUDART_INF_F}, l_run[2] = {0.f, 0.f};
+  const float sl2 = 0.125f * 1.4426950408889634f;
+  // the two query positions this thread owns, and their rows in the bd buffer
+  const int i_lo = q0 + warp * 16 + (lane >> 2), i_hi = i_lo + 8;
+  const __nv_bfloat16* bd_lo = bd + ((long long)(start + min(i_lo, len - 1)) * H + h) * Npad + (S_center - 1 - i_lo);
+  const __nv_bfloat16* bd_hi = bd + ((long long)(start + min(i_hi, len - 1)) * H + h) * Npad + (S_center - 1 - i_hi);
+  const bool ok_lo = i_lo < len, ok_hi = i_hi < len;
+
+  const int nkb = (len + 63) / 64;
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int k0 = kb * 64;
+    __syncthreads();
+    for (int i = tid; i < 64 * 8; i += 256) {
+      const int r = i >> 3, c = i & 7;
+      const bool ok = (k0 + r) < len;
+      const long long g = (long long)(ok ? k0 + r : 0) * rs + c * 8;
+      cp16(sKa + toff(r, c), kbase + g, ok);
+      cp16(sVa + toff(r, c), vbase + g, ok);
+    }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (tid < 64) {  // u . k_j for the 64 keys of this block
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 u4 = *reinterpret_cast<const uint4*>(sK + toff(tid, c));
+        const uint32_t w[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 k2 = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+          acc = fmaf(s_u[c * 8 + 2 * e], __low2float(k2), acc);
+          acc = fmaf(s_u[c * 8 + 2 * e + 1], __high2float(k2), acc);
+        }
+      }
+      s_kb[tid] = acc;
+    }
+    __syncthreads();
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        const int mtx = lane >> 3;
+        const int key = (jp * 2 + (mtx >> 1)) * 8 + (lane & 7);
+        uint32_t b0, b1, b2, b3;
+        ldsm4(sKa + toff(key, kk * 2 + (mtx & 1)), b0, b1, b2, b3);
+        mma16816(s[jp * 2], qf[kk], b0, b1);
+        mma16816(s[jp * 2 + 1], qf[kk], b2, b3);
+      }
+    }
+    const int kc = (lane & 3) * 2;  // key column inside each 8-key tile
+    float mx[2] = {-CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int kl = j * 8 + kc + (e & 1);  // key index inside the block
+        const int key = k0 + kl;
+        const bool rowok = (e < 2) ? ok_lo : ok_hi;
+        float val = -CUDART_INF_F;
+        if (key < len) {
+          const float pos = rowok ? __bfloat162float(((e < 2) ? bd_lo : bd_hi)[key]) : 0.f;
+          val = s[j][e] + s_kb[kl] + pos;
+        }
+        s[j][e] = val;
+        mx[e >> 1] = fmaxf(mx[e >> 1], val);
+      }
+    }
+    float corr[2], mnew[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      mnew[r] = fmaxf(m_run[r], mx[r]);
+      corr[r] = exp2f((m_run[r] - mnew[r]) * sl2);
+      m_run[r] = mnew[r];
+      l_run[r] *= corr[r];
+    }
+    uint32_t pf[4][4];
+    float ls[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = exp2f((s[j][0] - mnew[0]) * sl2), p1 = exp2f((s[j][1] - mnew[0]) * sl2);
+      const float p2 = exp2f((s[j][2] - mnew[1]) * sl2), p3 = exp2f((s[j][3] - mnew[1]) * sl2);
+      ls[0] += p0 + p1;
+      ls[1] += p2 + p3;
+      pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      o[j][0] *= corr[0]; o[j][1] *= corr[0]; o[j][2] *= corr[1]; o[j][3] *= corr[1];
+    }
+    l_run[0] += ls[0];
+    l_run[1] += ls[1];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        const int mtx = lane >> 3;
+        const int key = kk * 16 + (mtx & 1) * 8 + (lane & 7);
+        uint32_t b0, b1, b2, b3;
+        ldsm4t(sVa + toff(key, jp * 2 + (mtx >> 1)), b0, b1, b2, b3);
+        mma16816(o[jp * 2], pf[kk], b0, b1);
+        mma16816(o[jp * 2 + 1], pf[kk], b2, b3);
+      }
+    }
+  }
+  float inv[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float l = l_run[r];
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    inv[r] = 1.0f / l;
+  }
+  __syncwarp();
+  {
+    const int r0 = warp * 16 + (lane >> 2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int bo = (lane & 3) * 4;
+      *reinterpret_cast<uint32_t*>(sQ + toff(r0, j) + bo) = pack_bf16x2(o[j][0] * inv[0], o[j][1] * inv[0]);
+      *reinterpret_cast<uint32_t*>(sQ + toff(r0 + 8, j) + bo) = pack_bf16x2(o[j][2] * inv[1], o[j][3] * inv[1]);
+    }
+  }
+  __syncwarp();
+  __nv_bfloat16* obase = out + (long long)start * D + h * 64;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = i * 32 + lane;
+    const int r = warp * 16 + (idx >> 3), c = idx & 7;
+    if (q0 + r < len)
+      *reinterpret_cast<uint4*>(obase + (long long)(q0 + r) * D + c * 8) = *reinterpret_cast<const uint4*>(sQ + toff(r, c));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv module middle: GLU -> depthwise conv (k taps, "same", zero outside the utterance) -> BN(scale,shift) -> SiLU
+//   g bf16 [T, 2D] (pointwise_conv1 output: value | gate), out bf16 [T, D]
+// ---------------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(256)
+glu_dwconv_kernel(const __nv_bfloat16* __restrict__ g, const int32_t* __restrict__ cu, int D,
+                  const float* __restrict__ dw, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
+                  __nv_bfloat16* __restrict__ out) {
+  constexpr int TP = 64, HALO = KS / 2, ROWS = TP + KS - 1;
+  __shared__ float tile[ROWS][64];
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, t0 = blockIdx.x * TP;
+  const int start = cu[b], len = cu[b + 1] - start;
+  if (t0 >= len) return;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < ROWS * 32; i += 256) {
+    const int p = i >> 5, cp = (i & 31) * 2;
+    const int pos = t0 - HALO + p;
+    float v0 = 0.f, v1 = 0.f;
+    if (pos >= 0 && pos < len) {
+      const __nv_bfloat16* row = g + (long long)(start + pos) * 2 * D + c0 + cp;
+      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(row);
+      const __nv_bfloat162 gt = *reinterpret_cast<const __nv_bfloat162*>(row + D);
+      v0 = __low2float(a) / (1.0f + __expf(-__low2float(gt)));
+      v1 = __high2float(a) / (1.0f + __expf(-__high2float(gt)));
+    }
+    tile[p][cp] = v0;
+    tile[p][cp + 1] = v1;
+  }
+  __syncthreads();
+  const int c = tid & 63, pg = tid >> 6;  // 4 groups of 16 positions
+  float w[KS];
+#pragma unroll
+  for (int k = 0; k < KS; ++k) w[k] = dw[(long long)(c0 + c) * KS + k];
+  const float sc = bn_scale[c0 + c], sh = bn_shift[c0 + c];
+  for (int pp = 0; pp < 16; ++pp) {
+    const int p = pg * 16 + pp;
+    const int pos = t0 + p;
+    if (pos >= len) break;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) acc = fmaf(w[k], tile[p + k][c], acc);
+    const float y = acc * sc + sh;
+    out[(long long)(start + pos) * D + c0 + c] = __float2bfloat16_rn(y / (1.0f + __expf(-y)));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pooler cross-attention: ONE query per utterance; kv bf16 [T, 2D] (k | v); one warp per (utterance, head)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+pool_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kv,
+                      const int32_t* __restrict__ cu, int H, __nv_bfloat16* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int h = blockIdx.y * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (h >= H) return;
+  const int D = H * 64;
+  const int start = cu[b], len = cu[b + 1] - start;
+  float qv[64];
+  {
+    const __nv_bfloat16* qr = q + (long long)b * D + h * 64;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = *reinterpret_cast<const uint4*>(qr + c * 8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+        qv[c * 8 + 2 * e] = __low2float(t);
+        qv[c * 8 + 2 * e + 1] = __high2float(t);
+      }
+    }
+  }
+  const float sl2 = 0.125f * 1.4426950408889634f;
+  float m = -CUDART_INF_F, l = 0.f, a0 = 0.f, a1 = 0.f;
+  for (int k0 = 0; k0 < len; k0 += 32) {
+    const int key = k0 + lane;
+    float s = -CUDART_INF_F;
+    if (key < len) {
+      const uint4* kp = reinterpret_cast<const uint4*>(kv + (long long)(start + key) * 2 * D + h * 64);
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 u = kp[c];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+          d0 = fmaf(qv[c * 8 + 2 * e], __low2float(t), d0);
+          d1 = fmaf(qv[c * 8 + 2 * e + 1], __high2float(t), d1);
+        }
+      }
+      s = d0 + d1;
+    }
+    const float mn = fmaxf(m, warp_max(s));
+    const float corr = exp2f((m - mn) * sl2);
+    const float p = exp2f((s - mn) * sl2);
+    l = l * corr + warp_sum(p);
+    a0 *= corr;
+    a1 *= corr;
+    m = mn;
+    const int cnt = min(32, len - k0);
+    for (int j = 0; j < cnt; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, p, j);
+      const __nv_bfloat162 vv =
+          *reinterpret_cast<const __nv_bfloat162*>(kv + (long long)(start + k0 + j) * 2 * D + D + h * 64 + lane * 2);
+      a0 = fmaf(pj, __low2float(vv), a0);
+      a1 = fmaf(pj, __high2float(vv), a1);
+    }
+  }
+  const float inv = (len > 0) ? 1.0f / l : 0.f;
+  *reinterpret_cast<uint32_t*>(out + (long long)b * D + h * 64 + lane * 2) = pack_bf16x2(a0 * inv, a1 * inv);
+}
+
+__global__ void broadcast_rows_kernel(const float* __restrict__ v, float* __restrict__ x, __nv_bfloat16* __restrict__ xb,
+                                      int B, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * D) return;
+  const float f = v[i % D];
+  x[i] = f;
+  xb[i] = __float2bfloat16_rn(f);
+}
+
+}  // namespace
+}  // namespace sb
+
+using namespace sb;
+
+struct SbSpeechEncoder {
+  SbSpeechConfig cfg;
+  SbSpeechWeights w;
+  std::vector<SbConformerLayerWeights> layers;
+  std::vector<SbPoolerLayerWeights> pool;
+  int num_sms;
+};
+
+namespace {
+
+struct SpWs {
+  __nv_bfloat16* a192;  // [T,192]
+  float* x;             // [T,D]
+  __nv_bfloat16* h;     // [T,D]
+  __nv_bfloat16* big;   // [T,max(F,3D,2D)]
+  __nv_bfloat16* bd;    // [T,H,Npad]
+  __nv_bfloat16* p;     // [Npad,D]
+  float* vp;            // [H,Npad]
+  __nv_bfloat16* e;     // [T,D] pooler memory
+  float* px;            // [B,D]
+  __nv_bfloat16* ph;    // [B,D]
+  __nv_bfloat16* pt;    // [B,max(Fp,D)]
+  __nv_bfloat16* pq;    // [B,D]
+  size_t bytes;
+};
+
+int npad_of(int smax) { return ((2 * smax - 1) + 255) / 256 * 256; }
+
+SpWs carve_sp(const SbSpeechEncoder* e, int B, long long T, int smax, void* base) {
+  const size_t D = e->cfg.model_dim, F = e->cfg.ffn_inner_dim, Fp = e->cfg.pooler_ffn_inner_dim, H = e->cfg.num_heads;
+  const size_t np = npad_of(smax);
+  size_t wide = F > 3 * D ? F : 3 * D;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { uint8_t* q = p + off; off = align_up_c(off + bytes, 1024); return q; };
+  SpWs w;
+  const size_t t = (size_t)T;
+  w.a192 = reinterpret_cast<__nv_bfloat16*>(take(t * kFeatPad * 2));
+  w.x = reinterpret_cast<float*>(take(t * D * 4));
+  w.h = reinterpret_cast<__nv_bfloat16*>(take(t * D * 2));
+  w.big = reinterpret_cast<__nv_bfloat16*>(take(t * wide * 2));
+  w.bd = reinterpret_cast<__nv_bfloat16*>(take(t * H * np * 2));
+  w.p = reinterpret_cast<__nv_bfloat16*>(take(np * D * 2));
+  w.vp = reinterpret_cast<float*>(take(H * np * 4));
+  w.e = reinterpret_cast<__nv_bfloat16*>(take(t * D * 2));
+  w.px = reinterpret_cast<float*>(take((size_t)B * D * 4));
+  w.ph = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * D * 2));
+  w.pt = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * (Fp > D ? Fp : D) * 2));
+  w.pq = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * D * 2));
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sb_speech_encoder_create(const SbSpeechConfig* cfg, const SbSpeechWeights* w, SbSpeechEncoder** out) {
+  if (!cfg || !w || !out) { set_last_error("sb_speech_encoder_create: null argument"); return SB_ERR_INVALID; }
+  *out = nullptr;
+  const int D = cfg->model_dim, H = cfg->num_heads;
+  if (D <= 0 || D % 256 != 0 || D > 1024 || H <= 0 || D != 64 * H || cfg->ffn_inner_dim % 256 != 0 ||
+      cfg->pooler_ffn_inner_dim % 256 != 0 || cfg->conv_kernel != 31 || cfg->num_layers < 0 || cfg->pooler_layers < 0) {
+    set_last_error("sb_speech_encoder_create: unsupported configuration (need d%%256==0 <=1024, head_dim 64, conv kernel 31)");
+    return SB_ERR_INVALID;
+  }
+  if (!w->front_ln_g || !w->front_ln_b || !w->front_w || !w->front_b || !w->final_ln_g || !w->final_ln_b ||
+      !w->pooler_q0 || !w->proj_w || !w->zeros || (cfg->num_layers && !w->layers) || (cfg->pooler_layers && !w->pooler)) {
+    set_last_error("sb_speech_encoder_create: missing weight pointer");
+    return SB_ERR_INVALID;
+  }
+  int dev = 0, n_gpu = 0;
+  if (cudaGetDeviceCount(&n_gpu) != cudaSuccess || n_gpu == 0) {
+    set_last_error("sb_speech_encoder_create: no CUDA device (this engine has no CPU path)");
+    return SB_ERR_CUDA;
+  }
+  SB_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  SB_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) { set_last_error("sb_speech_encoder_create: needs a B200-class GPU"); return SB_ERR_CUDA; }
+  SbSpeechEncoder* e = new (std::nothrow) SbSpeechEncoder();
+  if (!e) { set_last_error("out of host memory"); return SB_ERR_INVALID; }
+  e->cfg = *cfg;
+  e->w = *w;
+  e->layers.assign(w->layers, w->layers + cfg->num_layers);
+  e->pool.assign(w->pooler, w->pooler + cfg->pooler_layers);
+  for (auto& l : e->layers) {
+    const void* const* ptrs = reinterpret_cast<const void* const*>(&l);
+    for (size_t i = 0; i < sizeof(l) / sizeof(void*); ++i)
+      if (!ptrs[i]) { set_last_error("sb_speech_encoder_create: null conformer weight"); delete e; return SB_ERR_INVALID; }
+  }
+  for (auto& l : e->pool) {
+    const void* const* ptrs = reinterpret_cast<const void* const*>(&l);
+    for (size_t i = 0; i < sizeof(l) / sizeof(void*); ++i)
+      if (!ptrs[i]) { set_last_error("sb_speech_encoder_create: null pooler weight"); delete e; return SB_ERR_INVALID; }
+  }
+  e->num_sms = prop.multiProcessorCount;
+  *out = e;
+  return SB_OK;
+}
+
+void sb_speech_encoder_destroy(SbSpeechEncoder* e) { delete e; }
+
+int sb_speech_encoder_workspace_bytes(const SbSpeechEncoder* e, int32_t B, int64_t total_positions, int32_t max_positions,
+                                      size_t* bytes) {
+  if (!e || !bytes || B <= 0 || total_positions <= 0 || max_positions <= 0) {
+    set_last_error("sb_speech_encoder_workspace_bytes: bad argument");
+    return SB_ERR_INVALID;
+  }
+  *bytes = carve_sp(e, B, total_positions, max_positions, nullptr).bytes + 1024;
+  return SB_OK;
+}
+
+int sb_speech_encoder_forward(SbSpeechEncoder* e, const float* fbank, int32_t padded_frames, const int32_t* cu_dev,
+                              const int32_t* lens_host, int32_t B, const void* relpos_table, int32_t relpos_rows,
+                              float* out, float* encoded_packed, void* workspace, size_t workspace_bytes,
+                              void* stream_v) {
+  if (!e || !fbank || !cu_dev || !lens_host || !relpos_table || !out || !workspace) {
+    set_last_error("sb_speech_encoder_forward: null argument");
+    return SB_ERR_INVALID;
+  }
+  if (B <= 0 || B > 65535) { set_last_error("sb_speech_encoder_forward: bad batch size %d", B); return SB_ERR_INVALID; }
+  long long T = 0;
+  int smax = 0;
+  for (int b = 0; b < B; ++b) {
+    const int n = lens_host[b];
+    if (n <= 0 || 2 * n > padded_frames) { set_last_error("sb_speech_encoder_forward: lens[%d]=%d invalid", b, n); return SB_ERR_INVALID; }
+    T += n;
+    if (n > smax) smax = n;
+  }
+  const int Npad = npad_of(smax);
+  if (relpos_rows != Npad) {
+    set_last_error("sb_speech_encoder_forward: relative-position table must have %d rows for max length %d (got %d)", Npad,
+                   smax, relpos_rows);
+    return SB_ERR_INVALID;
+  }
+  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023);
+  SpWs w = carve_sp(e, B, T, smax, reinterpret_cast<void*>(base));
+  if (base - reinterpret_cast<uintptr_t>(workspace) + w.bytes > workspace_bytes) {
+    set_last_error("sb_speech_encoder_forward: workspace too small");
+    return SB_ERR_INVALID;
+  }
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const int D = e->cfg.model_dim, F = e->cfg.ffn_inner_dim, H = e->cfg.num_heads, Fp = e->cfg.pooler_ffn_inner_dim;
+  const float eps = e->cfg.ln_eps;
+  int rc;
+  GemmArgs g;
+  g.cta_group = 2;
+  g.num_sms = e->num_sms;
+  auto gemm = [&](const __nv_bfloat16* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int fp32,
+                  const float* bias, int M, int N, int K, int epi) -> int {
+    g.A = A; g.lda = lda; g.W = reinterpret_cast<const __nv_bfloat16*>(W); g.ldw = ldw; g.C = C; g.ldc = ldc;
+    g.out_fp32 = fp32; g.bias = bias; g.residual = (epi == EPI_BIAS_RESIDUAL) ? C : nullptr; g.ldr = ldc;
+    g.M = M; g.N = N; g.K = K; g.epi = epi;
+    return gemm_bf16(g, stream);
+  };
+  // ---- frontend ----
+  frontend_ln_kernel<<<dim3((unsigned)B, (unsigned)((smax + 7) / 8)), 256, 0, stream>>>(
+      fbank, padded_frames, cu_dev, e->w.front_ln_g, e->w.front_ln_b, eps, w.a192);
+  SB_CUDA_CHECK(cudaGetLastError());
+  if ((rc = gemm(w.a192, kFeatPad, e->w.front_w, kFeatPad, w.x, D, 1, e->w.front_b, (int)T, D, kFeatPad, EPI_BIAS))) return rc;
+  // ---- conformer blocks ----
+  for (int li = 0; li < e->cfg.num_layers; ++li) {
+    const SbConformerLayerWeights& L = e->layers[li];
+    // (a) half-step FFN 1 (0.5 folded into w2/b2)
+    if ((rc = layernorm_bf16(w.x, L.ffn1_ln_g, L.ffn1_ln_b, eps, w.h, T, D, stream))) return rc;
+    if ((rc = gemm(w.h, D, L.ffn1_w1, D, w.big, F, 0, L.ffn1_b1, (int)T, F, D, EPI_BIAS_SILU))) return rc;
+    if ((rc = gemm(w.big, F, L.ffn1_w2, F, w.x, D, 1, L.ffn1_b2, (int)T, D, F, EPI_BIAS_RESIDUAL))) return rc;
+    // (b) relative-position self-attention
+    if ((rc = layernorm_bf16(w.x, L.attn_ln_g, L.attn_ln_b, eps, w.h, T, D, stream))) return rc;
+    if ((rc = gemm(w.h, D, L.wqkv, D, w.big, 3 * D, 0, L.bqkv, (int)T, 3 * D, D, EPI_BIAS))) return rc;
+    if ((rc = gemm(reinterpret_cast<const __nv_bfloat16*>(relpos_table), D, L.wr, D, w.p, D, 0, e->w.zeros, Npad, D, D, EPI_BIAS))) return rc;
+    relpos_bias_kernel<<<dim3((unsigned)((Npad + 7) / 8), (unsigned)H), 256, 0, stream>>>(w.p, L.v_bias, Npad, H, w.vp);
+    SB_CUDA_CHECK(cudaGetLastError());
+    for (int h = 0; h < H; ++h)  // bd[:, h, :] = q_h . p_h^T + v.p_h   (K = 64)
+      if ((rc = gemm(w.big + h * 64, 3 * D, w.p + h * 64, D, w.bd + (size_t)h * Npad, (long long)H * Npad, 0,
+                     w.vp + (size_t)h * Npad, (int)T, Npad, 64, EPI_BIAS)))
+        return rc;
+    attention_relpos_kernel<<<dim3((unsigned)((smax + 127) / 128), (unsigned)H, (unsigned)B), 256, 0, stream>>>(
+        w.big, cu_dev, H, L.u_bias, w.bd, Npad, smax, w.h);
+    SB_CUDA_CHECK(cudaGetLastError());
+    if ((rc = gemm(w.h, D, L.wo, D, w.x, D, 1, L.bo, (int)T, D, D, EPI_BIAS_RESIDUAL))) return rc;
+    // (c) convolution module
+    if ((rc = layernorm_bf16(w.x, L.conv_ln_g, L.conv_ln_b, eps, w.h, T, D, stream))) return rc;
+    if ((rc = gemm(w.h, D, L.pw1, D, w.big, 2 * D, 0, e->w.zeros, (int)T, 2 * D, D, EPI_BIAS))) return rc;
+    glu_dwconv_kernel<31><<<dim3((unsigned)((smax + 63) / 64), (unsigned)(D / 64), (unsigned)B), 256, 0, stream>>>(
+        w.big, cu_dev, D, L.dw, L.bn_scale, L.bn_shift, w.h);
+    SB_CUDA_CHECK(cudaGetLastError());
+    if ((rc = gemm(w.h, D, L.pw2, D, w.x, D, 1, e->w.zeros, (int)T, D, D, EPI_BIAS_RESIDUAL))) return rc;
+    // (d) half-step FFN 2
+    if ((rc = layernorm_bf16(w.x, L.ffn2_ln_g, L.ffn2_ln_b, eps, w.h, T, D, stream))) return rc;
+    if ((rc = gemm(w.h, D, L.ffn2_w1, D, w.big, F, 0, L.ffn2_b1, (int)T, F, D, EPI_BIAS_SILU))) return rc;
+    if ((rc = gemm(w.big, F, L.ffn2_w2, F, w.x, D, 1, L.ffn2_b2, (int)T, D, F, EPI_BIAS_RESIDUAL))) return rc;
+    // (e) block LayerNorm: the residual stream itself is normalised
+    if ((rc = layernorm_dual(w.x, L.ln_g, L.ln_b, eps, w.x, nullptr, T, D, stream))) return rc;
+  }
+  // ---- model.layer_norm (fp32 in place, bf16 copy = pooler memory) ----
+  if ((rc = layernorm_dual(w.x, e->w.final_ln_g, e->w.final_ln_b, eps, w.x, w.e, T, D, stream))) return rc;
+  if (encoded_packed) SB_CUDA_CHECK(cudaMemcpyAsync(encoded_packed, w.x, sizeof(float) * (size_t)T * D, cudaMemcpyDeviceToDevice, stream));
+  // ---- attention pooler ----
+  broadcast_rows_kernel<<<(unsigned)(((long long)B * D + 255) / 256), 256, 0, stream>>>(e->w.pooler_q0, w.px, w.ph, B, D);
+  SB_CUDA_CHECK(cudaGetLastError());
+  for (int li = 0; li < e->cfg.pooler_layers; ++li) {
+    const SbPoolerLayerWeights& P = e->pool[li];
+    // self-attention over the single query token == Wo(Wv x + bv) + bo
+    if ((rc = gemm(w.ph, D, P.sa_wv, D, w.pt, D, 0, P.sa_bv, B, D, D, EPI_BIAS))) return rc;
+    if ((rc = gemm(w.pt, D, P.sa_wo, D, w.px, D, 1, P.sa_bo, B, D, D, EPI_BIAS_RESIDUAL))) return rc;
+    if ((rc = layernorm_dual(w.px, P.sa_ln_g, P.sa_ln_b, eps, w.px, w.ph, B, D, stream))) return rc;
+    // cross-attention over the utterance
+    if ((rc = gemm(w.ph, D, P.ca_wq, D, w.pq, D, 0, P.ca_bq, B, D, D, EPI_BIAS))) return rc;
+    if ((rc = gemm(w.e, D, P.ca_wkv, D, w.big, 2 * D, 0, P.ca_bkv, (int)T, 2 * D, D, EPI_BIAS))) return rc;
+    pool_attention_kernel<<<dim3((unsigned)B, (unsigned)((H + 3) / 4)), 128, 0, stream>>>(w.pq, w.big, cu_dev, H, w.pt);
+    SB_CUDA_CHECK(cudaGetLastError());
+    if ((rc = gemm(w.pt, D, P.ca_wo, D, w.px, D, 1, P.ca_bo, B, D, D, EPI_BIAS_RESIDUAL))) return rc;
+    if ((rc = layernorm_dual(w.px, P.ca_ln_g, P.ca_ln_b, eps, w.px, w.ph, B, D, stream))) return rc;
+    // ReLU FFN
+    if ((rc = gemm(w.ph, D, P.w1, D, w.pt, Fp, 0, P.b1, B, Fp, D, EPI_BIAS_RELU))) return rc;
+    if ((rc = gemm(w.pt, Fp, P.w2, Fp, w.px, D, 1, P.b2, B, D, Fp, EPI_BIAS_RESIDUAL))) return rc;
+    if ((rc = layernorm_dual(w.px, P.ffn_ln_g, P.ffn_ln_b, eps, w.px, w.ph, B, D, stream))) return rc;
+  }
+  return gemm(w.ph, D, e->w.proj_w, D, out, D, 1, e->w.zeros, B, D, D, EPI_BIAS);
+}
+
+}  // extern "C"

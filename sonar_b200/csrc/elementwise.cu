@@ -127,6 +127,31 @@ layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gam
     if (i < nvec) yrow[i * 32 + lane] = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
 }
 
+// y32 = LN(x) in fp32 (may alias x: every row is read into registers before it is written) and/or a bf16 copy
+__global__ void __launch_bounds__(256)
+layernorm_dual_kernel(const float* x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                      float* y32, __nv_bfloat16* __restrict__ y16, long long T, int D) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= T) return;
+  const int nvec = D / 128;
+  float4 v[kMaxVec];
+  load_row(x + row * D, nvec, lane, v);
+  normalize_row(v, nvec, lane, D, gamma, beta, eps);
+  if (y32 != nullptr) {
+    float4* r = reinterpret_cast<float4*>(y32 + row * D);
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nvec) r[i * 32 + lane] = v[i];
+  }
+  if (y16 != nullptr) {
+    uint2* r = reinterpret_cast<uint2*>(y16 + row * D);
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nvec) r[i * 32 + lane] = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+  }
+}
+
 int layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, __nv_bfloat16* y, long long T,
                    int D, cudaStream_t stream) {
   if (T <= 0) return 0;
@@ -136,6 +161,18 @@ int layernorm_bf16(const float* x, const float* gamma, const float* beta, float 
   }
   const long long blocks = (T + 7) / 8;
   layernorm_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, gamma, beta, eps, y, T, D);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int layernorm_dual(const float* x, const float* gamma, const float* beta, float eps, float* y32, __nv_bfloat16* y16,
+                   long long T, int D, cudaStream_t stream) {
+  if (T <= 0) return 0;
+  if (D % 128 != 0 || D > 128 * kMaxVec) {
+    set_last_error("layernorm_dual: D must be a multiple of 128 and <= %d (got %d)", 128 * kMaxVec, D);
+    return -1;
+  }
+  layernorm_dual_kernel<<<(unsigned)((T + 7) / 8), 256, 0, stream>>>(x, gamma, beta, eps, y32, y16, T, D);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

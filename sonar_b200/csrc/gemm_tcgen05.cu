@@ -331,6 +331,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
+          if constexpr (kEpi == EPI_BIAS_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+          }
           if constexpr (kEpi == EPI_BIAS_RESIDUAL) {
             if (grow < M) {
               const OutT* rp = residual + (long long)grow * ldr + gcol;
@@ -566,6 +570,7 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   switch (epi) {                                                            \
     case EPI_BIAS: SB_DISPATCH(CG, EPI_BIAS, T);                            \
     case EPI_BIAS_RELU: SB_DISPATCH(CG, EPI_BIAS_RELU, T);                  \
+    case EPI_BIAS_SILU: SB_DISPATCH(CG, EPI_BIAS_SILU, T);                  \
     case EPI_BIAS_RESIDUAL: SB_DISPATCH(CG, EPI_BIAS_RESIDUAL, T);          \
     case EPI_BIAS_ACCUM: SB_DISPATCH(CG, EPI_BIAS_ACCUM, float);            \
     default: set_last_error("gemm_bf16: bad epilogue %d", epi); return -1;  \

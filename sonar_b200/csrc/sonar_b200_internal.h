@@ -13,7 +13,8 @@ namespace sb {
 // automatically for EPI_BIAS_RESIDUAL when the residual aliases a fp32 C (the encoder's x += ... case).
 // Bit-identical to EPI_BIAS_RESIDUAL: both compute fl32(x + fl32(acc + bias)).
 // EPI_TOPK (internal): no C at all -- the epilogue keeps a running per-row top-k of the product (xsim mining).
-enum EpiMode { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_RESIDUAL = 2, EPI_BIAS_ACCUM = 3, EPI_TOPK = 4 };
+// EPI_BIAS_SILU: x*sigmoid(x) (the Conformer's swish FFN activation)
+enum EpiMode { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_RESIDUAL = 2, EPI_BIAS_ACCUM = 3, EPI_TOPK = 4, EPI_BIAS_SILU = 5 };
 constexpr int kTopkCandidates = 16;  // bf16-similarity candidates per row handed to the exact fp64 re-rank
 enum PoolMode { POOL_MAX = 1, POOL_MEAN = 2, POOL_LAST = 3 };  // = reference `Pooling` enum values (model.py:23-27)
 
@@ -54,6 +55,10 @@ int embed_tokens(const int64_t* ids, long long ids_stride, const int32_t* cu_seq
 // y = LN(x) * gamma + beta, fp32 in, bf16 out, one warp per row
 int layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, __nv_bfloat16* y, long long T,
                    int D, cudaStream_t stream);
+
+// LN with an fp32 result (y32 may alias x) and/or a bf16 copy (either may be null)
+int layernorm_dual(const float* x, const float* gamma, const float* beta, float eps, float* y32, __nv_bfloat16* y16,
+                   long long T, int D, cudaStream_t stream);
 
 // softmax(q k^T / sqrt(64)) v over packed sequences; qkv [T, 3*D] bf16 (q | k | v), out [T, D] bf16
 // impl: 0 = auto (tcgen05 kernel when max_len <= 128, mma.sync flash kernel otherwise), 1 = mma.sync, 2 = tcgen05

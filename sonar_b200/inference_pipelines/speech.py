@@ -1,0 +1,79 @@
+"""Drop-in mirror of ``sonar.inference_pipelines.speech.SpeechToEmbeddingModelPipeline``
+(``/root/reference/sonar/inference_pipelines/speech.py:402-474``): same constructor / ``predict`` signature; the
+fairseq2n operators are replaced by the GPU fbank frontend (``sonar_b200.speech_frontend``) and the model stage by
+``B200SpeechEncoderModel``.  Inputs are ``[C, T]`` waveform tensors at 16 kHz (``_decode_audio`` transposes to
+``[T, C]``, ``speech.py:298-304``) or paths to PCM-16 mono ``.wav`` files (the reference decodes any libsndfile
+format; only plain WAV is read here, with the standard library).
+"""
+
+from __future__ import annotations
+
+import wave
+from pathlib import Path
+from typing import Iterable, List, Sequence, Union
+
+import torch
+from torch import Tensor
+
+from ..batching import bucket, prefetch
+from ..sequence import PaddingMask, SequenceBatch
+from ..speech_encoder import B200SpeechEncoderModel
+from ..speech_frontend import SAMPLE_RATE, WaveformToFbank
+from .utils import add_progress_bar
+
+Device = Union[str, torch.device]
+CPU_DEVICE = torch.device("cpu")
+
+
+def _read_wav(path: Union[str, Path]) -> Tensor:
+    with wave.open(str(path), "rb") as f:
+        if f.getsampwidth() != 2 or f.getnchannels() != 1:
+            raise ValueError(f"{path}: only 16-bit mono PCM WAV is supported")
+        if f.getframerate() != SAMPLE_RATE:
+            raise ValueError(f"{path}: sample rate must be {SAMPLE_RATE} Hz")
+        pcm = torch.frombuffer(bytearray(f.readframes(f.getnframes())), dtype=torch.int16)
+    return (pcm.float() / 32768.0)[None, :]  # [C=1, T] like a decoded file handed to the pipeline as a tensor
+
+
+class SpeechToEmbeddingModelPipeline(torch.nn.Module):
+    model: B200SpeechEncoderModel
+
+    def __init__(self, encoder: Union[str, B200SpeechEncoderModel], device: Device = CPU_DEVICE,
+                 fbank_dtype: torch.dtype = torch.float32) -> None:
+        super().__init__()
+        if isinstance(encoder, str):
+            raise FileNotFoundError(f"speech encoder card {encoder!r} cannot be resolved offline; pass a "
+                                    "B200SpeechEncoderModel object")
+        if fbank_dtype != torch.float32:
+            raise NotImplementedError("the B200 frontend produces fp32 features; the encoder computes in bf16/fp32")
+        self.device = torch.device(device)
+        self.model = encoder.eval()
+        self.convert_to_fbank = WaveformToFbank(self.model.device)
+
+    def _decode_audio(self, inp: Union[str, Path, Tensor]) -> Tensor:
+        if isinstance(inp, Tensor):
+            if inp.dim() != 2:
+                raise ValueError("waveform tensors must be [channels, samples]")
+            return inp
+        return _read_wav(inp)
+
+    @torch.inference_mode()
+    def predict(self, input: Union[Sequence[str], Sequence[Tensor]], batch_size: int = 3, n_parallel: int = 1,
+                pad_idx: int = 0, n_prefetched_batches: int = 2, progress_bar: bool = False) -> Tensor:
+        if pad_idx != 0:
+            raise NotImplementedError("fbank batches are zero padded (the reference default)")
+
+        def batches():
+            for group in bucket((self._decode_audio(x) for x in input), batch_size):
+                yield group
+
+        def run(group: List[Tensor]) -> Tensor:
+            fb, frames = self.convert_to_fbank(group)
+            mask = PaddingMask(torch.tensor(frames), fb.shape[1], seq_lens_host=frames)
+            return self.model(SequenceBatch(fb, mask)).sentence_embeddings
+
+        pipeline: Iterable = (run(g) for g in prefetch(batches(), n_prefetched_batches))
+        if progress_bar:
+            pipeline = add_progress_bar(pipeline, inputs=input, batch_size=batch_size)
+        results = list(iter(pipeline))
+        return torch.cat(results, dim=0)

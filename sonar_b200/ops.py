@@ -40,7 +40,7 @@ def gemm_bf16(a: Tensor, w: Tensor, bias: Tensor, *, epilogue: str = "bias", res
     m, k = a.shape
     n = w.shape[0]
     assert w.shape[1] == k and bias.numel() == n
-    epi = {"bias": _lib.SB_EPI_BIAS, "relu": _lib.SB_EPI_BIAS_RELU, "residual": _lib.SB_EPI_BIAS_RESIDUAL}[epilogue]
+    epi = {"bias": _lib.SB_EPI_BIAS, "relu": _lib.SB_EPI_BIAS_RELU, "residual": _lib.SB_EPI_BIAS_RESIDUAL, "silu": 5}[epilogue]
     if out is None:
         out = torch.empty((m, n), dtype=out_dtype, device=a.device)
     assert out.dtype in (torch.bfloat16, torch.float32) and out.stride(1) == 1

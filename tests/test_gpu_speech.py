@@ -42,3 +42,92 @@ def test_fbank_rejects_bad_input(native_lib, cuda_device):
         conv([torch.zeros((2, 1000), device=cuda_device)])
     with pytest.raises(RuntimeError):
         WaveformToFbank("cpu")
+
+
+# ---------------------------------------------------------------- Conformer encoder + pooler vs the oracle
+@pytest.fixture(scope="module")
+def speech_small(native_lib, cuda_device):
+    from oracle.speech_encoder import OracleSpeechConfig, OracleSpeechEncoder, make_synthetic_speech_state_dict
+    from sonar_b200 import B200SpeechEncoderModel, sonar_speech_encoder_config
+
+    ocfg = OracleSpeechConfig(num_layers=2, pooler_layers=2)
+    sd = make_synthetic_speech_state_dict(ocfg, seed=3)
+    cfg = sonar_speech_encoder_config("english", num_encoder_layers=2, num_decoder_layers=2)
+    return OracleSpeechEncoder(ocfg, sd), B200SpeechEncoderModel(cfg, sd, cuda_device)
+
+
+def _speech_check(m, what):
+    print(what, m)
+    assert m["one_minus_cos_max"] <= 1e-3 and m["rel_l2_max"] <= 2e-2, (what, m)
+
+
+def test_speech_encoder_vs_oracle(speech_small, cuda_device):
+    from sonar_b200 import PaddingMask, SequenceBatch
+    from tests.helpers import parity_metrics
+
+    oracle, model = speech_small
+    g = torch.Generator().manual_seed(5)
+    frames = [300, 131, 64, 257, 2]
+    tmax = 300
+    fb = torch.zeros((len(frames), tmax, 80))
+    for i, n in enumerate(frames):
+        fb[i, :n] = torch.randn((n, 80), generator=g)
+    ref, ref_enc, lens = oracle(fb, frames)
+    model.return_encoded_seqs = True
+    out = model(SequenceBatch(fb.to(cuda_device), PaddingMask(torch.tensor(frames), tmax, frames)))
+    model.return_encoded_seqs = False
+    torch.cuda.synchronize()
+    # encoder states (after model.layer_norm) at the real positions, packed order
+    start = 0
+    for i, n in enumerate(lens):
+        got, exp = out.encoded_seqs[start : start + n].cpu(), ref_enc[i, :n]
+        rel = float((got - exp).norm() / exp.norm())
+        assert rel <= 2e-2, (i, rel)
+        start += n
+    _speech_check(parity_metrics(out.sentence_embeddings, ref), "speech 2+2 layers ragged")
+
+
+def test_speech_batch_invariance_and_long_utterance(speech_small, cuda_device):
+    from sonar_b200 import PaddingMask, SequenceBatch
+    from tests.helpers import parity_metrics
+
+    oracle, model = speech_small
+    g = torch.Generator().manual_seed(6)
+    frames = [998, 400]  # config-3 shape: 10 s -> 998 frames -> 499 positions
+    fb = torch.zeros((2, 998, 80))
+    for i, n in enumerate(frames):
+        fb[i, :n] = torch.randn((n, 80), generator=g)
+    both = model(SequenceBatch(fb.to(cuda_device), PaddingMask(torch.tensor(frames), 998, frames))).sentence_embeddings
+    alone = model(SequenceBatch(fb[1:, :400].contiguous().to(cuda_device), None)).sentence_embeddings
+    torch.testing.assert_close(both[1], alone[0], rtol=1e-4, atol=1e-4)  # different S_max -> different bd rounding only
+    ref, _, _ = oracle(fb, frames)
+    _speech_check(parity_metrics(both, ref), "speech 998-frame utterance")
+
+
+def test_speech_pipeline_end_to_end(speech_small, cuda_device, tmp_path):
+    import wave
+
+    from oracle.speech_frontend import collate_fbank, waveform_to_fbank
+    from sonar_b200.inference_pipelines import SpeechToEmbeddingModelPipeline
+    from tests.helpers import parity_metrics
+
+    oracle, model = speech_small
+    pipe = SpeechToEmbeddingModelPipeline(model, device=cuda_device)
+    g = torch.Generator().manual_seed(8)
+    waves = [(torch.randn(16000 + 123 * i, generator=g) * 0.1).clamp(-1, 1) for i in range(4)]
+    emb = pipe.predict([w[None, :] for w in waves], batch_size=3)
+    assert emb.shape == (4, 1024)
+    feats = [waveform_to_fbank(w) for w in waves]
+    refs = []
+    for grp in (feats[:3], feats[3:]):  # same bucketing as batch_size=3
+        fb, fl = collate_fbank(grp)
+        refs.append(oracle(fb, fl)[0])
+    _speech_check(parity_metrics(emb, torch.cat(refs)), "speech pipeline")
+    # a PCM-16 wav file gives the same embedding as its tensor (test_sonar_speech_pipeline_models.py:28-40 analogue)
+    pcm = (waves[0] * 32767).round().clamp(-32768, 32767).to(torch.int16)
+    path = tmp_path / "a.wav"
+    with wave.open(str(path), "wb") as f:
+        f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(pcm.numpy().tobytes())
+    e_file = pipe.predict([str(path)])
+    e_tensor = pipe.predict([(pcm.float() / 32768.0)[None, :]])
+    torch.testing.assert_close(e_file, e_tensor, rtol=1e-5, atol=1e-5)

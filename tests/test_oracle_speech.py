@@ -42,3 +42,29 @@ def test_native_tables_match_oracle(native_lib):
         dense = torch.zeros(257)
         dense[lo[m] : lo[m] + ln[m]] = w[m, : ln[m]]
         torch.testing.assert_close(dense, mb[m], rtol=0, atol=1e-7)
+
+
+def test_oracle_conformer_block_matches_hf_golden():
+    from oracle.speech_encoder import OracleSpeechConfig, OracleSpeechEncoder
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "conformer_layer_small.pt"), weights_only=True)
+    enc = OracleSpeechEncoder(OracleSpeechConfig(**g["config"]), g["state_dict"])
+    s = g["x"].shape[1]
+    ok = torch.arange(s)[None, :] < g["lens"][:, None]
+    out = enc.conformer_block(0, g["x"], ok)
+    torch.testing.assert_close(out * ok[:, :, None], g["out"] * ok[:, :, None], rtol=1e-5, atol=1e-5)
+
+
+def test_oracle_speech_padding_invariance():
+    """An utterance's embedding must not depend on its batch neighbours / padding (key masks, zeroed conv inputs)."""
+    from oracle.speech_encoder import OracleSpeechConfig, OracleSpeechEncoder, make_synthetic_speech_state_dict
+
+    cfg = OracleSpeechConfig(model_dim=64, num_layers=2, num_heads=4, ffn_inner_dim=128, pooler_layers=2, pooler_heads=4,
+                             pooler_ffn_inner_dim=128, pooler_vocab=64)
+    enc = OracleSpeechEncoder(cfg, make_synthetic_speech_state_dict(cfg, seed=1, std=0.1))
+    fb = torch.randn(2, 24, 80)
+    fb[1, 14:] = 0
+    both, _, lens = enc(fb, [24, 14])
+    alone, _, _ = enc(fb[1:, :14], [14])
+    assert lens == [12, 7]
+    torch.testing.assert_close(both[1], alone[0], rtol=1e-5, atol=1e-5)
