@@ -20,7 +20,7 @@ def test_fbank_kernel_matches_oracle_and_golden(native_lib, cuda_device):
     gen = torch.Generator().manual_seed(3)
     waves = list(g["waveforms"]) + [(torch.randn(160000, generator=gen) * 0.05).clamp(-1, 1),   # config-3 shape: 10 s
                                     (torch.randn(16000 * 3 + 77, generator=gen) * 0.3).clamp(-1, 1),
-                                    torch.sin(torch.arange(400 + 160 * 5) * 0.05) * 0.5]
+                                    (torch.sin(torch.arange(400 + 160 * 5) * 0.05) * 0.5 + 0.02 * torch.randn(400 + 160 * 5, generator=gen))]  # tone + noise floor
     out, frames = conv([w.to(cuda_device) for w in waves])
     torch.cuda.synchronize()
     ref, ref_lens = collate_fbank([waveform_to_fbank(w) for w in waves])
