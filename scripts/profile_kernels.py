@@ -40,5 +40,39 @@ elif which == "layernorm":
     gg, bb = torch.ones(D, device=dev), torch.zeros(D, device=dev)
     for _ in range(4):
         ops.layernorm(x, gg, bb)
+elif which == "speech":  # one full speech-encoder forward (64 x 10 s), for a launch list
+    from oracle.speech_encoder import OracleSpeechConfig, make_synthetic_speech_state_dict
+    from sonar_b200 import B200SpeechEncoderModel, PaddingMask, SequenceBatch, sonar_speech_encoder_config
+    sd = make_synthetic_speech_state_dict(OracleSpeechConfig(), seed=3)
+    model = B200SpeechEncoderModel(sonar_speech_encoder_config("english"), sd, dev)
+    fb = torch.randn((64, 998, 80), device=dev)
+    fr = [998] * 64
+    for _ in range(2):
+        model(SequenceBatch(fb, PaddingMask(torch.tensor(fr), 998, fr)))
+elif which == "decoder":  # a few full-size decoder steps (512 x beam 5), for a launch list
+    from sonar_b200 import B200TextDecoderModel, sonar_text_decoder_config
+    gg = torch.Generator(device=dev).manual_seed(3)
+    sd = {}
+    def rn(*shape, s=0.02):
+        return torch.randn(*shape, generator=gg, device=dev) * s
+    sd["decoder_frontend.embed.weight"] = rn(256206, 1024, s=1 / 32)
+    for i in range(24):
+        p = f"decoder.layers.{i}."
+        for a in ("self_attn", "encoder_decoder_attn"):
+            for nme in ("q_proj", "k_proj", "v_proj", "output_proj"):
+                sd[p + f"{a}.{nme}.weight"], sd[p + f"{a}.{nme}.bias"] = rn(1024, 1024), rn(1024)
+            sd[p + f"{a}_layer_norm.weight"], sd[p + f"{a}_layer_norm.bias"] = 1 + rn(1024), rn(1024)
+        sd[p + "ffn.inner_proj.weight"], sd[p + "ffn.inner_proj.bias"] = rn(8192, 1024), rn(8192)
+        sd[p + "ffn.output_proj.weight"], sd[p + "ffn.output_proj.bias"] = rn(1024, 8192), rn(1024)
+        sd[p + "ffn_layer_norm.weight"], sd[p + "ffn_layer_norm.bias"] = 1 + rn(1024), rn(1024)
+    sd["decoder.layer_norm.weight"], sd["decoder.layer_norm.bias"] = 1 + rn(1024), rn(1024)
+    model = B200TextDecoderModel(sonar_text_decoder_config("basic"), sd, dev)
+    n, beam, tmax = 512, 5, 130
+    model.begin(torch.randn((n, 1024), device=dev) * 0.25, beam, tmax)
+    r = n * beam
+    table = torch.arange(r, dtype=torch.int32, device=dev)[:, None].expand(r, tmax).contiguous()
+    tk = torch.randint(4, 256000, (r,), device=dev)
+    for t in (0, 1, 64):
+        model.step(tk, table, t)
 torch.cuda.synchronize()
 print("done", which)
