@@ -10,9 +10,9 @@
 // masks them in the softmax; here they are simply out of range.
 //
 // Relative-position attention (Transformer-XL):  score(i,j) = ((q_i+u).k_j + (q_i+v).p_{i-j}) / 8
-//   = (q_i.k_j + u.k_j + q_i.p_{i-j} + v.p_{i-j}) / 8.  p = r_proj(R) is one small GEMM per layer; the term
-//   q_i.p_r + v.p_r for ALL r is one K=64 GEMM per head whose bias vector is v.p_r (written to `bd`, bf16); the
-//   flash kernel then adds bd[i, S-1-i+j] and u.k_j (computed from the K tile in shared memory) to q_i.k_j.
+//   = (q_i.k_j + u.k_j + q_i.p_{i-j} + v.p_{i-j}) / 8.  p = r_proj(R) is one small GEMM per layer and v.p one tiny
+//   kernel; the flash kernel computes q.p for the band of relative offsets each 16-query x 64-key tile can reach with
+//   the same mma path as q.k^T and applies the Transformer-XL shift as an anti-diagonal read from shared memory.
 
 #include "../../include/sonar_b200.h"
 #include "common.cuh"
@@ -92,15 +92,25 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 }
 __device__ __forceinline__ uint32_t toff(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
+// Dynamic shared memory layout of attention_relpos_kernel (bytes)
+constexpr int kRpQ = 0, kRpK = 16384, kRpV = 24576, kRpP = 32768 /* 192-row band of p */, kRpG = 57344 /* 8 x [16][80] fp32 */;
+constexpr int kRpVp = kRpG + 8 * 16 * 80 * 4, kRpU = kRpVp + 192 * 4, kRpKb = kRpU + 64 * 4;
+constexpr int kRpSmem = kRpKb + 64 * 4;
+
+// score(i,j) = (q_i.k_j + u.k_j + q_i.p[c-1-i+j] + v.p[c-1-i+j]) / 8 with c = S_center.  Per 64-key block the CTA stages
+// the 192 rows of p its 128 queries can reach; each warp multiplies its 16 queries with its own 80-row window on the
+// tensor cores (mma.sync), adds v.p, parks the [16 x 80] result in shared memory and reads it back along the
+// anti-diagonals -- the Transformer-XL "shift" -- while it masks and soft-maxes q.k^T.
 __global__ void __launch_bounds__(256)
 attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu, int H,
-                        const float* __restrict__ u_bias, const __nv_bfloat16* __restrict__ bd, int Npad, int S_center,
-                        __nv_bfloat16* __restrict__ out) {
-  __shared__ __align__(128) uint8_t sQ[128 * 128];
-  __shared__ __align__(128) uint8_t sK[64 * 128];
-  __shared__ __align__(128) uint8_t sV[64 * 128];
-  __shared__ float s_u[64];
-  __shared__ float s_kb[64];
+                        const float* __restrict__ u_bias, const __nv_bfloat16* __restrict__ p, const float* __restrict__ vp,
+                        int Npad, int S_center, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sQ = smem + kRpQ;
+  uint8_t* sK = smem + kRpK;
+  float* s_vp = reinterpret_cast<float*>(smem + kRpVp);
+  float* s_u = reinterpret_cast<float*>(smem + kRpU);
+  float* s_kb = reinterpret_cast<float*>(smem + kRpKb);
   const int qblk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int start = cu[b], len = cu[b + 1] - start;
   const int q0 = qblk * 128;
@@ -111,7 +121,8 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
   const __nv_bfloat16* kbase = qbase + D;
   const __nv_bfloat16* vbase = qbase + 2 * D;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t sQa = smem_u32(sQ), sKa = smem_u32(sK), sVa = smem_u32(sV);
+  const uint32_t sQa = smem_u32(sQ), sKa = smem_u32(sK), sVa = smem_u32(smem + kRpV), sPa = smem_u32(smem + kRpP);
+  float* sG = reinterpret_cast<float*>(smem + kRpG) + warp * 16 * 80;
   if (tid < 64) s_u[tid] = u_bias[h * 64 + tid];
   for (int i = tid; i < 128 * 8; i += 256) {
     const int r = i >> 3, c = i & 7;
@@ -131,15 +142,13 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
   for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
   float m_run[2] = {-CUDART_INF_F, -CUDART_INF_F}, l_run[2] = {0.f, 0.f};
   const float sl2 = 0.125f * 1.4426950408889634f;
-  // the two query positions this thread owns, and their rows in the bd buffer
-  const int i_lo = q0 + warp * 16 + (lane >> 2), i_hi = i_lo + 8;
-  const __nv_bfloat16* bd_lo = bd + ((long long)(start + min(i_lo, len - 1)) * H + h) * Npad + (S_center - 1 - i_lo);
-  const __nv_bfloat16* bd_hi = bd + ((long long)(start + min(i_hi, len - 1)) * H + h) * Npad + (S_center - 1 - i_hi);
-  const bool ok_lo = i_lo < len, ok_hi = i_hi < len;
+  const int rl_lo = lane >> 2, rl_hi = rl_lo + 8;  // this thread's two rows inside the warp's 16
+  const int wrow0 = 112 - 16 * warp;               // first row of this warp's 80-row window inside the 192-row band
 
   const int nkb = (len + 63) / 64;
   for (int kb = 0; kb < nkb; ++kb) {
     const int k0 = kb * 64;
+    const int band0 = S_center - 1 - (q0 + 127) + k0;  // p row held by band row 0
     __syncthreads();
     for (int i = tid; i < 64 * 8; i += 256) {
       const int r = i >> 3, c = i & 7;
@@ -147,6 +156,16 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
       const long long g = (long long)(ok ? k0 + r : 0) * rs + c * 8;
       cp16(sKa + toff(r, c), kbase + g, ok);
       cp16(sVa + toff(r, c), vbase + g, ok);
+    }
+    for (int i = tid; i < 192 * 8; i += 256) {
+      const int r = i >> 3, c = i & 7;
+      const int idx = band0 + r;
+      const bool ok = idx >= 0 && idx < Npad;
+      cp16(sPa + toff(r, c), p + (long long)(ok ? idx : 0) * D + h * 64 + c * 8, ok);
+    }
+    if (tid < 192) {
+      const int idx = band0 + tid;
+      s_vp[tid] = (idx >= 0 && idx < Npad) ? vp[(long long)h * Npad + idx] : 0.f;
     }
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncthreads();
@@ -165,7 +184,33 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
       }
       s_kb[tid] = acc;
     }
-    __syncthreads();
+    // ---- G[16 x 80] = Q_warp . Pband_warp^T (+ v.p), parked in shared memory ----
+    {
+      float gacc[10][4];
+#pragma unroll
+      for (int j = 0; j < 10; ++j) gacc[j][0] = gacc[j][1] = gacc[j][2] = gacc[j][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int jp = 0; jp < 5; ++jp) {
+          const int mtx = lane >> 3;
+          const int prow = wrow0 + (jp * 2 + (mtx >> 1)) * 8 + (lane & 7);
+          uint32_t b0, b1, b2, b3;
+          ldsm4(sPa + toff(prow, kk * 2 + (mtx & 1)), b0, b1, b2, b3);
+          mma16816(gacc[jp * 2], qf[kk], b0, b1);
+          mma16816(gacc[jp * 2 + 1], qf[kk], b2, b3);
+        }
+      }
+      const int cc = (lane & 3) * 2;
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+        const int c = j * 8 + cc;
+        const float v0 = s_vp[wrow0 + c], v1 = s_vp[wrow0 + c + 1];
+        *reinterpret_cast<float2*>(sG + rl_lo * 80 + c) = make_float2(gacc[j][0] + v0, gacc[j][1] + v1);
+        *reinterpret_cast<float2*>(sG + rl_hi * 80 + c) = make_float2(gacc[j][2] + v0, gacc[j][3] + v1);
+      }
+    }
+    __syncthreads();  // s_kb + every warp's G visible
     float s[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
@@ -181,20 +226,16 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
         mma16816(s[jp * 2 + 1], qf[kk], b2, b3);
       }
     }
-    const int kc = (lane & 3) * 2;  // key column inside each 8-key tile
+    const int kc = (lane & 3) * 2;
     float mx[2] = {-CUDART_INF_F, -CUDART_INF_F};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int kl = j * 8 + kc + (e & 1);  // key index inside the block
-        const int key = k0 + kl;
-        const bool rowok = (e < 2) ? ok_lo : ok_hi;
+        const int kl = j * 8 + kc + (e & 1);
+        const int rl = (e < 2) ? rl_lo : rl_hi;
         float val = -CUDART_INF_F;
-        if (key < len) {
-          const float pos = rowok ? __bfloat162float(((e < 2) ? bd_lo : bd_hi)[key]) : 0.f;
-          val = s[j][e] + s_kb[kl] + pos;
-        }
+        if (k0 + kl < len) val = s[j][e] + s_kb[kl] + sG[rl * 80 + kl + 15 - rl];  // band column of (i, j): 15 - r + key
         s[j][e] = val;
         mx[e >> 1] = fmaxf(mx[e >> 1], val);
       }
@@ -409,7 +450,6 @@ struct SpWs {
   float* x;             // [T,D]
   __nv_bfloat16* h;     // [T,D]
   __nv_bfloat16* big;   // [T,max(F,3D,2D)]
-  __nv_bfloat16* bd;    // [T,H,Npad]
   __nv_bfloat16* p;     // [Npad,D]
   float* vp;            // [H,Npad]
   __nv_bfloat16* e;     // [T,D] pooler memory
@@ -435,7 +475,6 @@ SpWs carve_sp(const SbSpeechEncoder* e, int B, long long T, int smax, void* base
   w.x = reinterpret_cast<float*>(take(t * D * 4));
   w.h = reinterpret_cast<__nv_bfloat16*>(take(t * D * 2));
   w.big = reinterpret_cast<__nv_bfloat16*>(take(t * wide * 2));
-  w.bd = reinterpret_cast<__nv_bfloat16*>(take(t * H * np * 2));
   w.p = reinterpret_cast<__nv_bfloat16*>(take(np * D * 2));
   w.vp = reinterpret_cast<float*>(take(H * np * 4));
   w.e = reinterpret_cast<__nv_bfloat16*>(take(t * D * 2));
@@ -539,6 +578,11 @@ int sb_speech_encoder_forward(SbSpeechEncoder* e, const float* fbank, int32_t pa
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   const int D = e->cfg.model_dim, F = e->cfg.ffn_inner_dim, H = e->cfg.num_heads, Fp = e->cfg.pooler_ffn_inner_dim;
   const float eps = e->cfg.ln_eps;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SB_CUDA_CHECK(cudaFuncSetAttribute(attention_relpos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRpSmem));
+    attr_set = true;
+  }
   int rc;
   GemmArgs g;
   g.cta_group = 2;
@@ -568,12 +612,8 @@ int sb_speech_encoder_forward(SbSpeechEncoder* e, const float* fbank, int32_t pa
     if ((rc = gemm(reinterpret_cast<const __nv_bfloat16*>(relpos_table), D, L.wr, D, w.p, D, 0, e->w.zeros, Npad, D, D, EPI_BIAS))) return rc;
     relpos_bias_kernel<<<dim3((unsigned)((Npad + 7) / 8), (unsigned)H), 256, 0, stream>>>(w.p, L.v_bias, Npad, H, w.vp);
     SB_CUDA_CHECK(cudaGetLastError());
-    for (int h = 0; h < H; ++h)  // bd[:, h, :] = q_h . p_h^T + v.p_h   (K = 64)
-      if ((rc = gemm(w.big + h * 64, 3 * D, w.p + h * 64, D, w.bd + (size_t)h * Npad, (long long)H * Npad, 0,
-                     w.vp + (size_t)h * Npad, (int)T, Npad, 64, EPI_BIAS)))
-        return rc;
-    attention_relpos_kernel<<<dim3((unsigned)((smax + 127) / 128), (unsigned)H, (unsigned)B), 256, 0, stream>>>(
-        w.big, cu_dev, H, L.u_bias, w.bd, Npad, smax, w.h);
+    attention_relpos_kernel<<<dim3((unsigned)((smax + 127) / 128), (unsigned)H, (unsigned)B), 256, kRpSmem, stream>>>(
+        w.big, cu_dev, H, L.u_bias, w.p, w.vp, Npad, smax, w.h);
     SB_CUDA_CHECK(cudaGetLastError());
     if ((rc = gemm(w.h, D, L.wo, D, w.x, D, 1, L.bo, (int)T, D, D, EPI_BIAS_RESIDUAL))) return rc;
     // (c) convolution module

@@ -174,13 +174,23 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
   for (int i = 0; i < kMaxKeyIters; ++i) {
     if (i * 32 < nk) {
       const int cnt = min(32, nk - i * 32);
-      for (int j = 0; j < cnt; ++j) {
-        const float p = __shfl_sync(0xffffffffu, sc[i], j);
-        const int pr = __shfl_sync(0xffffffffu, prow[i], j);
-        const __nv_bfloat162 vv = *reinterpret_cast<const __nv_bfloat162*>(
-            vcache + ((long long)pr * Tmax + (i * 32 + j)) * D + h * 64 + lane * 2);
-        a0 = fmaf(p, __low2float(vv), a0);
-        a1 = fmaf(p, __high2float(vv), a1);
+      // 8 independent V loads in flight per step (the loads only depend on shuffles, never on each other)
+      for (int j0 = 0; j0 < cnt; j0 += 8) {
+        __nv_bfloat162 vv[8];
+        float pj[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = min(j0 + u, cnt - 1);
+          pj[u] = (j0 + u < cnt) ? __shfl_sync(0xffffffffu, sc[i], j) : (__shfl_sync(0xffffffffu, sc[i], j), 0.f);
+          const int pr = __shfl_sync(0xffffffffu, prow[i], j);
+          vv[u] = *reinterpret_cast<const __nv_bfloat162*>(
+              vcache + ((long long)pr * Tmax + (i * 32 + j)) * D + h * 64 + lane * 2);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          a0 = fmaf(pj[u], __low2float(vv[u]), a0);
+          a1 = fmaf(pj[u], __high2float(vv[u]), a1);
+        }
       }
     }
   }
