@@ -345,6 +345,31 @@ def main():
                     "whole_step_frac": (value / world) * flops_per_sentence(S) / 1e12 / peak}
         del a, f
 
+    # ---- ragged variant: lengths U{16..128}; the engine packs tokens, the reference would pad to 128 ----
+    ragged = None
+    if rank == 0 and world == 1 and (B, S) == (BATCH, SEQ):
+        from sonar_b200 import PaddingMask
+
+        gl = torch.Generator().manual_seed(7)
+        lens = torch.randint(16, 129, (B,), generator=gl)
+        lens_list = lens.tolist()
+        rb = SequenceBatch(ids_dev, PaddingMask(lens, S, lens_list))
+        for _ in range(2):
+            model(rb)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(3):
+            model(rb)
+        r1.record()
+        torch.cuda.synchronize()
+        rms = r0.elapsed_time(r1) / 3
+        rflops = sum(flops_per_sentence(n) for n in lens_list)
+        peak_s = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))
+        ragged = {"lengths": "U{16..128}, seed 7", "tokens": int(lens.sum()), "padded_tokens": B * S,
+                  "value": B / rms * 1e3, "unit": "sentences/s", "ms_per_step": rms,
+                  "roofline_frac_of_real_flops": rflops / (rms / 1e3) / 1e12 / peak_s}
+
     cpu_baseline = None
     if sd_cpu is not None:
         calibrate_cpu_threads()
@@ -378,6 +403,7 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "ragged": ragged,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

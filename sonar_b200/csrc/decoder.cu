@@ -93,12 +93,21 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __
 // Incremental causal self-attention: one warp per (row, head).  Appends this step's K/V to the cache at
 // position t (physical row r) and attends over positions 0..t, where position t' < t of hypothesis r lives in
 // physical cache row table[r, t'] (its ancestor at that step).
-//   phase 1: lanes are parallel over keys (each lane owns keys lane, lane+32, ... and does the full 64-dim dot
-//            against q held in registers) -- no shuffles inside the loop;
-//   phase 2: one warp max / sum for the softmax;
-//   phase 3: lanes are parallel over the 64 output dims (2 each); each key's probability and cache row are
-//            broadcast with one shuffle, V rows are read fully coalesced.
-constexpr int kMaxKeyIters = 16;  // positions <= 512 (the decoder's position table)
+// The warp walks the keys FOUR at a time: lane group g = lane/8 owns keys g, g+4, ..., and inside a group each lane
+// owns 8 of the 64 head dims, so every K and V access is one 16-byte load per lane and 128 contiguous bytes per group.
+// Each group keeps its own online-softmax state (max, sum, 8 accumulators per lane); the four states are merged
+// with two shuffle rounds at the end.  HBM-bound: 2 x 128 B per (hypothesis, head, cached position).
+constexpr int kMaxDecodeLen = 512;  // positions <= the decoder's position table
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+    f[2 * e] = __low2float(b);
+    f[2 * e + 1] = __high2float(b);
+  }
+}
 
 __global__ void __launch_bounds__(128)
 decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ kcache,
@@ -110,92 +119,66 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
   if (h >= H) return;
   const int D = H * 64;
   const __nv_bfloat16* row = qkv + (long long)r * 3 * D + h * 64;
-  // append this step's K / V (2 dims per lane) to the cache
-  {
-    const __nv_bfloat162 k2 = *reinterpret_cast<const __nv_bfloat162*>(row + D + lane * 2);
-    const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(row + 2 * D + lane * 2);
+  {  // append this step's K / V (2 dims per lane) to the cache
     const long long own = ((long long)r * Tmax + t) * D + h * 64 + lane * 2;
-    *reinterpret_cast<__nv_bfloat162*>(kcache + own) = k2;
-    *reinterpret_cast<__nv_bfloat162*>(vcache + own) = v2;
+    *reinterpret_cast<__nv_bfloat162*>(kcache + own) = *reinterpret_cast<const __nv_bfloat162*>(row + D + lane * 2);
+    *reinterpret_cast<__nv_bfloat162*>(vcache + own) = *reinterpret_cast<const __nv_bfloat162*>(row + 2 * D + lane * 2);
   }
-  float q[64];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint4 u = *reinterpret_cast<const uint4*>(row + c * 8);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
-      q[c * 8 + 2 * e] = __low2float(b);
-      q[c * 8 + 2 * e + 1] = __high2float(b);
-    }
-  }
-  __syncwarp();  // the row written above is read back below by a single lane
+  const int grp = lane >> 3, sub = lane & 7;
+  float q8[8];
+  unpack8(*reinterpret_cast<const uint4*>(row + sub * 8), q8);
+  __syncwarp();  // the row appended above is read back below by other lanes of this warp
   const int nk = t + 1;
   const int32_t* trow = table + (long long)r * Tmax;
-  float sc[kMaxKeyIters];
-  int prow[kMaxKeyIters];
-  float m = -CUDART_INF_F;
-#pragma unroll
-  for (int i = 0; i < kMaxKeyIters; ++i) {
-    sc[i] = -CUDART_INF_F;
-    prow[i] = r;
-    const int tp = i * 32 + lane;
-    if (i * 32 < nk && tp < nk) {
-      prow[i] = (tp == t) ? r : trow[tp];
-      const uint4* kp = reinterpret_cast<const uint4*>(kcache + ((long long)prow[i] * Tmax + tp) * D + h * 64);
-      float d0 = 0.f, d1 = 0.f;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint4 u = kp[c];
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
-          d0 = fmaf(q[c * 8 + 2 * e], __low2float(b), d0);
-          d1 = fmaf(q[c * 8 + 2 * e + 1], __high2float(b), d1);
-        }
-      }
-      sc[i] = d0 + d1;
-      m = fmaxf(m, sc[i]);
-    }
-  }
-  m = warp_max(m);
   const float sl2 = 0.125f * 1.4426950408889634f;
-  float l = 0.f;
+  float m = -CUDART_INF_F, l = 0.f;
+  float acc[8];
 #pragma unroll
-  for (int i = 0; i < kMaxKeyIters; ++i) {
-    sc[i] = exp2f((sc[i] - m) * sl2);  // exp2(-inf) = 0 for the slots without a key
-    l += sc[i];
-  }
-  l = warp_sum(l);
-  float a0 = 0.f, a1 = 0.f;
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int base = 0; base < nk; base += 4) {
+    const int tp = base + grp;
+    const bool valid = tp < nk;
+    const int pr = (valid && tp != t) ? trow[tp] : r;
+    const long long off = ((long long)pr * Tmax + (valid ? tp : t)) * D + h * 64 + sub * 8;
+    float k8[8], v8[8];
+    unpack8(*reinterpret_cast<const uint4*>(kcache + off), k8);
+    unpack8(*reinterpret_cast<const uint4*>(vcache + off), v8);
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kMaxKeyIters; ++i) {
-    if (i * 32 < nk) {
-      const int cnt = min(32, nk - i * 32);
-      // 8 independent V loads in flight per step (the loads only depend on shuffles, never on each other)
-      for (int j0 = 0; j0 < cnt; j0 += 8) {
-        __nv_bfloat162 vv[8];
-        float pj[8];
+    for (int e = 0; e < 8; ++e) s = fmaf(q8[e], k8[e], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (valid) {  // uniform inside each 8-lane group
+      const float mn = fmaxf(m, s);
+      const float corr = exp2f((m - mn) * sl2);  // m = -inf on the group's first key -> 0
+      const float pj = exp2f((s - mn) * sl2);
+      l = l * corr + pj;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int j = min(j0 + u, cnt - 1);
-          pj[u] = (j0 + u < cnt) ? __shfl_sync(0xffffffffu, sc[i], j) : (__shfl_sync(0xffffffffu, sc[i], j), 0.f);
-          const int pr = __shfl_sync(0xffffffffu, prow[i], j);
-          vv[u] = *reinterpret_cast<const __nv_bfloat162*>(
-              vcache + ((long long)pr * Tmax + (i * 32 + j)) * D + h * 64 + lane * 2);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          a0 = fmaf(pj[u], __low2float(vv[u]), a0);
-          a1 = fmaf(pj[u], __high2float(vv[u]), a1);
-        }
-      }
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, v8[e], acc[e] * corr);
+      m = mn;
     }
   }
-  const float inv = 1.0f / l;
-  *reinterpret_cast<uint32_t*>(out + (long long)r * D + h * 64 + lane * 2) = pack_bf16x2(a0 * inv, a1 * inv);
+  // merge the four group states (a group that saw no key has m = -inf, l = 0)
+  float M = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+  M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 16));
+  const float sc = (m == -CUDART_INF_F) ? 0.f : exp2f((m - M) * sl2);
+  l *= sc;
+  l += __shfl_xor_sync(0xffffffffu, l, 8);
+  l += __shfl_xor_sync(0xffffffffu, l, 16);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float a = acc[e] * sc;
+    a += __shfl_xor_sync(0xffffffffu, a, 8);
+    a += __shfl_xor_sync(0xffffffffu, a, 16);
+    acc[e] = a;
+  }
+  if (grp == 0) {
+    const float inv = 1.0f / l;
+    *reinterpret_cast<uint4*>(out + (long long)r * D + h * 64 + sub * 8) =
+        make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
+                   pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
+  }
 }
 
 // Merge the per-chunk partials of the vocabulary GEMM: one warp per row.
@@ -459,7 +442,7 @@ int sb_decoder_step(SbDecoder* d, const int64_t* tokens, const int32_t* table, i
   if (rc) return rc;
   if (!tokens || !table || !out_lprob || !out_tok || !out_eos_lprob) { set_last_error("sb_decoder_step: null pointer"); return SB_ERR_INVALID; }
   if (t < 0 || t >= max_len) { set_last_error("sb_decoder_step: position %d outside [0,%d)", t, max_len); return SB_ERR_INVALID; }
-  if (max_len > 32 * kMaxKeyIters) { set_last_error("sb_decoder_step: max_len %d > %d", max_len, 32 * kMaxKeyIters); return SB_ERR_INVALID; }
+  if (max_len > kMaxDecodeLen) { set_last_error("sb_decoder_step: max_len %d > %d", max_len, kMaxDecodeLen); return SB_ERR_INVALID; }
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   const int D = d->cfg.model_dim, F = d->cfg.ffn_inner_dim, H = d->cfg.num_heads;
   const int R = N * beam;
