@@ -302,7 +302,13 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), clocks
 
+    # dominant kernel timed INSIDE the real steps: events recorded by the engine around the middle layer's FFN1 GEMM
+    k_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    k_ev[0].record(); k_ev[1].record()  # materialise the handles
+    model.profile_ffn1(*k_ev)
     total_ms, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
+    in_step_kernel_ms = k_ev[0].elapsed_time(k_ev[1])  # the last timed step's launch
+    model.profile_ffn1(None, None)
     e2e_ms, _ = timed(step_e2e, args.steps, 1)
     model.check_inputs()
     value = world * B * args.steps / (total_ms / 1e3)
@@ -329,19 +335,23 @@ def main():
         torch.cuda.synchronize()
         kms = k0.elapsed_time(k1) / reps
         flops = 2.0 * T * FFN * D  # algorithmic FLOPs of one launch
-        achieved = flops / (kms / 1e3) / 1e12
+        alone_tflops = flops / (kms / 1e3) / 1e12
+        achieved = flops / (in_step_kernel_ms / 1e3) / 1e12  # the launch inside the last timed step
         peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))
+        burst = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
         traffic = None
         tp = os.path.join(ROOT, "profiles", "ncu_gemm_ffn1.json")
         if os.path.exists(tp) and (B, S) == (BATCH, SEQ):
-            with open(tp) as f:
-                tj = json.load(f)
+            with open(tp) as fh:
+                tj = json.load(fh)
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]  # per launch, from the committed ncu capture
         roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel<cta_group,EPI_BIAS_RELU,bf16> "
                     f"M={T} N={FFN} K={D}", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": traffic,
-                    "algorithmic_bytes": 2.0 * T * D + 2.0 * FFN * D + 4.0 * FFN + 2.0 * T * FFN, "peak_source": f"{peak_kind} bf16_tflops_sustained",
-                    "ms_per_launch": kms,
+                    "frac": achieved / peak, "traffic": traffic, "ms_per_launch_in_step": in_step_kernel_ms,
+                    "timed_alone": {"achieved": alone_tflops, "peak": burst, "frac": alone_tflops / burst,
+                                    "peak_source": f"{peak_kind} bf16_tflops (burst)", "ms_per_launch": kms},
+                    "algorithmic_bytes": 2.0 * T * D + 2.0 * FFN * D + 4.0 * FFN + 2.0 * T * FFN,
+                    "peak_source": f"{peak_kind} bf16_tflops_sustained (kernel timed inside the long step)",
                     "whole_step_frac": (value / world) * flops_per_sentence(S) / 1e12 / peak}
         del a, f
 

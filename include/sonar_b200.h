@@ -124,6 +124,11 @@ int sb_encoder_forward_host(SbEncoder* enc, const int64_t* ids_host, const int32
                             int32_t seq_len, float* out_host, int64_t* ids_staging, float* out_staging,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* Measurement hook: every following forward records the two caller-owned CUDA events (cudaEvent_t, timing enabled)
+ * around the FFN inner-projection GEMM of the middle layer -- the dominant kernel -- on the forward's stream, so its
+ * duration can be read INSIDE a real step.  Pass NULL, NULL to switch it off. */
+int sb_encoder_profile_ffn1(SbEncoder* enc, void* start_event, void* stop_event);
+
 /* Checks the sticky device-side input flag (token id out of range) of the last forwards;
  * synchronises `stream`.  Returns SB_OK or SB_ERR_INPUT. */
 int sb_encoder_check_inputs(SbEncoder* enc, void* workspace, void* stream);

@@ -97,6 +97,7 @@ _SIGNATURES = {
     "sb_encoder_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                           C.c_void_p]),
+    "sb_encoder_profile_ffn1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sb_encoder_check_inputs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sb_gemm_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,

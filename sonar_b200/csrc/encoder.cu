@@ -64,6 +64,8 @@ struct SbEncoder {
   cudaEvent_t ev[kSlots];
   bool ev_ok[kSlots];
   unsigned next_slot = 0;
+  // optional in-step timing of the dominant kernel (FFN inner-projection GEMM of the middle layer)
+  cudaEvent_t prof_start = nullptr, prof_stop = nullptr;
 };
 
 static Workspace carve(const SbEncoder* e, int32_t max_batch, int64_t max_tokens, void* base) {
@@ -257,7 +259,10 @@ int sb_encoder_forward(SbEncoder* e, const int64_t* ids, int64_t ids_row_stride,
     g.A = w.h; g.lda = D; g.W = reinterpret_cast<const __nv_bfloat16*>(L.w1); g.ldw = D;
     g.C = w.f; g.ldc = F; g.out_fp32 = 0; g.bias = L.b1; g.residual = nullptr; g.ldr = 0;
     g.N = F; g.K = D; g.epi = EPI_BIAS_RELU;
+    const bool prof = e->prof_start && li == e->cfg.num_layers / 2;
+    if (prof) SB_CUDA_CHECK(cudaEventRecord(e->prof_start, stream));
     if ((rc = gemm_bf16(g, stream))) return rc;
+    if (prof) SB_CUDA_CHECK(cudaEventRecord(e->prof_stop, stream));
     g.A = w.f; g.lda = F; g.W = reinterpret_cast<const __nv_bfloat16*>(L.w2); g.ldw = F;
     g.C = w.x; g.ldc = D; g.out_fp32 = 1; g.bias = L.b2; g.residual = w.x; g.ldr = D;
     g.N = D; g.K = F; g.epi = EPI_BIAS_RESIDUAL;
@@ -283,6 +288,13 @@ int sb_encoder_forward_host(SbEncoder* e, const int64_t* ids_host, const int32_t
   SB_CUDA_CHECK(cudaMemcpyAsync(out_host, out_staging, sizeof(float) * (size_t)B * e->cfg.model_dim,
                                 cudaMemcpyDeviceToHost, stream));
   SB_CUDA_CHECK(cudaStreamSynchronize(stream));
+  return SB_OK;
+}
+
+int sb_encoder_profile_ffn1(SbEncoder* e, void* start_event, void* stop_event) {
+  if (!e || (!start_event) != (!stop_event)) { set_last_error("sb_encoder_profile_ffn1: bad argument"); return SB_ERR_INVALID; }
+  e->prof_start = reinterpret_cast<cudaEvent_t>(start_event);
+  e->prof_stop = reinterpret_cast<cudaEvent_t>(stop_event);
   return SB_OK;
 }
 

@@ -270,6 +270,13 @@ class B200TextEncoderModel(torch.nn.Module):
         _lib.check(rc, "sb_encoder_forward")
         return SonarEncoderOutput(encoded_seqs=enc, sentence_embeddings=out, padding_mask=pm)
 
+    def profile_ffn1(self, start: Optional[torch.cuda.Event], stop: Optional[torch.cuda.Event]) -> None:
+        """Record `start`/`stop` (timing-enabled events that have been recorded once, so their handles exist) around
+        the FFN inner-projection GEMM of the middle layer in every following forward; (None, None) switches it off."""
+        _lib.check(self._lib.sb_encoder_profile_ffn1(self._handle, start.cuda_event if start is not None else None,
+                                                     stop.cuda_event if stop is not None else None),
+                   "sb_encoder_profile_ffn1")
+
     def check_inputs(self) -> None:
         """Raise ``ValueError`` if the last batch contained a token id outside the vocabulary."""
         if self._workspace is None:
