@@ -1,4 +1,4 @@
-from .speech import SpeechToEmbeddingModelPipeline  # noqa: F401
+from .speech import SpeechToEmbeddingModelPipeline, SpeechToTextModelPipeline  # noqa: F401
 from .text import (  # noqa: F401
     EmbeddingToTextModelPipeline,
     TextToEmbeddingModelPipeline,

@@ -1,5 +1,6 @@
-"""Drop-in mirror of ``sonar.inference_pipelines.speech.SpeechToEmbeddingModelPipeline``
-(``/root/reference/sonar/inference_pipelines/speech.py:402-474``): same constructor / ``predict`` signature; the
+"""Drop-in mirrors of ``sonar.inference_pipelines.speech.SpeechToEmbeddingModelPipeline``
+(``/root/reference/sonar/inference_pipelines/speech.py:402-474``) and ``SpeechToTextModelPipeline``
+(``speech.py:311-400``): same constructor / ``predict`` signature; the
 fairseq2n operators are replaced by the GPU fbank frontend (``sonar_b200.speech_frontend``) and the model stage by
 ``B200SpeechEncoderModel``.  Inputs are ``[C, T]`` waveform tensors at 16 kHz (``_decode_audio`` transposes to
 ``[T, C]``, ``speech.py:298-304``) or paths to PCM-16 mono ``.wav`` files (the reference decodes any libsndfile
@@ -16,9 +17,11 @@ import torch
 from torch import Tensor
 
 from ..batching import bucket, prefetch
+from ..generation import BeamSearchSeq2SeqGenerator, SequenceToTextConverter
 from ..sequence import PaddingMask, SequenceBatch
 from ..speech_encoder import B200SpeechEncoderModel
 from ..speech_frontend import SAMPLE_RATE, WaveformToFbank
+from ..text_decoder import B200TextDecoderModel
 from .utils import add_progress_bar
 
 Device = Union[str, torch.device]
@@ -77,3 +80,46 @@ class SpeechToEmbeddingModelPipeline(torch.nn.Module):
             pipeline = add_progress_bar(pipeline, inputs=input, batch_size=batch_size)
         results = list(iter(pipeline))
         return torch.cat(results, dim=0)
+
+
+class SpeechToTextModelPipeline(SpeechToEmbeddingModelPipeline):
+    """Speech -> text (``speech.py:311-400``).  The reference wraps encoder and decoder as
+    ``SonarEncoderDecoderModel`` whose ``encode`` hands the decoder the pooled sentence embedding as a one-position
+    encoder output (``sonar/models/sonar_translation/model.py:48-53``); here the speech engine produces that
+    embedding and the decoder engine's beam search consumes it, both on the device, per bucket of utterances."""
+
+    decoder: B200TextDecoderModel
+
+    def __init__(self, encoder: Union[str, B200SpeechEncoderModel], decoder: Union[str, B200TextDecoderModel], tokenizer,
+                 device: Device = CPU_DEVICE, fbank_dtype: torch.dtype = torch.float32) -> None:
+        super().__init__(encoder, device=device, fbank_dtype=fbank_dtype)
+        if isinstance(decoder, str):
+            raise FileNotFoundError(f"decoder card {decoder!r} cannot be resolved offline; pass a B200TextDecoderModel object")
+        if isinstance(tokenizer, str):
+            raise FileNotFoundError(f"tokenizer card {tokenizer!r} cannot be resolved offline; pass a tokenizer object")
+        self.decoder = decoder.eval()  # type: ignore
+        self.tokenizer = tokenizer
+
+    @torch.inference_mode()
+    def predict(self, input: Union[Sequence[str], Sequence[Tensor]], target_lang: str, batch_size: int = 3,  # type: ignore
+                n_parallel: int = 1, pad_idx: int = 0, n_prefetched_batches: int = 2, progress_bar: bool = False,
+                **generator_kwargs) -> List[str]:
+        if pad_idx != 0:
+            raise NotImplementedError("fbank batches are zero padded (the reference default)")
+        generator_kwargs.setdefault("pad_idx", self.tokenizer.vocab_info.pad_idx)
+        generator = BeamSearchSeq2SeqGenerator(self.decoder, **generator_kwargs)
+        converter = SequenceToTextConverter(generator, self.tokenizer, task="translation", target_lang=target_lang)
+
+        def run(group: List[Tensor]) -> List[str]:
+            fb, frames = self.convert_to_fbank(group)
+            mask = PaddingMask(torch.tensor(frames), fb.shape[1], seq_lens_host=frames)
+            emb = self.model(SequenceBatch(fb, mask)).sentence_embeddings
+            texts, _ = converter.batch_convert(emb, None)
+            return texts
+
+        groups = bucket((self._decode_audio(x) for x in input), batch_size)
+        pipeline: Iterable = (run(g) for g in prefetch(groups, n_prefetched_batches))
+        if progress_bar:
+            pipeline = add_progress_bar(pipeline, inputs=input, batch_size=batch_size)
+        results: List[List[str]] = list(iter(pipeline))
+        return [x for y in results for x in y]

@@ -131,3 +131,31 @@ def test_speech_pipeline_end_to_end(speech_small, cuda_device, tmp_path):
     e_file = pipe.predict([str(path)])
     e_tensor = pipe.predict([(pcm.float() / 32768.0)[None, :]])
     torch.testing.assert_close(e_file, e_tensor, rtol=1e-5, atol=1e-5)
+
+
+def test_speech_to_text_pipeline_composes_encoder_and_decoder(speech_small, cuda_device):
+    """``SpeechToTextModelPipeline`` (speech.py:311-400) = speech encoder -> one-position encoder output -> beam
+    search: its texts equal EmbeddingToText over SpeechToEmbedding's vectors with the same bucketing."""
+    from oracle.text_decoder import OracleDecoderConfig, make_synthetic_decoder_state_dict
+    from sonar_b200 import B200TextDecoderModel, VocabularyInfo, sonar_text_decoder_config
+    from sonar_b200.inference_pipelines import (EmbeddingToTextModelPipeline, SpeechToEmbeddingModelPipeline,
+                                                SpeechToTextModelPipeline)
+    from sonar_b200.tokenizer import SyntheticTokenizer
+
+    _, enc = speech_small
+    vocab = 4096
+    ocfg = OracleDecoderConfig(vocab_size=vocab, num_layers=2, max_seq_len=64)
+    sd = make_synthetic_decoder_state_dict(ocfg, seed=4)
+    cfg = sonar_text_decoder_config("basic", num_decoder_layers=2, max_seq_len=64,
+                                    vocab_info=VocabularyInfo(size=vocab, unk_idx=1, bos_idx=2, eos_idx=3, pad_idx=1))
+    dec = B200TextDecoderModel(cfg, sd, cuda_device)
+    tok = SyntheticTokenizer(vocab_size=vocab)
+    g = torch.Generator().manual_seed(11)
+    waves = [(torch.randn(12000 + 777 * i, generator=g) * 0.1).clamp(-1, 1)[None, :] for i in range(4)]
+    s2t = SpeechToTextModelPipeline(enc, dec, tok, device=cuda_device)
+    texts = s2t.predict(waves, target_lang="fra_Latn", batch_size=2, max_seq_len=10)
+    assert len(texts) == 4 and all(isinstance(t, str) for t in texts)
+    emb = SpeechToEmbeddingModelPipeline(enc, device=cuda_device).predict(waves, batch_size=2)
+    want = EmbeddingToTextModelPipeline(dec, tok, device=cuda_device).predict(emb, target_lang="fra_Latn", batch_size=2,
+                                                                              max_seq_len=10)
+    assert texts == want
