@@ -72,7 +72,7 @@ elif which == "decoder":  # a few full-size decoder steps (512 x beam 5), for a 
     r = n * beam
     table = torch.arange(r, dtype=torch.int32, device=dev)[:, None].expand(r, tmax).contiguous()
     tk = torch.randint(4, 256000, (r,), device=dev)
-    for t in (0, 1, 64):
+    for t in (0, 1, 64, 120):
         model.step(tk, table, t)
 torch.cuda.synchronize()
 print("done", which)

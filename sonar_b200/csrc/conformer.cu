@@ -92,22 +92,36 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 }
 __device__ __forceinline__ uint32_t toff(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
-// Dynamic shared memory layout of attention_relpos_kernel (bytes)
-constexpr int kRpQ = 0, kRpK = 16384, kRpV = 24576, kRpP = 32768 /* 192-row band of p */, kRpG = 57344 /* 8 x [16][80] fp32 */;
-constexpr int kRpVp = kRpG + 8 * 16 * 80 * 4, kRpU = kRpVp + 192 * 4, kRpKb = kRpU + 64 * 4;
-constexpr int kRpSmem = kRpKb + 64 * 4;
+// Dynamic shared memory layout of attention_relpos_kernel (bytes).  G (the per-warp [16 x 88] fp32 band products) also
+// serves as the Q staging area before the key loop and as the output staging area after it.
+constexpr int kRpGStride = 88;                                    // floats per G row: 8-byte stores of 4 rows hit 32 distinct banks
+constexpr int kRpG = 0, kRpGBytes = 8 * 16 * kRpGStride * 4;      // 45056
+constexpr int kRpKV = kRpG + kRpGBytes;                           // 2 stages x (K 8 KB | V 8 KB)
+constexpr int kRpP = kRpKV + 2 * 16384;                           // ring of 256 rows of p (32 KB): 192 live + 64 in flight
+constexpr int kRpVp = kRpP + 256 * 128, kRpU = kRpVp + 256 * 4, kRpKb = kRpU + 64 * 4;
+constexpr int kRpSmem = kRpKb + 64 * 4;                           // 112128 B -> two CTAs per SM
+static_assert(kRpGBytes >= 16384, "Q / output staging lives inside G");
 
-// score(i,j) = (q_i.k_j + u.k_j + q_i.p[c-1-i+j] + v.p[c-1-i+j]) / 8 with c = S_center.  Per 64-key block the CTA stages
-// the 192 rows of p its 128 queries can reach; each warp multiplies its 16 queries with its own 80-row window on the
-// tensor cores (mma.sync), adds v.p, parks the [16 x 80] result in shared memory and reads it back along the
-// anti-diagonals -- the Transformer-XL "shift" -- while it masks and soft-maxes q.k^T.
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void cp4(uint32_t dst, const void* src, bool ok) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// score(i,j) = (q_i.k_j + u.k_j + q_i.p[c-1-i+j] + v.p[c-1-i+j]) / 8 with c = S_center.  Per 64-key block the CTA needs the
+// 192 rows of p its 128 queries can reach; consecutive key blocks share 128 of them, so p lives in a 256-row ring and only
+// 64 new rows arrive per block, prefetched with K and V one block ahead (cp.async double buffering).  Each warp multiplies
+// its 16 queries with its own 80-row window on the tensor cores (mma.sync), adds v.p, parks the [16 x 80] result in shared
+// memory and reads it back along the anti-diagonals -- the Transformer-XL "shift" -- while it masks and soft-maxes q.k^T.
+__global__ void __launch_bounds__(256, 2)
 attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu, int H,
                         const float* __restrict__ u_bias, const __nv_bfloat16* __restrict__ p, const float* __restrict__ vp,
                         int Npad, int S_center, __nv_bfloat16* __restrict__ out) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sQ = smem + kRpQ;
-  uint8_t* sK = smem + kRpK;
+  uint8_t* sQ = smem + kRpG;
   float* s_vp = reinterpret_cast<float*>(smem + kRpVp);
   float* s_u = reinterpret_cast<float*>(smem + kRpU);
   float* s_kb = reinterpret_cast<float*>(smem + kRpKb);
@@ -120,16 +134,47 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
   const __nv_bfloat16* qbase = qkv + (long long)start * rs + h * 64;
   const __nv_bfloat16* kbase = qbase + D;
   const __nv_bfloat16* vbase = qbase + 2 * D;
+  const __nv_bfloat16* pbase = p + h * 64;
+  const float* vpbase = vp + (long long)h * Npad;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t sQa = smem_u32(sQ), sKa = smem_u32(sK), sVa = smem_u32(smem + kRpV), sPa = smem_u32(smem + kRpP);
-  float* sG = reinterpret_cast<float*>(smem + kRpG) + warp * 16 * 80;
+  const uint32_t sQa = smem_u32(sQ), sKVa = smem_u32(smem + kRpKV), sPa = smem_u32(smem + kRpP), sVpa = smem_u32(s_vp);
+  float* sG = reinterpret_cast<float*>(smem + kRpG) + warp * 16 * kRpGStride;
+  const int band_first = S_center - 1 - (q0 + 127);  // p row of ring position 0
+  const int nkb = (len + 63) / 64;
+
+  // K/V of key block kb -> stage kb&1; ring positions [r_lo, r_hi) of p and v.p
+  auto issue_loads = [&](int kb, int r_lo, int r_hi) {
+    const int k0 = kb * 64;
+    const uint32_t sKa = sKVa + (kb & 1) * 16384, sVa = sKa + 8192;
+    for (int i = tid; i < 64 * 8; i += 256) {
+      const int r = i >> 3, c = i & 7;
+      const bool ok = (k0 + r) < len;
+      const long long g = (long long)(ok ? k0 + r : 0) * rs + c * 8;
+      cp16(sKa + toff(r, c), kbase + g, ok);
+      cp16(sVa + toff(r, c), vbase + g, ok);
+    }
+    for (int i = r_lo * 8 + tid; i < r_hi * 8; i += 256) {
+      const int rr = i >> 3, c = i & 7;
+      const int idx = band_first + rr;
+      const bool ok = idx >= 0 && idx < Npad;
+      cp16(sPa + toff(rr & 255, c), pbase + (long long)(ok ? idx : 0) * D + c * 8, ok);
+    }
+    for (int rr = r_lo + tid; rr < r_hi; rr += 256) {
+      const int idx = band_first + rr;
+      const bool ok = idx >= 0 && idx < Npad;
+      cp4(sVpa + (rr & 255) * 4, vpbase + (ok ? idx : 0), ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
   if (tid < 64) s_u[tid] = u_bias[h * 64 + tid];
   for (int i = tid; i < 128 * 8; i += 256) {
     const int r = i >> 3, c = i & 7;
     const bool ok = (q0 + r) < len;
     cp16(sQa + toff(r, c), qbase + (long long)(ok ? q0 + r : 0) * rs + c * 8, ok);
   }
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  issue_loads(0, 0, 192);  // one group: Q + block 0
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   uint32_t qf[4][4];
   {
@@ -144,32 +189,17 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
   const float sl2 = 0.125f * 1.4426950408889634f;
   const int rl_lo = lane >> 2, rl_hi = rl_lo + 8;  // this thread's two rows inside the warp's 16
   const int wrow0 = 112 - 16 * warp;               // first row of this warp's 80-row window inside the 192-row band
+  const int kc = (lane & 3) * 2;
 
-  const int nkb = (len + 63) / 64;
   for (int kb = 0; kb < nkb; ++kb) {
     const int k0 = kb * 64;
-    const int band0 = S_center - 1 - (q0 + 127) + k0;  // p row held by band row 0
+    const int ring0 = kb * 64;  // ring position of band row 0 of this block
+    // block kb has landed (waited below / before the loop); everyone is past block kb-1 (and past the Q fragments)
     __syncthreads();
-    for (int i = tid; i < 64 * 8; i += 256) {
-      const int r = i >> 3, c = i & 7;
-      const bool ok = (k0 + r) < len;
-      const long long g = (long long)(ok ? k0 + r : 0) * rs + c * 8;
-      cp16(sKa + toff(r, c), kbase + g, ok);
-      cp16(sVa + toff(r, c), vbase + g, ok);
-    }
-    for (int i = tid; i < 192 * 8; i += 256) {
-      const int r = i >> 3, c = i & 7;
-      const int idx = band0 + r;
-      const bool ok = idx >= 0 && idx < Npad;
-      cp16(sPa + toff(r, c), p + (long long)(ok ? idx : 0) * D + h * 64 + c * 8, ok);
-    }
-    if (tid < 192) {
-      const int idx = band0 + tid;
-      s_vp[tid] = (idx >= 0 && idx < Npad) ? vp[(long long)h * Npad + idx] : 0.f;
-    }
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
+    if (kb + 1 < nkb) issue_loads(kb + 1, 192 + ring0, 256 + ring0);
+    const uint32_t sKa = sKVa + (kb & 1) * 16384, sVa = sKa + 8192;
     if (tid < 64) {  // u . k_j for the 64 keys of this block
+      const uint8_t* sK = smem + kRpKV + (kb & 1) * 16384;
       float acc = 0.f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -194,23 +224,21 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
 #pragma unroll
         for (int jp = 0; jp < 5; ++jp) {
           const int mtx = lane >> 3;
-          const int prow = wrow0 + (jp * 2 + (mtx >> 1)) * 8 + (lane & 7);
+          const int prow = (ring0 + wrow0 + (jp * 2 + (mtx >> 1)) * 8 + (lane & 7)) & 255;
           uint32_t b0, b1, b2, b3;
           ldsm4(sPa + toff(prow, kk * 2 + (mtx & 1)), b0, b1, b2, b3);
           mma16816(gacc[jp * 2], qf[kk], b0, b1);
           mma16816(gacc[jp * 2 + 1], qf[kk], b2, b3);
         }
       }
-      const int cc = (lane & 3) * 2;
 #pragma unroll
       for (int j = 0; j < 10; ++j) {
-        const int c = j * 8 + cc;
-        const float v0 = s_vp[wrow0 + c], v1 = s_vp[wrow0 + c + 1];
-        *reinterpret_cast<float2*>(sG + rl_lo * 80 + c) = make_float2(gacc[j][0] + v0, gacc[j][1] + v1);
-        *reinterpret_cast<float2*>(sG + rl_hi * 80 + c) = make_float2(gacc[j][2] + v0, gacc[j][3] + v1);
+        const int c = j * 8 + kc;
+        const float2 v01 = *reinterpret_cast<const float2*>(s_vp + ((ring0 + wrow0 + c) & 255));
+        *reinterpret_cast<float2*>(sG + rl_lo * kRpGStride + c) = make_float2(gacc[j][0] + v01.x, gacc[j][1] + v01.y);
+        *reinterpret_cast<float2*>(sG + rl_hi * kRpGStride + c) = make_float2(gacc[j][2] + v01.x, gacc[j][3] + v01.y);
       }
     }
-    __syncthreads();  // s_kb + every warp's G visible
     float s[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
@@ -226,36 +254,51 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
         mma16816(s[jp * 2 + 1], qf[kk], b2, b3);
       }
     }
-    const int kc = (lane & 3) * 2;
+    __syncthreads();  // s_kb visible (each warp's own G only needed __syncwarp)
+    const float* g_lo = sG + rl_lo * kRpGStride + 15 - rl_lo + kc;  // band column of (i, j): 15 - r + key
+    const float* g_hi = sG + rl_hi * kRpGStride + 15 - rl_hi + kc;
     float mx[2] = {-CUDART_INF_F, -CUDART_INF_F};
+    if (k0 + 64 <= len) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 8; ++j) {
+        const float2 kb2 = *reinterpret_cast<const float2*>(s_kb + j * 8 + kc);
+        s[j][0] += kb2.x + g_lo[j * 8];
+        s[j][1] += kb2.y + g_lo[j * 8 + 1];
+        s[j][2] += kb2.x + g_hi[j * 8];
+        s[j][3] += kb2.y + g_hi[j * 8 + 1];
+        mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
+      }
+    } else {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int kl = j * 8 + kc + (e & 1);
-        const int rl = (e < 2) ? rl_lo : rl_hi;
-        float val = -CUDART_INF_F;
-        if (k0 + kl < len) val = s[j][e] + s_kb[kl] + sG[rl * 80 + kl + 15 - rl];  // band column of (i, j): 15 - r + key
-        s[j][e] = val;
-        mx[e >> 1] = fmaxf(mx[e >> 1], val);
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int kl = j * 8 + kc + (e & 1);
+          float val = -CUDART_INF_F;
+          if (k0 + kl < len) val = s[j][e] + s_kb[kl] + ((e < 2) ? g_lo : g_hi)[j * 8 + (e & 1)];
+          s[j][e] = val;
+          mx[e >> 1] = fmaxf(mx[e >> 1], val);
+        }
       }
     }
-    float corr[2], mnew[2];
+    float corr[2], msc[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-      mnew[r] = fmaxf(m_run[r], mx[r]);
-      corr[r] = exp2f((m_run[r] - mnew[r]) * sl2);
-      m_run[r] = mnew[r];
+      const float mnew = fmaxf(m_run[r], mx[r]);  // finite: key 0 of every block is inside the utterance
+      corr[r] = ex2_approx((m_run[r] - mnew) * sl2);
+      m_run[r] = mnew;
+      msc[r] = mnew * sl2;
       l_run[r] *= corr[r];
     }
     uint32_t pf[4][4];
     float ls[2] = {0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float p0 = exp2f((s[j][0] - mnew[0]) * sl2), p1 = exp2f((s[j][1] - mnew[0]) * sl2);
-      const float p2 = exp2f((s[j][2] - mnew[1]) * sl2), p3 = exp2f((s[j][3] - mnew[1]) * sl2);
+      const float p0 = ex2_approx(fmaf(s[j][0], sl2, -msc[0])), p1 = ex2_approx(fmaf(s[j][1], sl2, -msc[0]));
+      const float p2 = ex2_approx(fmaf(s[j][2], sl2, -msc[1])), p3 = ex2_approx(fmaf(s[j][3], sl2, -msc[1]));
       ls[0] += p0 + p1;
       ls[1] += p2 + p3;
       pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
@@ -276,7 +319,9 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
         mma16816(o[jp * 2 + 1], pf[kk], b2, b3);
       }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's share of block kb+1; the loop-top barrier publishes it
   }
+  __syncthreads();  // every warp is done with its G before the region is reused for the output rows
   float inv[2];
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -329,27 +374,29 @@ glu_dwconv_kernel(const __nv_bfloat16* __restrict__ g, const int32_t* __restrict
       const __nv_bfloat16* row = g + (long long)(start + pos) * 2 * D + c0 + cp;
       const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(row);
       const __nv_bfloat162 gt = *reinterpret_cast<const __nv_bfloat162*>(row + D);
-      v0 = __low2float(a) / (1.0f + __expf(-__low2float(gt)));
-      v1 = __high2float(a) / (1.0f + __expf(-__high2float(gt)));
+      v0 = __low2float(a) * sigmoid_fast(__low2float(gt));
+      v1 = __high2float(a) * sigmoid_fast(__high2float(gt));
     }
     tile[p][cp] = v0;
     tile[p][cp + 1] = v1;
   }
   __syncthreads();
-  const int c = tid & 63, pg = tid >> 6;  // 4 groups of 16 positions
+  const int c = tid & 63, pg = tid >> 6;  // 4 groups of 16 positions; each thread slides a register window down one channel
   float w[KS];
 #pragma unroll
   for (int k = 0; k < KS; ++k) w[k] = dw[(long long)(c0 + c) * KS + k];
   const float sc = bn_scale[c0 + c], sh = bn_shift[c0 + c];
-  for (int pp = 0; pp < 16; ++pp) {
-    const int p = pg * 16 + pp;
-    const int pos = t0 + p;
-    if (pos >= len) break;
+  constexpr int PP = 16;
+  float win[PP + KS - 1];
+#pragma unroll
+  for (int i = 0; i < PP + KS - 1; ++i) win[i] = tile[pg * PP + i][c];
+#pragma unroll
+  for (int pp = 0; pp < PP; ++pp) {
+    const int pos = t0 + pg * PP + pp;
     float acc = 0.f;
 #pragma unroll
-    for (int k = 0; k < KS; ++k) acc = fmaf(w[k], tile[p + k][c], acc);
-    const float y = acc * sc + sh;
-    out[(long long)(start + pos) * D + c0 + c] = __float2bfloat16_rn(y / (1.0f + __expf(-y)));
+    for (int k = 0; k < KS; ++k) acc = fmaf(w[k], win[pp + k], acc);
+    if (pos < len) out[(long long)(start + pos) * D + c0 + c] = __float2bfloat16_rn(silu_fast(acc * sc + sh));
   }
 }
 

@@ -333,7 +333,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           }
           if constexpr (kEpi == EPI_BIAS_SILU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+            for (int j = 0; j < 32; ++j) f[j] = silu_fast(f[j]);
           }
           if constexpr (kEpi == EPI_BIAS_RESIDUAL) {
             if (grow < M) {
