@@ -92,10 +92,11 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 }
 __device__ __forceinline__ uint32_t toff(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
-// Dynamic shared memory layout of attention_relpos_kernel (bytes).  G (the per-warp [16 x 88] fp32 band products) also
-// serves as the Q staging area before the key loop and as the output staging area after it.
+// Dynamic shared memory layout of attention_relpos_kernel (bytes).  G (per warp two [16 x 88] fp32 band products, one per
+// 16-row m-tile) also serves as the Q staging area before the key loop and as the output staging area after it.
+constexpr int kRpThreads = 128;                                   // 4 warps x 32 query rows
 constexpr int kRpGStride = 88;                                    // floats per G row: 8-byte stores of 4 rows hit 32 distinct banks
-constexpr int kRpG = 0, kRpGBytes = 8 * 16 * kRpGStride * 4;      // 45056
+constexpr int kRpG = 0, kRpGBytes = 4 * 2 * 16 * kRpGStride * 4;  // 45056
 constexpr int kRpKV = kRpG + kRpGBytes;                           // 2 stages x (K 8 KB | V 8 KB)
 constexpr int kRpP = kRpKV + 2 * 16384;                           // ring of 256 rows of p (32 KB): 192 live + 64 in flight
 constexpr int kRpVp = kRpP + 256 * 128, kRpU = kRpVp + 256 * 4, kRpKb = kRpU + 64 * 4;
@@ -113,10 +114,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 // score(i,j) = (q_i.k_j + u.k_j + q_i.p[c-1-i+j] + v.p[c-1-i+j]) / 8 with c = S_center.  Per 64-key block the CTA needs the
 // 192 rows of p its 128 queries can reach; consecutive key blocks share 128 of them, so p lives in a 256-row ring and only
-// 64 new rows arrive per block, prefetched with K and V one block ahead (cp.async double buffering).  Each warp multiplies
-// its 16 queries with its own 80-row window on the tensor cores (mma.sync), adds v.p, parks the [16 x 80] result in shared
-// memory and reads it back along the anti-diagonals -- the Transformer-XL "shift" -- while it masks and soft-maxes q.k^T.
-__global__ void __launch_bounds__(256, 2)
+// 64 new rows arrive per block, prefetched with K and V one block ahead (cp.async double buffering).  The kernel is bound
+// by shared-memory wavefronts (ldmatrix), so each warp owns 32 query rows = two m-tiles that share every K, V and p
+// fragment it loads.  A warp multiplies its queries with its own 96-row window of p on the tensor cores (mma.sync), adds
+// v.p, parks the two [16 x 80] results in shared memory and reads them back along the anti-diagonals -- the
+// Transformer-XL "shift" -- while it masks and soft-maxes q.k^T.
+__global__ void __launch_bounds__(kRpThreads, 2)
 attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu, int H,
                         const float* __restrict__ u_bias, const __nv_bfloat16* __restrict__ p, const float* __restrict__ vp,
                         int Npad, int S_center, __nv_bfloat16* __restrict__ out) {
@@ -138,7 +141,7 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
   const float* vpbase = vp + (long long)h * Npad;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sQa = smem_u32(sQ), sKVa = smem_u32(smem + kRpKV), sPa = smem_u32(smem + kRpP), sVpa = smem_u32(s_vp);
-  float* sG = reinterpret_cast<float*>(smem + kRpG) + warp * 16 * kRpGStride;
+  float* sG = reinterpret_cast<float*>(smem + kRpG) + warp * 2 * 16 * kRpGStride;  // [m-tile][16][stride]
   const int band_first = S_center - 1 - (q0 + 127);  // p row of ring position 0
   const int nkb = (len + 63) / 64;
 
@@ -146,20 +149,20 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
   auto issue_loads = [&](int kb, int r_lo, int r_hi) {
     const int k0 = kb * 64;
     const uint32_t sKa = sKVa + (kb & 1) * 16384, sVa = sKa + 8192;
-    for (int i = tid; i < 64 * 8; i += 256) {
+    for (int i = tid; i < 64 * 8; i += kRpThreads) {
       const int r = i >> 3, c = i & 7;
       const bool ok = (k0 + r) < len;
       const long long g = (long long)(ok ? k0 + r : 0) * rs + c * 8;
       cp16(sKa + toff(r, c), kbase + g, ok);
       cp16(sVa + toff(r, c), vbase + g, ok);
     }
-    for (int i = r_lo * 8 + tid; i < r_hi * 8; i += 256) {
+    for (int i = r_lo * 8 + tid; i < r_hi * 8; i += kRpThreads) {
       const int rr = i >> 3, c = i & 7;
       const int idx = band_first + rr;
       const bool ok = idx >= 0 && idx < Npad;
       cp16(sPa + toff(rr & 255, c), pbase + (long long)(ok ? idx : 0) * D + c * 8, ok);
     }
-    for (int rr = r_lo + tid; rr < r_hi; rr += 256) {
+    for (int rr = r_lo + tid; rr < r_hi; rr += kRpThreads) {
       const int idx = band_first + rr;
       const bool ok = idx >= 0 && idx < Npad;
       cp4(sVpa + (rr & 255) * 4, vpbase + (ok ? idx : 0), ok);
@@ -168,7 +171,7 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
   };
 
   if (tid < 64) s_u[tid] = u_bias[h * 64 + tid];
-  for (int i = tid; i < 128 * 8; i += 256) {
+  for (int i = tid; i < 128 * 8; i += kRpThreads) {
     const int r = i >> 3, c = i & 7;
     const bool ok = (q0 + r) < len;
     cp16(sQa + toff(r, c), qbase + (long long)(ok ? q0 + r : 0) * rs + c * 8, ok);
@@ -176,20 +179,29 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
   issue_loads(0, 0, 192);  // one group: Q + block 0
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  uint32_t qf[4][4];
-  {
-    const int r = warp * 16 + (lane & 15);
+  uint32_t qf[2][4][4];
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) ldsm4(sQa + toff(r, kk * 2 + (lane >> 4)), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
+  for (int m = 0; m < 2; ++m) {
+    const int r = warp * 32 + m * 16 + (lane & 15);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      ldsm4(sQa + toff(r, kk * 2 + (lane >> 4)), qf[m][kk][0], qf[m][kk][1], qf[m][kk][2], qf[m][kk][3]);
   }
-  float o[8][4];
+  float o[2][8][4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
-  float m_run[2] = {-CUDART_INF_F, -CUDART_INF_F}, l_run[2] = {0.f, 0.f};
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[m][j][0] = o[m][j][1] = o[m][j][2] = o[m][j][3] = 0.f;
+  float m_run[2][2], l_run[2][2];
+#pragma unroll
+  for (int m = 0; m < 2; ++m) m_run[m][0] = m_run[m][1] = -CUDART_INF_F, l_run[m][0] = l_run[m][1] = 0.f;
   const float sl2 = 0.125f * 1.4426950408889634f;
-  const int rl_lo = lane >> 2, rl_hi = rl_lo + 8;  // this thread's two rows inside the warp's 16
-  const int wrow0 = 112 - 16 * warp;               // first row of this warp's 80-row window inside the 192-row band
+  const int rl_lo = lane >> 2, rl_hi = rl_lo + 8;  // this thread's two rows inside each 16-row m-tile
+  // band row (ring-relative to the block) of (query i, key j) is 127 - i + j.  The warp's 32 rows reach the 96-row window
+  // starting at wrow0; m-tile 0 (rows 32w..32w+15) uses window columns [16, 96), m-tile 1 uses [0, 80).
+  const int wrow0 = 96 - 32 * warp;
   const int kc = (lane & 3) * 2;
+  const int mtx = lane >> 3;
 
   for (int kb = 0; kb < nkb; ++kb) {
     const int k0 = kb * 64;
@@ -214,138 +226,161 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
       }
       s_kb[tid] = acc;
     }
-    // ---- G[16 x 80] = Q_warp . Pband_warp^T (+ v.p), parked in shared memory ----
-    {
-      float gacc[10][4];
+    // ---- G_m[16 x 80] = Q_m . Pwindow_m^T (+ v.p), parked in shared memory; window n-tile pair np feeds both m-tiles ----
 #pragma unroll
-      for (int j = 0; j < 10; ++j) gacc[j][0] = gacc[j][1] = gacc[j][2] = gacc[j][3] = 0.f;
+    for (int np = 0; np < 6; ++np) {
+      const bool use0 = np >= 1, use1 = np <= 4;  // m-tile 0: window n-tiles 2..11; m-tile 1: 0..9
+      float ga[2][2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int t = 0; t < 2; ++t) ga[m][t][0] = ga[m][t][1] = ga[m][t][2] = ga[m][t][3] = 0.f;
+      const int prow = (ring0 + wrow0 + (np * 2 + (mtx >> 1)) * 8 + (lane & 7)) & 255;
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-        for (int jp = 0; jp < 5; ++jp) {
-          const int mtx = lane >> 3;
-          const int prow = (ring0 + wrow0 + (jp * 2 + (mtx >> 1)) * 8 + (lane & 7)) & 255;
-          uint32_t b0, b1, b2, b3;
-          ldsm4(sPa + toff(prow, kk * 2 + (mtx & 1)), b0, b1, b2, b3);
-          mma16816(gacc[jp * 2], qf[kk], b0, b1);
-          mma16816(gacc[jp * 2 + 1], qf[kk], b2, b3);
+        uint32_t b0, b1, b2, b3;
+        ldsm4(sPa + toff(prow, kk * 2 + (mtx & 1)), b0, b1, b2, b3);
+        if (use0) {
+          mma16816(ga[0][0], qf[0][kk], b0, b1);
+          mma16816(ga[0][1], qf[0][kk], b2, b3);
+        }
+        if (use1) {
+          mma16816(ga[1][0], qf[1][kk], b0, b1);
+          mma16816(ga[1][1], qf[1][kk], b2, b3);
         }
       }
 #pragma unroll
-      for (int j = 0; j < 10; ++j) {
-        const int c = j * 8 + kc;
-        const float2 v01 = *reinterpret_cast<const float2*>(s_vp + ((ring0 + wrow0 + c) & 255));
-        *reinterpret_cast<float2*>(sG + rl_lo * kRpGStride + c) = make_float2(gacc[j][0] + v01.x, gacc[j][1] + v01.y);
-        *reinterpret_cast<float2*>(sG + rl_hi * kRpGStride + c) = make_float2(gacc[j][2] + v01.x, gacc[j][3] + v01.y);
+      for (int t = 0; t < 2; ++t) {
+        const int wc = (np * 2 + t) * 8 + kc;  // window column of this thread's pair
+        const float2 v01 = *reinterpret_cast<const float2*>(s_vp + ((ring0 + wrow0 + wc) & 255));
+        if (use0) {
+          float* g0 = sG + wc - 16;  // m-tile 0 stores relative to its own 80-column window
+          *reinterpret_cast<float2*>(g0 + rl_lo * kRpGStride) = make_float2(ga[0][t][0] + v01.x, ga[0][t][1] + v01.y);
+          *reinterpret_cast<float2*>(g0 + rl_hi * kRpGStride) = make_float2(ga[0][t][2] + v01.x, ga[0][t][3] + v01.y);
+        }
+        if (use1) {
+          float* g1 = sG + 16 * kRpGStride + wc;
+          *reinterpret_cast<float2*>(g1 + rl_lo * kRpGStride) = make_float2(ga[1][t][0] + v01.x, ga[1][t][1] + v01.y);
+          *reinterpret_cast<float2*>(g1 + rl_hi * kRpGStride) = make_float2(ga[1][t][2] + v01.x, ga[1][t][3] + v01.y);
+        }
       }
     }
-    float s[8][4];
+    float s[2][8][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[m][j][0] = s[m][j][1] = s[m][j][2] = s[m][j][3] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
       for (int jp = 0; jp < 4; ++jp) {
-        const int mtx = lane >> 3;
         const int key = (jp * 2 + (mtx >> 1)) * 8 + (lane & 7);
         uint32_t b0, b1, b2, b3;
         ldsm4(sKa + toff(key, kk * 2 + (mtx & 1)), b0, b1, b2, b3);
-        mma16816(s[jp * 2], qf[kk], b0, b1);
-        mma16816(s[jp * 2 + 1], qf[kk], b2, b3);
-      }
-    }
-    __syncthreads();  // s_kb visible (each warp's own G only needed __syncwarp)
-    const float* g_lo = sG + rl_lo * kRpGStride + 15 - rl_lo + kc;  // band column of (i, j): 15 - r + key
-    const float* g_hi = sG + rl_hi * kRpGStride + 15 - rl_hi + kc;
-    float mx[2] = {-CUDART_INF_F, -CUDART_INF_F};
-    if (k0 + 64 <= len) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float2 kb2 = *reinterpret_cast<const float2*>(s_kb + j * 8 + kc);
-        s[j][0] += kb2.x + g_lo[j * 8];
-        s[j][1] += kb2.y + g_lo[j * 8 + 1];
-        s[j][2] += kb2.x + g_hi[j * 8];
-        s[j][3] += kb2.y + g_hi[j * 8 + 1];
-        mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
-        mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int kl = j * 8 + kc + (e & 1);
-          float val = -CUDART_INF_F;
-          if (k0 + kl < len) val = s[j][e] + s_kb[kl] + ((e < 2) ? g_lo : g_hi)[j * 8 + (e & 1)];
-          s[j][e] = val;
-          mx[e >> 1] = fmaxf(mx[e >> 1], val);
+        for (int m = 0; m < 2; ++m) {
+          mma16816(s[m][jp * 2], qf[m][kk], b0, b1);
+          mma16816(s[m][jp * 2 + 1], qf[m][kk], b2, b3);
         }
       }
     }
-    float corr[2], msc[2];
+    __syncthreads();  // s_kb visible (each warp's own G only needed __syncwarp)
+    uint32_t pf[2][4][4];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-      const float mnew = fmaxf(m_run[r], mx[r]);  // finite: key 0 of every block is inside the utterance
-      corr[r] = ex2_approx((m_run[r] - mnew) * sl2);
-      m_run[r] = mnew;
-      msc[r] = mnew * sl2;
-      l_run[r] *= corr[r];
-    }
-    uint32_t pf[4][4];
-    float ls[2] = {0.f, 0.f};
+    for (int m = 0; m < 2; ++m) {
+      const float* g_lo = sG + (m * 16 + rl_lo) * kRpGStride + 15 - rl_lo + kc;  // band column of (i, j): 15 - r + key
+      const float* g_hi = sG + (m * 16 + rl_hi) * kRpGStride + 15 - rl_hi + kc;
+      float mx[2] = {-CUDART_INF_F, -CUDART_INF_F};
+      if (k0 + 64 <= len) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float p0 = ex2_approx(fmaf(s[j][0], sl2, -msc[0])), p1 = ex2_approx(fmaf(s[j][1], sl2, -msc[0]));
-      const float p2 = ex2_approx(fmaf(s[j][2], sl2, -msc[1])), p3 = ex2_approx(fmaf(s[j][3], sl2, -msc[1]));
-      ls[0] += p0 + p1;
-      ls[1] += p2 + p3;
-      pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
-      pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
-      o[j][0] *= corr[0]; o[j][1] *= corr[0]; o[j][2] *= corr[1]; o[j][3] *= corr[1];
+        for (int j = 0; j < 8; ++j) {
+          const float2 kb2 = *reinterpret_cast<const float2*>(s_kb + j * 8 + kc);
+          s[m][j][0] += kb2.x + g_lo[j * 8];
+          s[m][j][1] += kb2.y + g_lo[j * 8 + 1];
+          s[m][j][2] += kb2.x + g_hi[j * 8];
+          s[m][j][3] += kb2.y + g_hi[j * 8 + 1];
+          mx[0] = fmaxf(mx[0], fmaxf(s[m][j][0], s[m][j][1]));
+          mx[1] = fmaxf(mx[1], fmaxf(s[m][j][2], s[m][j][3]));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int kl = j * 8 + kc + (e & 1);
+            float val = -CUDART_INF_F;
+            if (k0 + kl < len) val = s[m][j][e] + s_kb[kl] + ((e < 2) ? g_lo : g_hi)[j * 8 + (e & 1)];
+            s[m][j][e] = val;
+            mx[e >> 1] = fmaxf(mx[e >> 1], val);
+          }
+        }
+      }
+      float corr[2], msc[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        const float mnew = fmaxf(m_run[m][r], mx[r]);  // finite: key 0 of every block is inside the utterance
+        corr[r] = ex2_approx((m_run[m][r] - mnew) * sl2);
+        m_run[m][r] = mnew;
+        msc[r] = mnew * sl2;
+        l_run[m][r] *= corr[r];
+      }
+      float ls[2] = {0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float p0 = ex2_approx(fmaf(s[m][j][0], sl2, -msc[0])), p1 = ex2_approx(fmaf(s[m][j][1], sl2, -msc[0]));
+        const float p2 = ex2_approx(fmaf(s[m][j][2], sl2, -msc[1])), p3 = ex2_approx(fmaf(s[m][j][3], sl2, -msc[1]));
+        ls[0] += p0 + p1;
+        ls[1] += p2 + p3;
+        pf[m][j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+        pf[m][j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+        o[m][j][0] *= corr[0]; o[m][j][1] *= corr[0]; o[m][j][2] *= corr[1]; o[m][j][3] *= corr[1];
+      }
+      l_run[m][0] += ls[0];
+      l_run[m][1] += ls[1];
     }
-    l_run[0] += ls[0];
-    l_run[1] += ls[1];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
       for (int jp = 0; jp < 4; ++jp) {
-        const int mtx = lane >> 3;
         const int key = kk * 16 + (mtx & 1) * 8 + (lane & 7);
         uint32_t b0, b1, b2, b3;
         ldsm4t(sVa + toff(key, jp * 2 + (mtx >> 1)), b0, b1, b2, b3);
-        mma16816(o[jp * 2], pf[kk], b0, b1);
-        mma16816(o[jp * 2 + 1], pf[kk], b2, b3);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          mma16816(o[m][jp * 2], pf[m][kk], b0, b1);
+          mma16816(o[m][jp * 2 + 1], pf[m][kk], b2, b3);
+        }
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's share of block kb+1; the loop-top barrier publishes it
   }
   __syncthreads();  // every warp is done with its G before the region is reused for the output rows
-  float inv[2];
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    float l = l_run[r];
-    l += __shfl_xor_sync(0xffffffffu, l, 1);
-    l += __shfl_xor_sync(0xffffffffu, l, 2);
-    inv[r] = 1.0f / l;
-  }
-  __syncwarp();
-  {
-    const int r0 = warp * 16 + (lane >> 2);
+  for (int m = 0; m < 2; ++m) {
+    float inv[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float l = l_run[m][r];
+      l += __shfl_xor_sync(0xffffffffu, l, 1);
+      l += __shfl_xor_sync(0xffffffffu, l, 2);
+      inv[r] = 1.0f / l;
+    }
+    const int r0 = warp * 32 + m * 16 + (lane >> 2);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int bo = (lane & 3) * 4;
-      *reinterpret_cast<uint32_t*>(sQ + toff(r0, j) + bo) = pack_bf16x2(o[j][0] * inv[0], o[j][1] * inv[0]);
-      *reinterpret_cast<uint32_t*>(sQ + toff(r0 + 8, j) + bo) = pack_bf16x2(o[j][2] * inv[1], o[j][3] * inv[1]);
+      *reinterpret_cast<uint32_t*>(sQ + toff(r0, j) + bo) = pack_bf16x2(o[m][j][0] * inv[0], o[m][j][1] * inv[0]);
+      *reinterpret_cast<uint32_t*>(sQ + toff(r0 + 8, j) + bo) = pack_bf16x2(o[m][j][2] * inv[1], o[m][j][3] * inv[1]);
     }
   }
   __syncwarp();
   __nv_bfloat16* obase = out + (long long)start * D + h * 64;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 8; ++i) {
     const int idx = i * 32 + lane;
-    const int r = warp * 16 + (idx >> 3), c = idx & 7;
+    const int r = warp * 32 + (idx >> 3), c = idx & 7;
     if (q0 + r < len)
       *reinterpret_cast<uint4*>(obase + (long long)(q0 + r) * D + c * 8) = *reinterpret_cast<const uint4*>(sQ + toff(r, c));
   }
@@ -356,29 +391,47 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
 //   g bf16 [T, 2D] (pointwise_conv1 output: value | gate), out bf16 [T, D]
 // ---------------------------------------------------------------------------------------------
 template <int KS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 glu_dwconv_kernel(const __nv_bfloat16* __restrict__ g, const int32_t* __restrict__ cu, int D,
                   const float* __restrict__ dw, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
                   __nv_bfloat16* __restrict__ out) {
   constexpr int TP = 64, HALO = KS / 2, ROWS = TP + KS - 1;
-  __shared__ float tile[ROWS][64];
+  __shared__ __align__(16) float tile[ROWS][64];
   const int b = blockIdx.z, c0 = blockIdx.y * 64, t0 = blockIdx.x * TP;
   const int start = cu[b], len = cu[b + 1] - start;
   if (t0 >= len) return;
   const int tid = threadIdx.x;
-  for (int i = tid; i < ROWS * 32; i += 256) {
-    const int p = i >> 5, cp = (i & 31) * 2;
-    const int pos = t0 - HALO + p;
-    float v0 = 0.f, v1 = 0.f;
-    if (pos >= 0 && pos < len) {
-      const __nv_bfloat16* row = g + (long long)(start + pos) * 2 * D + c0 + cp;
-      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(row);
-      const __nv_bfloat162 gt = *reinterpret_cast<const __nv_bfloat162*>(row + D);
-      v0 = __low2float(a) * sigmoid_fast(__low2float(gt));
-      v1 = __high2float(a) * sigmoid_fast(__high2float(gt));
+  // 16-byte loads, 8 channels of value and gate per thread; every load of the block is in flight before the first use
+  constexpr int kIt = (ROWS * 8 + 255) / 256;
+  uint4 a4[kIt], g4[kIt];
+#pragma unroll
+  for (int it = 0; it < kIt; ++it) {
+    const int i = tid + it * 256;
+    const int pos = t0 - HALO + (i >> 3);
+    a4[it] = g4[it] = make_uint4(0u, 0u, 0u, 0u);  // bf16 zeros: 0 * sigmoid(0) = 0 outside the utterance
+    if (i < ROWS * 8 && pos >= 0 && pos < len) {
+      const __nv_bfloat16* row = g + (long long)(start + pos) * 2 * D + c0 + (i & 7) * 8;
+      a4[it] = __ldg(reinterpret_cast<const uint4*>(row));
+      g4[it] = __ldg(reinterpret_cast<const uint4*>(row + D));
     }
-    tile[p][cp] = v0;
-    tile[p][cp + 1] = v1;
+  }
+#pragma unroll
+  for (int it = 0; it < kIt; ++it) {
+    const int i = tid + it * 256;
+    if (i < ROWS * 8) {
+      const int p = i >> 3, c8 = (i & 7) * 8;
+      const uint32_t aw[4] = {a4[it].x, a4[it].y, a4[it].z, a4[it].w}, gw[4] = {g4[it].x, g4[it].y, g4[it].z, g4[it].w};
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&aw[e]);
+        const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(&gw[e]);
+        v[2 * e] = __low2float(a2) * sigmoid_fast(__low2float(g2));
+        v[2 * e + 1] = __high2float(a2) * sigmoid_fast(__high2float(g2));
+      }
+      *reinterpret_cast<float4*>(&tile[p][c8]) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(&tile[p][c8 + 4]) = make_float4(v[4], v[5], v[6], v[7]);
+    }
   }
   __syncthreads();
   const int c = tid & 63, pg = tid >> 6;  // 4 groups of 16 positions; each thread slides a register window down one channel
@@ -659,7 +712,7 @@ int sb_speech_encoder_forward(SbSpeechEncoder* e, const float* fbank, int32_t pa
     if ((rc = gemm(reinterpret_cast<const __nv_bfloat16*>(relpos_table), D, L.wr, D, w.p, D, 0, e->w.zeros, Npad, D, D, EPI_BIAS))) return rc;
     relpos_bias_kernel<<<dim3((unsigned)((Npad + 7) / 8), (unsigned)H), 256, 0, stream>>>(w.p, L.v_bias, Npad, H, w.vp);
     SB_CUDA_CHECK(cudaGetLastError());
-    attention_relpos_kernel<<<dim3((unsigned)((smax + 127) / 128), (unsigned)H, (unsigned)B), 256, kRpSmem, stream>>>(
+    attention_relpos_kernel<<<dim3((unsigned)((smax + 127) / 128), (unsigned)H, (unsigned)B), kRpThreads, kRpSmem, stream>>>(
         w.big, cu_dev, H, L.u_bias, w.p, w.vp, Npad, smax, w.h);
     SB_CUDA_CHECK(cudaGetLastError());
     if ((rc = gemm(w.h, D, L.wo, D, w.x, D, 1, L.bo, (int)T, D, D, EPI_BIAS_RESIDUAL))) return rc;
