@@ -100,7 +100,9 @@ constexpr int kRpG = 0, kRpGBytes = 4 * 2 * 16 * kRpGStride * 4;  // 45056
 constexpr int kRpKV = kRpG + kRpGBytes;                           // 2 stages x (K 8 KB | V 8 KB)
 constexpr int kRpP = kRpKV + 2 * 16384;                           // ring of 256 rows of p (32 KB): 192 live + 64 in flight
 constexpr int kRpVp = kRpP + 256 * 128, kRpU = kRpVp + 256 * 4, kRpKb = kRpU + 64 * 4;
-constexpr int kRpSmem = kRpKb + 64 * 4;                           // 112128 B -> two CTAs per SM
+constexpr int kRpBar = kRpKb + 64 * 4;                            // 2 mbarriers: TMA completion per K/V/p stage
+constexpr int kRpSmem = kRpBar + 16 + 1024;                       // 113168 B incl. 1 KB alignment slack -> two CTAs per SM
+constexpr uint32_t kRpBlockBytes = 3 * 8192;                      // K + V + 64 new rows of p per key block
 static_assert(kRpGBytes >= 16384, "Q / output staging lives inside G");
 
 __device__ __forceinline__ void cp4(uint32_t dst, const void* src, bool ok) {
@@ -120,11 +122,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // v.p, parks the two [16 x 80] results in shared memory and reads them back along the anti-diagonals -- the
 // Transformer-XL "shift" -- while it masks and soft-maxes q.k^T.
 __global__ void __launch_bounds__(kRpThreads, 2)
-attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu, int H,
-                        const float* __restrict__ u_bias, const __nv_bfloat16* __restrict__ p, const float* __restrict__ vp,
-                        int Npad, int S_center, __nv_bfloat16* __restrict__ out) {
-  extern __shared__ __align__(128) uint8_t smem[];
+attention_relpos_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_p,
+                        const int32_t* __restrict__ cu, int H, const float* __restrict__ u_bias,
+                        const float* __restrict__ vp, int Npad, int S_center, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));  // SW128 tiles
   uint8_t* sQ = smem + kRpG;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kRpBar);
   float* s_vp = reinterpret_cast<float*>(smem + kRpVp);
   float* s_u = reinterpret_cast<float*>(smem + kRpU);
   float* s_kb = reinterpret_cast<float*>(smem + kRpKb);
@@ -133,11 +137,6 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
   const int q0 = qblk * 128;
   if (q0 >= len) return;
   const int D = H * 64;
-  const long long rs = 3ll * D;
-  const __nv_bfloat16* qbase = qkv + (long long)start * rs + h * 64;
-  const __nv_bfloat16* kbase = qbase + D;
-  const __nv_bfloat16* vbase = qbase + 2 * D;
-  const __nv_bfloat16* pbase = p + h * 64;
   const float* vpbase = vp + (long long)h * Npad;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sQa = smem_u32(sQ), sKVa = smem_u32(smem + kRpKV), sPa = smem_u32(smem + kRpP), sVpa = smem_u32(s_vp);
@@ -145,40 +144,52 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
   const int band_first = S_center - 1 - (q0 + 127);  // p row of ring position 0
   const int nkb = (len + 63) / 64;
 
-  // K/V of key block kb -> stage kb&1; ring positions [r_lo, r_hi) of p and v.p
-  auto issue_loads = [&](int kb, int r_lo, int r_hi) {
-    const int k0 = kb * 64;
-    const uint32_t sKa = sKVa + (kb & 1) * 16384, sVa = sKa + 8192;
-    for (int i = tid; i < 64 * 8; i += kRpThreads) {
-      const int r = i >> 3, c = i & 7;
-      const bool ok = (k0 + r) < len;
-      const long long g = (long long)(ok ? k0 + r : 0) * rs + c * 8;
-      cp16(sKa + toff(r, c), kbase + g, ok);
-      cp16(sVa + toff(r, c), vbase + g, ok);
+  // One elected thread feeds the CTA by TMA (128-byte swizzle = toff()): K/V of key block kb -> stage kb&1 and the 64
+  // rows of p at ring positions [r_lo, r_lo+64).  Rows past the utterance belong to the next one (or are zero-filled
+  // past the buffer): their keys are masked below and their probabilities are exactly 0.  Rows of p outside the table
+  // (negative or >= Npad) are zero-filled by the TMA unit.  v.p (64 floats) rides on cp.async from 64 threads.
+  auto issue_loads = [&](int kb, int r_lo) {
+    if (tid == 0) {
+      uint64_t* bar = &full_bar[kb & 1];
+      uint8_t* stage = smem + kRpKV + (kb & 1) * 16384;
+      mbar_arrive_expect_tx(bar, kRpBlockBytes);
+      tma_load_2d(stage, &tm_qkv, bar, D + h * 64, start + kb * 64);
+      tma_load_2d(stage + 8192, &tm_qkv, bar, 2 * D + h * 64, start + kb * 64);
+      tma_load_2d(smem + kRpP + (r_lo & 255) * 128, &tm_p, bar, h * 64, band_first + r_lo);
     }
-    for (int i = r_lo * 8 + tid; i < r_hi * 8; i += kRpThreads) {
-      const int rr = i >> 3, c = i & 7;
-      const int idx = band_first + rr;
-      const bool ok = idx >= 0 && idx < Npad;
-      cp16(sPa + toff(rr & 255, c), pbase + (long long)(ok ? idx : 0) * D + c * 8, ok);
-    }
-    for (int rr = r_lo + tid; rr < r_hi; rr += kRpThreads) {
-      const int idx = band_first + rr;
+    if (tid < 64) {
+      const int rr = r_lo + tid, idx = band_first + rr;
       const bool ok = idx >= 0 && idx < Npad;
       cp4(sVpa + (rr & 255) * 4, vpbase + (ok ? idx : 0), ok);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  if (tid < 64) s_u[tid] = u_bias[h * 64 + tid];
-  for (int i = tid; i < 128 * 8; i += kRpThreads) {
-    const int r = i >> 3, c = i & 7;
-    const bool ok = (q0 + r) < len;
-    cp16(sQa + toff(r, c), qbase + (long long)(ok ? q0 + r : 0) * rs + c * 8, ok);
+  if (tid == 0) {
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    fence_mbar_init();
   }
-  issue_loads(0, 0, 192);  // one group: Q + block 0
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (tid < 64) s_u[tid] = u_bias[h * 64 + tid];
   __syncthreads();
+  if (tid == 0) {  // Q (two 64-row boxes), K/V of block 0 and its 192 rows of p: one transaction on barrier 0
+    uint64_t* bar = &full_bar[0];
+    mbar_arrive_expect_tx(bar, 7 * 8192);
+    tma_load_2d(sQ, &tm_qkv, bar, h * 64, start + q0);
+    tma_load_2d(sQ + 8192, &tm_qkv, bar, h * 64, start + q0 + 64);
+    tma_load_2d(smem + kRpKV, &tm_qkv, bar, D + h * 64, start);
+    tma_load_2d(smem + kRpKV + 8192, &tm_qkv, bar, 2 * D + h * 64, start);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) tma_load_2d(smem + kRpP + i * 8192, &tm_p, bar, h * 64, band_first + i * 64);
+  }
+  for (int rr = tid; rr < 192; rr += kRpThreads) {
+    const int idx = band_first + rr;
+    const bool ok = idx >= 0 && idx < Npad;
+    cp4(sVpa + rr * 4, vpbase + (ok ? idx : 0), ok);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  mbar_wait(&full_bar[0], 0);
   uint32_t qf[2][4][4];
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
@@ -208,7 +219,8 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
     const int ring0 = kb * 64;  // ring position of band row 0 of this block
     // block kb has landed (waited below / before the loop); everyone is past block kb-1 (and past the Q fragments)
     __syncthreads();
-    if (kb + 1 < nkb) issue_loads(kb + 1, 192 + ring0, 256 + ring0);
+    if (kb + 1 < nkb) issue_loads(kb + 1, 192 + ring0);
+    if (kb > 0) mbar_wait(&full_bar[kb & 1], (kb >> 1) & 1);  // block 0 was awaited before the Q fragments were read
     const uint32_t sKa = sKVa + (kb & 1) * 16384, sVa = sKa + 8192;
     if (tid < 64) {  // u . k_j for the 64 keys of this block
       const uint8_t* sK = smem + kRpKV + (kb & 1) * 16384;
@@ -228,40 +240,51 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __
     }
     // ---- G_m[16 x 80] = Q_m . Pwindow_m^T (+ v.p), parked in shared memory; window n-tile pair np feeds both m-tiles ----
 #pragma unroll
-    for (int np = 0; np < 6; ++np) {
-      const bool use0 = np >= 1, use1 = np <= 4;  // m-tile 0: window n-tiles 2..11; m-tile 1: 0..9
-      float ga[2][2][4];
+    for (int nq = 0; nq < 3; ++nq) {  // two n-tile pairs per pass: up to 8 independent accumulator chains in flight
+      float ga[2][2][2][4];  // [pair][m-tile][n-tile of the pair][c]
 #pragma unroll
-      for (int m = 0; m < 2; ++m)
+      for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int t = 0; t < 2; ++t) ga[m][t][0] = ga[m][t][1] = ga[m][t][2] = ga[m][t][3] = 0.f;
-      const int prow = (ring0 + wrow0 + (np * 2 + (mtx >> 1)) * 8 + (lane & 7)) & 255;
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int t = 0; t < 2; ++t) ga[a][m][t][0] = ga[a][m][t][1] = ga[a][m][t][2] = ga[a][m][t][3] = 0.f;
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        uint32_t b0, b1, b2, b3;
-        ldsm4(sPa + toff(prow, kk * 2 + (mtx & 1)), b0, b1, b2, b3);
-        if (use0) {
-          mma16816(ga[0][0], qf[0][kk], b0, b1);
-          mma16816(ga[0][1], qf[0][kk], b2, b3);
-        }
-        if (use1) {
-          mma16816(ga[1][0], qf[1][kk], b0, b1);
-          mma16816(ga[1][1], qf[1][kk], b2, b3);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const int np = nq * 2 + a;
+          const bool use0 = np >= 1, use1 = np <= 4;  // m-tile 0: window n-tiles 2..11; m-tile 1: 0..9
+          const int prow = (ring0 + wrow0 + (np * 2 + (mtx >> 1)) * 8 + (lane & 7)) & 255;
+          uint32_t b0, b1, b2, b3;
+          ldsm4(sPa + toff(prow, kk * 2 + (mtx & 1)), b0, b1, b2, b3);
+          if (use0) {
+            mma16816(ga[a][0][0], qf[0][kk], b0, b1);
+            mma16816(ga[a][0][1], qf[0][kk], b2, b3);
+          }
+          if (use1) {
+            mma16816(ga[a][1][0], qf[1][kk], b0, b1);
+            mma16816(ga[a][1][1], qf[1][kk], b2, b3);
+          }
         }
       }
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int wc = (np * 2 + t) * 8 + kc;  // window column of this thread's pair
-        const float2 v01 = *reinterpret_cast<const float2*>(s_vp + ((ring0 + wrow0 + wc) & 255));
-        if (use0) {
-          float* g0 = sG + wc - 16;  // m-tile 0 stores relative to its own 80-column window
-          *reinterpret_cast<float2*>(g0 + rl_lo * kRpGStride) = make_float2(ga[0][t][0] + v01.x, ga[0][t][1] + v01.y);
-          *reinterpret_cast<float2*>(g0 + rl_hi * kRpGStride) = make_float2(ga[0][t][2] + v01.x, ga[0][t][3] + v01.y);
-        }
-        if (use1) {
-          float* g1 = sG + 16 * kRpGStride + wc;
-          *reinterpret_cast<float2*>(g1 + rl_lo * kRpGStride) = make_float2(ga[1][t][0] + v01.x, ga[1][t][1] + v01.y);
-          *reinterpret_cast<float2*>(g1 + rl_hi * kRpGStride) = make_float2(ga[1][t][2] + v01.x, ga[1][t][3] + v01.y);
+      for (int a = 0; a < 2; ++a) {
+        const int np = nq * 2 + a;
+        const bool use0 = np >= 1, use1 = np <= 4;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int wc = (np * 2 + t) * 8 + kc;  // window column of this thread's pair
+          const float2 v01 = *reinterpret_cast<const float2*>(s_vp + ((ring0 + wrow0 + wc) & 255));
+          if (use0) {
+            float* g0 = sG + wc - 16;  // m-tile 0 stores relative to its own 80-column window
+            *reinterpret_cast<float2*>(g0 + rl_lo * kRpGStride) = make_float2(ga[a][0][t][0] + v01.x, ga[a][0][t][1] + v01.y);
+            *reinterpret_cast<float2*>(g0 + rl_hi * kRpGStride) = make_float2(ga[a][0][t][2] + v01.x, ga[a][0][t][3] + v01.y);
+          }
+          if (use1) {
+            float* g1 = sG + 16 * kRpGStride + wc;
+            *reinterpret_cast<float2*>(g1 + rl_lo * kRpGStride) = make_float2(ga[a][1][t][0] + v01.x, ga[a][1][t][1] + v01.y);
+            *reinterpret_cast<float2*>(g1 + rl_hi * kRpGStride) = make_float2(ga[a][1][t][2] + v01.x, ga[a][1][t][3] + v01.y);
+          }
         }
       }
     }
@@ -443,13 +466,17 @@ glu_dwconv_kernel(const __nv_bfloat16* __restrict__ g, const int32_t* __restrict
   float win[PP + KS - 1];
 #pragma unroll
   for (int i = 0; i < PP + KS - 1; ++i) win[i] = tile[pg * PP + i][c];
+  float acc[PP];
+#pragma unroll
+  for (int pp = 0; pp < PP; ++pp) acc[pp] = 0.f;
+#pragma unroll
+  for (int k = 0; k < KS; ++k)  // tap-major: PP independent FMA chains in flight
+#pragma unroll
+    for (int pp = 0; pp < PP; ++pp) acc[pp] = fmaf(w[k], win[pp + k], acc[pp]);
 #pragma unroll
   for (int pp = 0; pp < PP; ++pp) {
     const int pos = t0 + pg * PP + pp;
-    float acc = 0.f;
-#pragma unroll
-    for (int k = 0; k < KS; ++k) acc = fmaf(w[k], win[pp + k], acc);
-    if (pos < len) out[(long long)(start + pos) * D + c0 + c] = __float2bfloat16_rn(silu_fast(acc * sc + sh));
+    if (pos < len) out[(long long)(start + pos) * D + c0 + c] = __float2bfloat16_rn(silu_fast(acc[pp] * sc + sh));
   }
 }
 
@@ -684,6 +711,10 @@ int sb_speech_encoder_forward(SbSpeechEncoder* e, const float* fbank, int32_t pa
     attr_set = true;
   }
   int rc;
+  // TMA views for the rel-pos attention: 64 x 64 boxes of the packed qkv rows [T, 3D] and of the projected table [Npad, D]
+  CUtensorMap tm_qkv, tm_p;
+  if ((rc = make_tmap_2d(&tm_qkv, w.big, 2, T, 3ll * D, 3ll * D, 64, 64))) return rc;
+  if ((rc = make_tmap_2d(&tm_p, w.p, 2, Npad, D, D, 64, 64))) return rc;
   GemmArgs g;
   g.cta_group = 2;
   g.num_sms = e->num_sms;
@@ -713,7 +744,7 @@ int sb_speech_encoder_forward(SbSpeechEncoder* e, const float* fbank, int32_t pa
     relpos_bias_kernel<<<dim3((unsigned)((Npad + 7) / 8), (unsigned)H), 256, 0, stream>>>(w.p, L.v_bias, Npad, H, w.vp);
     SB_CUDA_CHECK(cudaGetLastError());
     attention_relpos_kernel<<<dim3((unsigned)((smax + 127) / 128), (unsigned)H, (unsigned)B), kRpThreads, kRpSmem, stream>>>(
-        w.big, cu_dev, H, L.u_bias, w.p, w.vp, Npad, smax, w.h);
+        tm_qkv, tm_p, cu_dev, H, L.u_bias, w.vp, Npad, smax, w.h);
     SB_CUDA_CHECK(cudaGetLastError());
     if ((rc = gemm(w.h, D, L.wo, D, w.x, D, 1, L.bo, (int)T, D, D, EPI_BIAS_RESIDUAL))) return rc;
     // (c) convolution module
