@@ -100,20 +100,40 @@ def bench_decoder(peaks):
     del sd
     n, beam, max_seq_len = 512, 5, 128
     emb = torch.randn((n, 1024), device=DEV) * 0.25 / math.sqrt(1024) * 32
-    gen = BeamSearchSeq2SeqGenerator(model, beam_size=beam, max_seq_len=max_seq_len, pad_idx=0)
     prompt = torch.tensor([3, 256100])
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    out = gen(emb, None, prompt, None)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    runs = {}
+    for label, flag in (("eager", False), ("cuda_graphs", True)):
+        gen = BeamSearchSeq2SeqGenerator(model, beam_size=beam, max_seq_len=max_seq_len, pad_idx=0, cuda_graphs=flag)
+        walls = []
+        for _ in range(3):  # the first call allocates the 32 GB KV cache / records the graphs
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = gen(emb, None, prompt, None)
+            torch.cuda.synchronize()
+            walls.append(time.perf_counter() - t0)
+        runs[label] = walls
+    dt = min(runs["eager"][1:] + runs["cuda_graphs"][1:])
     steps = max(len(h[0].seq) for h in out.hypotheses if h)
+    # the pipelines' default batch (5 sentences x beam 5 = 25 hypothesis rows): launch-bound unless the step is a CUDA graph
+    small = {}
+    emb5 = emb[:5].contiguous()
+    for label, flag in (("eager", False), ("cuda_graphs", True)):
+        gsm = BeamSearchSeq2SeqGenerator(model, beam_size=beam, max_seq_len=max_seq_len, pad_idx=0, cuda_graphs=flag)
+        gsm(emb5, None, prompt, None)  # warm-up (records the graphs)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        o5 = gsm(emb5, None, prompt, None)
+        torch.cuda.synchronize()
+        d5 = time.perf_counter() - t1
+        st5 = max(len(h[0].seq) for h in o5.hypotheses if h)
+        small[label] = {"wall_s": d5, "steps": st5, "ms_per_step": d5 / st5 * 1e3}
     hyp_tokens = n * beam * steps
     peak = float(peaks["bf16_tflops_sustained"])
     return {"config": f"text_sonar_basic_decoder arch: {n} embeddings, beam {beam}, max_seq_len {max_seq_len}, random weights "
                       f"(random-weight hypotheses rarely emit EOS early: {steps} steps ran)",
             "metric": "sentences/sec decoded", "value": n / dt, "unit": "sentences/s", "wall_s": dt, "steps": steps,
             "ms_per_step": dt / steps * 1e3, "hypothesis_tokens_per_s": hyp_tokens / dt,
+            "wall_s_by_mode_3_calls_each": runs, "batch5_beam5": small,
             "roofline": {"bound": "tensor", "achieved": hyp_tokens * 1.63e9 / dt / 1e12, "peak": peak, "unit": "TFLOP/s",
                          "frac": hyp_tokens * 1.63e9 / dt / 1e12 / peak,
                          "note": "1.63 GFLOP per hypothesis-token (BASELINE.md §3); KV-cache reads (4 KB x t per hypothesis-layer) "

@@ -49,7 +49,7 @@ elif which == "speech":  # one full speech-encoder forward (64 x 10 s), for a la
     fr = [998] * 64
     for _ in range(2):
         model(SequenceBatch(fb, PaddingMask(torch.tensor(fr), 998, fr)))
-elif which == "decoder":  # a few full-size decoder steps (512 x beam 5), for a launch list
+elif which in ("decoder", "decoder_small"):  # a few decoder steps (512 x beam 5, or the pipelines' default 5 x beam 5)
     from sonar_b200 import B200TextDecoderModel, sonar_text_decoder_config
     gg = torch.Generator(device=dev).manual_seed(3)
     sd = {}
@@ -67,7 +67,7 @@ elif which == "decoder":  # a few full-size decoder steps (512 x beam 5), for a 
         sd[p + "ffn_layer_norm.weight"], sd[p + "ffn_layer_norm.bias"] = 1 + rn(1024), rn(1024)
     sd["decoder.layer_norm.weight"], sd["decoder.layer_norm.bias"] = 1 + rn(1024), rn(1024)
     model = B200TextDecoderModel(sonar_text_decoder_config("basic"), sd, dev)
-    n, beam, tmax = 512, 5, 130
+    n, beam, tmax = (512 if which == "decoder" else 5), 5, 130
     model.begin(torch.randn((n, 1024), device=dev) * 0.25, beam, tmax)
     r = n * beam
     table = torch.arange(r, dtype=torch.int32, device=dev)[:, None].expand(r, tmax).contiguous()

@@ -537,6 +537,7 @@ int gemm_bf16_topk(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W
 
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   if (g.M <= 0) return 0;
+  if (gemm_skinny_eligible(g)) return gemm_skinny(g, stream);
   if (g.N % 256 != 0 || g.K % 64 != 0 || g.K <= 0 || g.N <= 0) {
     set_last_error("gemm_bf16: need N %% 256 == 0 and K %% 64 == 0 (got M=%d N=%d K=%d)", g.M, g.N, g.K);
     return -1;

@@ -39,6 +39,10 @@ struct GemmArgs {
 
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
 
+// M <= 64 rows: weight-streaming mma.sync path (gemm_skinny.cu); gemm_bf16 dispatches to it when eligible
+bool gemm_skinny_eligible(const GemmArgs& g);
+int gemm_skinny(const GemmArgs& g, cudaStream_t stream);
+
 int gemm_topk_chunks(int M, int N, int cta_group, int num_sms);
 int gemm_bf16_topk(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
                    float* cand_val, int* cand_idx, float* lse_part, int n_chunks, int cta_group, int num_sms,

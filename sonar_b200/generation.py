@@ -11,6 +11,7 @@ oracle (``oracle/text_decoder.py::beam_search_step``) defines.
 
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple, Union
 
@@ -47,11 +48,66 @@ def select_candidates(total: Tensor, tok: Tensor, vocab: int, k: int):
     return torch.gather(flat, 1, sel), torch.gather(beam_id, 1, sel), torch.gather(ftok, 1, sel)
 
 
+class _DecodeState:
+    """Persistent device tensors of one beam search (shapes fixed by N, beam, Tmax): every step updates them IN PLACE so that
+    a step can be captured once as a CUDA graph and replayed."""
+
+    def __init__(self, N: int, B: int, Tmax: int, dev: torch.device):
+        R, CAP = N * B, 2 * B
+        self.N, self.B, self.Tmax, self.CAP = N, B, Tmax, CAP
+        self.seqs = torch.empty((N, B, Tmax), dtype=torch.int64, device=dev)
+        self.table = torch.empty((R, Tmax), dtype=torch.int32, device=dev)
+        self.tokens = torch.empty((R,), dtype=torch.int64, device=dev)
+        self.cum = torch.empty((N, B), dtype=torch.float32, device=dev)
+        self.alive = torch.empty((N, B), dtype=torch.bool, device=dev)
+        self.done = torch.empty((N,), dtype=torch.bool, device=dev)
+        self.fin_score = torch.empty((N, CAP + 1), dtype=torch.float32, device=dev)
+        self.fin_seq = torch.empty((N, CAP + 1, Tmax), dtype=torch.int64, device=dev)
+        self.fin_len = torch.empty((N, CAP + 1), dtype=torch.int64, device=dev)
+        self.fin_count = torch.empty((N,), dtype=torch.int64, device=dev)
+        self.ar_n = torch.arange(N, device=dev)
+        self.rank = torch.arange(2 * B, device=dev)[None, :]
+        self.row_ids = torch.arange(R, device=dev, dtype=torch.int32)[:, None]
+
+    def reset(self, prompt: Tensor, pad: int) -> None:
+        P = prompt.shape[1]
+        self.seqs.fill_(pad)
+        self.seqs[:, :, :P] = prompt[:, None, :]
+        self.table.copy_(self.row_ids.expand_as(self.table))
+        self.cum.zero_()
+        self.alive.fill_(True)
+        self.done.fill_(False)
+        self.fin_score.fill_(NEG_INF)
+        self.fin_seq.fill_(pad)
+        self.fin_len.zero_()
+        self.fin_count.zero_()
+
+
+class _GraphEntry:
+    """CUDA graphs of the decode steps of one (shape, search-parameter) configuration; they bake the addresses of the state
+    tensors and of the decoder workspace."""
+
+    def __init__(self, state: _DecodeState, ws_ptr: int):
+        self.state = state
+        self.ws_ptr = ws_ptr
+        self.graphs = {}
+        self.pool = torch.cuda.graph_pool_handle()
+        self.stream = torch.cuda.Stream(device=state.seqs.device)
+
+
+_MAX_GRAPH_ENTRIES = 8
+
+
 class BeamSearchSeq2SeqGenerator:
     def __init__(self, model: B200TextDecoderModel, *, beam_size: int = 5, min_gen_len: int = 1,
                  max_gen_len: Tuple[int, int] = (1, 128), max_seq_len: Optional[int] = None, echo_prompt: bool = False,
                  normalize_scores: bool = True, temperature: float = 1.0, unk_penalty: float = 0.0,
-                 len_penalty: float = 1.0, pad_idx: int = 0, sync_every: int = 8) -> None:
+                 len_penalty: float = 1.0, pad_idx: int = 0, sync_every: int = 8,
+                 cuda_graphs: Optional[bool] = None) -> None:
+        """``cuda_graphs``: replay each decode step (the ~290 engine launches + the beam bookkeeping) as one CUDA graph.
+        A small batch -- the pipelines' default ``batch_size=5`` is 25 hypotheses -- is launch-bound otherwise.  ``None``
+        (default) turns it on for up to 512 hypothesis rows unless ``SONAR_B200_DECODE_GRAPHS=0``; graphs are captured the
+        first time a (batch shape, step) is seen and cached on the model, so only repeated shapes benefit."""
         if beam_size < 1:
             raise ValueError("`beam_size` must be greater than or equal to 1")
         if 2 * beam_size > TOPK:
@@ -71,14 +127,98 @@ class BeamSearchSeq2SeqGenerator:
         self.len_penalty = len_penalty
         self.pad_idx = pad_idx
         self.sync_every = sync_every
+        self.cuda_graphs = cuda_graphs
+
+    def _advance(self, st: _DecodeState, g: int, P: int, min_gen: int, max_gen: int) -> None:
+        """One decode step: position t = P-1+g of every live hypothesis -> the next beam, all state updated in place."""
+        m = self.model
+        vi = m.target_vocab_info
+        eos, unk, pad, V = vi.eos_idx, vi.unk_idx, self.pad_idx, vi.size
+        N, B, Tmax, CAP = st.N, st.B, st.Tmax, st.CAP
+        R = N * B
+        dev = st.seqs.device
+        t = P - 1 + g  # position of the input token; the new token lands at t + 1
+        lp, tok, eos_lp = m.step(st.tokens, st.table, t)
+        lp = lp.view(N, B, TOPK)
+        tok = tok.view(N, B, TOPK).long()
+        lp = lp.masked_fill((tok < 0) | (tok == pad), NEG_INF)
+        if self.unk_penalty:
+            lp = torch.where(tok == unk, lp - self.unk_penalty, lp)
+        if g < min_gen:
+            lp = lp.masked_fill(tok == eos, NEG_INF)
+        if g >= max_gen - 1:  # the last allowed token must be EOS
+            lp = torch.full_like(lp, NEG_INF)
+            lp[:, :, 0] = eos_lp.view(N, B)
+            tok = tok.clone()
+            tok[:, :, 0] = eos
+        total = (st.cum[:, :, None] + lp).masked_fill(~st.alive[:, :, None], NEG_INF)
+        if g == 0:
+            total[:, 1:, :] = NEG_INF  # all beams are copies of the prompt
+        c_score, c_beam, c_tok = select_candidates(total, tok, V, 2 * B)
+
+        valid = c_score > NEG_INF
+        is_eos = (c_tok == eos) & valid
+        # ---- finalise EOS candidates ranked inside the beam ----
+        fin_mask = is_eos & (st.rank < B) & ~st.done[:, None]
+        fin_pos = st.fin_count[:, None] + torch.cumsum(fin_mask, 1) - 1
+        fin_ok = fin_mask & (fin_pos < CAP)
+        dest = torch.where(fin_ok, fin_pos, torch.full_like(fin_pos, CAP))
+        gen_len = g + 1
+        fscore = c_score / (float(gen_len) ** self.len_penalty) if self.normalize_scores else c_score
+        st.fin_score.scatter_(1, dest, torch.where(fin_ok, fscore, torch.full_like(fscore, NEG_INF)))
+        cand_seqs = torch.gather(st.seqs, 1, c_beam[:, :, None].expand(N, 2 * B, Tmax)).clone()
+        cand_seqs[:, :, t + 1] = c_tok
+        st.fin_seq.scatter_(1, dest[:, :, None].expand(N, 2 * B, Tmax), cand_seqs)
+        st.fin_len.scatter_(1, dest, torch.full_like(dest, t + 2))
+        st.fin_score[:, CAP] = NEG_INF
+        st.fin_count.add_(fin_mask.sum(1))
+        # ---- next beam: the first B non-EOS candidates ----
+        keep = valid & ~is_eos & ~st.done[:, None]
+        kpos = torch.cumsum(keep, 1) - 1
+        keep_ok = keep & (kpos < B)
+        kdest = torch.where(keep_ok, kpos, torch.full_like(kpos, B))
+        new_cum = torch.full((N, B + 1), NEG_INF, dtype=torch.float32, device=dev).scatter_(
+            1, kdest, torch.where(keep_ok, c_score, torch.full_like(c_score, NEG_INF)))[:, :B]
+        new_alive = torch.zeros((N, B + 1), dtype=torch.bool, device=dev).scatter_(1, kdest, keep_ok)[:, :B]
+        new_src = torch.zeros((N, B + 1), dtype=torch.int64, device=dev).scatter_(1, kdest, c_beam)[:, :B]
+        new_tok = torch.full((N, B + 1), pad, dtype=torch.int64, device=dev).scatter_(1, kdest, c_tok)[:, :B]
+        new_src = torch.where(new_alive, new_src, torch.zeros_like(new_src))
+        new_tok = torch.where(new_alive, new_tok, torch.full_like(new_tok, pad))
+        st.done.logical_or_(st.fin_count >= B)
+        new_alive = new_alive & ~st.done[:, None]
+        new_seqs = torch.gather(st.seqs, 1, new_src[:, :, None].expand(N, B, Tmax))
+        st.seqs.copy_(new_seqs)
+        st.seqs[:, :, t + 1] = new_tok
+        src_row = (st.ar_n[:, None] * B + new_src).reshape(R)
+        new_table = st.table.index_select(0, src_row)
+        st.table.copy_(new_table)
+        st.table[:, t] = src_row.to(torch.int32)
+        st.cum.copy_(new_cum)
+        st.alive.copy_(new_alive)
+        st.tokens.copy_(new_tok.reshape(R))
+
+    def _graph_entry(self, key, N: int, B: int, Tmax: int) -> _GraphEntry:
+        m = self.model
+        cache = m.__dict__.setdefault("_decode_graph_cache", {})
+        ws_ptr = m._workspace.data_ptr()
+        ent = cache.get(key)
+        if ent is not None and ent.ws_ptr != ws_ptr:  # the workspace moved: the captured addresses are stale
+            del cache[key]
+            ent = None
+        if ent is None:
+            while len(cache) >= _MAX_GRAPH_ENTRIES:
+                cache.pop(next(iter(cache)))
+            ent = _GraphEntry(_DecodeState(N, B, Tmax, m.device), ws_ptr)
+            cache[key] = ent
+        else:  # most recently used last
+            cache[key] = cache.pop(key)
+        return ent
 
     @torch.inference_mode()
     def __call__(self, source_seqs: Tensor, source_padding_mask, prompt_seqs: Tensor, prompt_padding_mask=None
                  ) -> Seq2SeqGeneratorOutput:
         m = self.model
         dev = m.device
-        vi = m.target_vocab_info
-        eos, unk, pad, V = vi.eos_idx, vi.unk_idx, self.pad_idx, vi.size
         if source_seqs.dim() == 2:
             source_seqs = source_seqs[:, None, :]  # DummyEncoderModel + encode(): [N,1,D] (model.py:48-53)
         N = source_seqs.shape[0]
@@ -98,86 +238,40 @@ class BeamSearchSeq2SeqGenerator:
         Tmax = P + max_gen
         m.begin(source_seqs[:, 0], B, Tmax)
 
-        ar_n = torch.arange(N, device=dev)
-        seqs = torch.full((N, B, Tmax), pad, dtype=torch.int64, device=dev)
-        seqs[:, :, :P] = prompt[:, None, :]
-        table = torch.arange(R, device=dev, dtype=torch.int32)[:, None].expand(R, Tmax).contiguous()
-        cum = torch.zeros((N, B), dtype=torch.float32, device=dev)
-        alive = torch.ones((N, B), dtype=torch.bool, device=dev)
-        done = torch.zeros((N,), dtype=torch.bool, device=dev)
-        CAP = 2 * B
-        fin_score = torch.full((N, CAP + 1), NEG_INF, dtype=torch.float32, device=dev)
-        fin_seq = torch.full((N, CAP + 1, Tmax), pad, dtype=torch.int64, device=dev)
-        fin_len = torch.zeros((N, CAP + 1), dtype=torch.int64, device=dev)
-        fin_count = torch.zeros((N,), dtype=torch.int64, device=dev)
-        rank = torch.arange(2 * B, device=dev)[None, :]
+        use_graphs = self.cuda_graphs
+        if use_graphs is None:
+            use_graphs = R <= 512 and os.environ.get("SONAR_B200_DECODE_GRAPHS", "1") != "0"
+        use_graphs = bool(use_graphs) and torch.device(dev).type == "cuda"  # (CPU only in the host-logic tests)
+        ent = None
+        if use_graphs:
+            key = (N, B, Tmax, P, min_gen, max_gen, self.unk_penalty, self.len_penalty, self.normalize_scores, self.pad_idx)
+            ent = self._graph_entry(key, N, B, Tmax)
+            st = ent.state
+        else:
+            st = _DecodeState(N, B, Tmax, dev)
+        st.reset(prompt, self.pad_idx)
 
         # prefill: every prompt position but the last only feeds the KV cache
         for p in range(P - 1):
-            m.step(seqs[:, :, p].reshape(R).contiguous(), table, p)
-
-        tokens = seqs[:, :, P - 1].reshape(R).contiguous()
+            m.step(st.seqs[:, :, p].reshape(R).contiguous(), st.table, p)
+        st.tokens.copy_(st.seqs[:, :, P - 1].reshape(R))
         for g in range(max_gen):
-            t = P - 1 + g  # position of the input token; the new token lands at t + 1
-            lp, tok, eos_lp = m.step(tokens, table, t)
-            lp = lp.view(N, B, TOPK)
-            tok = tok.view(N, B, TOPK).long()
-            lp = lp.masked_fill((tok < 0) | (tok == pad), NEG_INF)
-            if self.unk_penalty:
-                lp = torch.where(tok == unk, lp - self.unk_penalty, lp)
-            if g < min_gen:
-                lp = lp.masked_fill(tok == eos, NEG_INF)
-            if g >= max_gen - 1:  # the last allowed token must be EOS
-                lp = torch.full_like(lp, NEG_INF)
-                lp[:, :, 0] = eos_lp.view(N, B)
-                tok = tok.clone()
-                tok[:, :, 0] = eos
-            total = (cum[:, :, None] + lp).masked_fill(~alive[:, :, None], NEG_INF)
-            if g == 0:
-                total[:, 1:, :] = NEG_INF  # all beams are copies of the prompt
-            c_score, c_beam, c_tok = select_candidates(total, tok, V, 2 * B)
-
-            valid = c_score > NEG_INF
-            is_eos = (c_tok == eos) & valid
-            # ---- finalise EOS candidates ranked inside the beam ----
-            fin_mask = is_eos & (rank < B) & ~done[:, None]
-            fin_pos = fin_count[:, None] + torch.cumsum(fin_mask, 1) - 1
-            fin_ok = fin_mask & (fin_pos < CAP)
-            dest = torch.where(fin_ok, fin_pos, torch.full_like(fin_pos, CAP))
-            gen_len = g + 1
-            fscore = c_score / (float(gen_len) ** self.len_penalty) if self.normalize_scores else c_score
-            fin_score.scatter_(1, dest, torch.where(fin_ok, fscore, torch.full_like(fscore, NEG_INF)))
-            cand_seqs = torch.gather(seqs, 1, c_beam[:, :, None].expand(N, 2 * B, Tmax)).clone()
-            cand_seqs[:, :, t + 1] = c_tok
-            fin_seq.scatter_(1, dest[:, :, None].expand(N, 2 * B, Tmax), cand_seqs)
-            fin_len.scatter_(1, dest, torch.full_like(dest, t + 2))
-            fin_score[:, CAP] = NEG_INF
-            fin_count = fin_count + fin_mask.sum(1)
-            # ---- next beam: the first B non-EOS candidates ----
-            keep = valid & ~is_eos & ~done[:, None]
-            kpos = torch.cumsum(keep, 1) - 1
-            keep_ok = keep & (kpos < B)
-            kdest = torch.where(keep_ok, kpos, torch.full_like(kpos, B))
-            new_cum = torch.full((N, B + 1), NEG_INF, dtype=torch.float32, device=dev).scatter_(
-                1, kdest, torch.where(keep_ok, c_score, torch.full_like(c_score, NEG_INF)))[:, :B]
-            new_alive = torch.zeros((N, B + 1), dtype=torch.bool, device=dev).scatter_(1, kdest, keep_ok)[:, :B]
-            new_src = torch.zeros((N, B + 1), dtype=torch.int64, device=dev).scatter_(1, kdest, c_beam)[:, :B]
-            new_tok = torch.full((N, B + 1), pad, dtype=torch.int64, device=dev).scatter_(1, kdest, c_tok)[:, :B]
-            new_src = torch.where(new_alive, new_src, torch.zeros_like(new_src))
-            new_tok = torch.where(new_alive, new_tok, torch.full_like(new_tok, pad))
-            done = done | (fin_count >= B)
-            new_alive = new_alive & ~done[:, None]
-            seqs = torch.gather(seqs, 1, new_src[:, :, None].expand(N, B, Tmax)).clone()
-            seqs[:, :, t + 1] = new_tok
-            src_row = (ar_n[:, None] * B + new_src).reshape(R)
-            table = table.index_select(0, src_row).contiguous()
-            table[:, t] = src_row.to(torch.int32)
-            cum, alive = new_cum, new_alive
-            tokens = new_tok.reshape(R).contiguous()
-            if (g + 1) % self.sync_every == 0 and bool(done.all()):
+            if ent is None:
+                self._advance(st, g, P, min_gen, max_gen)
+            else:
+                graph = ent.graphs.get(g)
+                if graph is None:  # record this step once (recording does not execute it), then replay
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, pool=ent.pool, stream=ent.stream):
+                        self._advance(st, g, P, min_gen, max_gen)
+                    ent.graphs[g] = graph
+                graph.replay()
+            if (g + 1) % self.sync_every == 0 and bool(st.done.all()):
                 break
 
         m.check_inputs()
+        CAP = st.CAP
+        fin_score, fin_len, fin_seq = st.fin_score, st.fin_len, st.fin_seq
         # ---- best-first hypotheses (score desc, earlier-finished first on ties) ----
         order = torch.argsort(fin_score[:, :CAP], dim=1, descending=True, stable=True)[:, :B]
         s_sorted = torch.gather(fin_score[:, :CAP], 1, order).cpu()

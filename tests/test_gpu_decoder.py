@@ -121,3 +121,35 @@ def test_embedding_to_text_pipeline(small, cuda_device):
     assert texts == again  # batch composition does not change the result
     with pytest.raises(ValueError):
         pipe.predict(emb, target_lang="fra_Latn", max_seq_len=2)  # no room after the 2-token prompt
+
+
+def test_cuda_graph_replay_equals_eager_generation(small, cuda_device):
+    """The per-step CUDA graphs (engine launches + beam bookkeeping, captured once per step index) reproduce the eager
+    search token for token, also when the cached graphs are replayed for a second batch of the same shape."""
+    from sonar_b200.generation import BeamSearchSeq2SeqGenerator
+
+    _, model = small
+    prompt = torch.tensor([2, 7])
+    kw = dict(beam_size=3, max_seq_len=14, pad_idx=1)
+    before = set(model.__dict__.get("_decode_graph_cache", {}))  # earlier tests of this module may have recorded graphs
+    eager = BeamSearchSeq2SeqGenerator(model, cuda_graphs=False, **kw)
+    graphed = BeamSearchSeq2SeqGenerator(model, cuda_graphs=True, **kw)
+    for seed in (21, 22):  # second round replays the graphs recorded in the first
+        emb = _emb(4, seed=seed).to(cuda_device)
+        a = eager(emb, None, prompt, None)
+        b = graphed(emb, None, prompt, None)
+        assert len(a.hypotheses) == len(b.hypotheses) == 4
+        for ha, hb in zip(a.hypotheses, b.hypotheses):
+            assert len(ha) == len(hb)
+            for x, y in zip(ha, hb):
+                assert torch.equal(x.seq, y.seq) and x.score == y.score
+    cache = model.__dict__["_decode_graph_cache"]
+    mine = [k for k in cache if k not in before]
+    assert len(mine) == 1 and len(cache[mine[0]].graphs) >= 1
+    # a different batch size is a different graph set; the first one stays valid
+    graphed(_emb(2, seed=5).to(cuda_device), None, prompt, None)
+    assert len([k for k in cache if k not in before]) == 2 and mine[0] in cache
+    c = graphed(_emb(4, seed=22).to(cuda_device), None, prompt, None)
+    for ha, hc in zip(a.hypotheses, c.hypotheses):
+        for x, y in zip(ha, hc):
+            assert torch.equal(x.seq, y.seq) and x.score == y.score

@@ -76,6 +76,51 @@ def test_gemm_residual_fp32_inplace(ops, cuda_device, cta_group, m, n, k):
     torch.testing.assert_close(x, ref, rtol=1e-4, atol=2e-3)
 
 
+SKINNY_SHAPES = [(1, 1024, 1024), (7, 3072, 1024), (16, 1024, 8192), (25, 8192, 1024), (25, 1024, 8192), (33, 1024, 1024),
+                 (64, 3072, 1024), (5, 8, 256)]
+
+
+@pytest.mark.parametrize("m,n,k", SKINNY_SHAPES)
+@pytest.mark.parametrize("epilogue", ["bias", "relu", "silu"])
+def test_gemm_skinny_rows(ops, cuda_device, m, n, k, epilogue):
+    """M <= 64 goes down the weight-streaming mma.sync path (gemm_skinny.cu): the decoder's small-batch beam step and the
+    speech pooler.  Same contract and tolerances as the tcgen05 path."""
+    a = _rand((m, k), 1.0, 31, cuda_device, torch.bfloat16)
+    w = _rand((n, k), 1.0 / math.sqrt(k), 32, cuda_device, torch.bfloat16)
+    bias = _rand((n,), 0.5, 33, cuda_device)
+    out = ops.gemm_bf16(a, w, bias, epilogue=epilogue)
+    ref = a.float() @ w.float().T + bias
+    if epilogue == "relu":
+        ref = torch.relu(ref)
+    elif epilogue == "silu":
+        ref = torch.nn.functional.silu(ref)
+    err = (out.float() - ref).abs()
+    assert bool((err <= ref.abs() * (1.5 * 2 ** -8) + 2e-2).all()), f"max err {err.max().item()}"
+    out32 = ops.gemm_bf16(a, w, bias, epilogue=epilogue, out_dtype=torch.float32)
+    tol = dict(rtol=1e-4, atol=2e-3) if epilogue != "silu" else dict(rtol=2e-3, atol=2e-3)  # tanh.approx in the SiLU
+    torch.testing.assert_close(out32, ref, **tol)
+
+
+@pytest.mark.parametrize("m,n,k", [(25, 1024, 8192), (40, 1024, 1024)])
+def test_gemm_skinny_residual_inplace_and_reproducible(ops, cuda_device, m, n, k):
+    a = _rand((m, k), 1.0, 34, cuda_device, torch.bfloat16)
+    w = _rand((n, k), 1.0 / math.sqrt(k), 35, cuda_device, torch.bfloat16)
+    bias = _rand((n,), 0.5, 36, cuda_device)
+    x0 = _rand((m, n), 2.0, 37, cuda_device)
+    ref = x0 + a.float() @ w.float().T + bias
+    x = x0.clone()
+    out = ops.gemm_bf16(a, w, bias, epilogue="residual", residual=x, out=x)
+    assert out.data_ptr() == x.data_ptr()
+    torch.testing.assert_close(x, ref, rtol=1e-4, atol=2e-3)
+    y = x0.clone()
+    ops.gemm_bf16(a, w, bias, epilogue="residual", residual=y, out=y)
+    assert torch.equal(x, y)  # fixed reduction order across the K-split warps
+    # rows are independent of the batch they sit in (beam search relies on it): row 3 alone == row 3 of the batch
+    z = x0[3:4].clone()
+    ops.gemm_bf16(a[3:4].contiguous(), w, bias, epilogue="residual", residual=z, out=z)
+    assert torch.equal(z[0], x[3])
+
+
 def test_gemm_rejects_bad_shapes(ops, cuda_device):
     a = torch.zeros((8, 64), dtype=torch.bfloat16, device=cuda_device)
     w = torch.zeros((100, 64), dtype=torch.bfloat16, device=cuda_device)
