@@ -136,7 +136,9 @@ int sb_encoder_check_inputs(SbEncoder* enc, void* workspace, void* stream);
 /* ---- individual kernels (used by the parity tests and the micro-benchmarks) ---- */
 
 /* C[M,N] = epi(A[M,K] * W[N,K]^T + bias[N]) ; A, W bf16 row-major; C bf16 (out_fp32=0) or fp32;
- * residual (SB_EPI_BIAS_RESIDUAL) has C's dtype and may alias C.  N % 256 == 0, K % 64 == 0. */
+ * residual (SB_EPI_BIAS_RESIDUAL) has C's dtype and may alias C.  N % 256 == 0, K % 64 == 0.
+ * cta_group: 2 = paired-CTA tcgen05 tiles, 1 = single-CTA tiles, 0 = automatic (paired tiles, except that M <= 64 with
+ * K % 256 == 0 takes the weight-streaming mma.sync path the decoder step uses; then only N % 8 == 0 is required). */
 int sb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int32_t out_fp32,
                  const float* bias, const void* residual, int64_t ldr, int32_t M, int32_t N, int32_t K, int32_t epi,
                  int32_t cta_group, void* stream);

@@ -716,6 +716,7 @@ int sb_speech_encoder_forward(SbSpeechEncoder* e, const float* fbank, int32_t pa
   if ((rc = make_tmap_2d(&tm_qkv, w.big, 2, T, 3ll * D, 3ll * D, 64, 64))) return rc;
   if ((rc = make_tmap_2d(&tm_p, w.p, 2, Npad, D, D, 64, 64))) return rc;
   GemmArgs g;
+  g.allow_skinny = 1;
   g.cta_group = 2;
   g.num_sms = e->num_sms;
   auto gemm = [&](const __nv_bfloat16* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int fp32,

@@ -411,6 +411,7 @@ int sb_decoder_begin(SbDecoder* d, const float* embeddings, int32_t N, int32_t b
   cast_bf16_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, stream>>>(embeddings, w.ebf, n);
   SB_CUDA_CHECK(cudaGetLastError());
   GemmArgs g;
+  g.allow_skinny = 1;
   g.cta_group = 2;
   g.num_sms = d->num_sms;
   g.M = N;
@@ -453,6 +454,7 @@ int sb_decoder_step(SbDecoder* d, const int64_t* tokens, const int32_t* table, i
                                                       d->cfg.embed_scale, w.x, R, w.err_flag);
   SB_CUDA_CHECK(cudaGetLastError());
   GemmArgs g;
+  g.allow_skinny = 1;
   g.cta_group = 2;
   g.num_sms = d->num_sms;
   g.M = R;

@@ -14,7 +14,6 @@
 
 namespace sb {
 
-static constexpr int kMaxVec = 8;  // float4 per lane -> D <= 1024
 
 // ----------------------------------------------------------------------------
 // embedding frontend
@@ -72,43 +71,6 @@ int embed_tokens(const int64_t* ids, long long ids_stride, const int32_t* cu_seq
                                          err_flag, pos_offset);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
-}
-
-// ----------------------------------------------------------------------------
-// row LayerNorm helpers (one warp owns one row of D = 128*nvec floats)
-// ----------------------------------------------------------------------------
-__device__ __forceinline__ void load_row(const float* __restrict__ row, int nvec, int lane, float4 (&v)[kMaxVec]) {
-#pragma unroll
-  for (int i = 0; i < kMaxVec; ++i)
-    if (i < nvec) v[i] = *reinterpret_cast<const float4*>(row + (i * 32 + lane) * 4);
-}
-
-__device__ __forceinline__ void normalize_row(float4 (&v)[kMaxVec], int nvec, int lane, int D,
-                                              const float* __restrict__ gamma, const float* __restrict__ beta,
-                                              float eps) {
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < kMaxVec; ++i)
-    if (i < nvec) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  const float mean = warp_sum(s) / float(D);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < kMaxVec; ++i)
-    if (i < nvec) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      q += (a * a + b * b) + (c * c + d * d);
-    }
-  const float rstd = 1.0f / sqrtf(warp_sum(q) / float(D) + eps);
-#pragma unroll
-  for (int i = 0; i < kMaxVec; ++i)
-    if (i < nvec) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
-      const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
-      v[i].x = (v[i].x - mean) * rstd * g.x + bt.x;
-      v[i].y = (v[i].y - mean) * rstd * g.y + bt.y;
-      v[i].z = (v[i].z - mean) * rstd * g.z + bt.z;
-      v[i].w = (v[i].w - mean) * rstd * g.w + bt.w;
-    }
 }
 
 __global__ void __launch_bounds__(256)

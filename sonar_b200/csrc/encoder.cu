@@ -13,6 +13,8 @@
 //   f   bf16 [T, F]   FFN inner activations
 
 #include "../../include/sonar_b200.h"
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sonar_b200_internal.h"
 
@@ -38,6 +40,8 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 struct Workspace {
   int32_t* cu;
   int32_t* err_flag;
+  int32_t* ln_counters;  // one arrival counter per 128-row block (LayerNorm fused behind the residual GEMMs)
+  size_t ln_counter_bytes;
   float* x;
   __nv_bfloat16* h;
   __nv_bfloat16* qkv;
@@ -78,6 +82,9 @@ static Workspace carve(const SbEncoder* e, int32_t max_batch, int64_t max_tokens
   off = align_up(off + 256, 1024);
   w.cu = reinterpret_cast<int32_t*>(p + off);
   off = align_up(off + sizeof(int32_t) * ((size_t)max_batch + 1), 1024);
+  w.ln_counters = reinterpret_cast<int32_t*>(p + off);
+  w.ln_counter_bytes = sizeof(int32_t) * (T / 128 + 8);
+  off = align_up(off + w.ln_counter_bytes, 1024);
   w.x = reinterpret_cast<float*>(p + off);
   off = align_up(off + T * D * 4, 1024);
   w.h = reinterpret_cast<__nv_bfloat16*>(p + off);
@@ -241,10 +248,22 @@ int sb_encoder_forward(SbEncoder* e, const int64_t* ids, int64_t ids_row_stride,
   g.cta_group = (e->cfg.cta_group == 1) ? 1 : 2;
   g.num_sms = e->num_sms;
   g.M = (int)T;
+  // Experimental (off by default): LayerNorm riding behind the residual GEMMs -- their two idle warps normalise each
+  // 128-row block out of L2 once all of its n-tiles have been reduced into x (LnFuse, gemm_tcgen05.cu).  Bit-identical
+  // to the separate kernels (tests/test_gpu_encoder.py), but measured on B200 it does not pay: behind FFN2 it is a wash
+  // (9 340 vs 9 293 sent/s, same box), behind the out-projection it loses 6 % -- two warps keep only 32 KB in flight
+  // against ~5 us of loaded memory latency, so a 1 ms GEMM cannot hide its 14 MB of LayerNorm traffic per SM.
+  // SONAR_B200_FUSE_LN=1 fuses behind FFN2, =2 behind both GEMMs.
+  const char* fuse_env = getenv("SONAR_B200_FUSE_LN");
+  const int fuse_mode = fuse_env ? (fuse_env[0] - '0') : 0;  // 0 = separate kernels, 1 = behind FFN2, 2 = behind both GEMMs
+  const bool fuse_ln = fuse_mode >= 1 && fuse_mode <= 2 && T > 64 && gemm_ln_fusable((int)T, D, g.cta_group, e->num_sms);
+  const bool fuse_ln2 = fuse_ln && fuse_mode == 2;
+  if (fuse_ln) SB_CUDA_CHECK(cudaMemsetAsync(w.ln_counters, 0, w.ln_counter_bytes, stream));
   for (int li = 0; li < e->cfg.num_layers; ++li) {
     const SbLayerWeights& L = e->layers[li];
     // --- self-attention block: x += Wo . SDPA(LN1(x)) + bo ---
-    if ((rc = layernorm_bf16(w.x, L.ln1_g, L.ln1_b, e->cfg.ln_eps, w.h, T, D, stream))) return rc;
+    if (li == 0 || !fuse_ln)
+      if ((rc = layernorm_bf16(w.x, L.ln1_g, L.ln1_b, e->cfg.ln_eps, w.h, T, D, stream))) return rc;
     g.A = w.h; g.lda = D; g.W = reinterpret_cast<const __nv_bfloat16*>(L.wqkv); g.ldw = D;
     g.C = w.qkv; g.ldc = 3 * D; g.out_fp32 = 0; g.bias = L.bqkv; g.residual = nullptr; g.ldr = 0;
     g.N = 3 * D; g.K = D; g.epi = EPI_BIAS;
@@ -253,9 +272,16 @@ int sb_encoder_forward(SbEncoder* e, const int64_t* ids, int64_t ids_row_stride,
     g.A = w.h; g.lda = D; g.W = reinterpret_cast<const __nv_bfloat16*>(L.wo); g.ldw = D;
     g.C = w.x; g.ldc = D; g.out_fp32 = 1; g.bias = L.bo; g.residual = w.x; g.ldr = D;
     g.N = D; g.K = D; g.epi = EPI_BIAS_RESIDUAL;
-    if ((rc = gemm_bf16(g, stream))) return rc;
+    if (fuse_ln2) {  // h (the attention output this GEMM reads) is overwritten block by block with LN2(x): a block is
+      g.ln.gamma = L.ln2_g; g.ln.beta = L.ln2_b; g.ln.eps = e->cfg.ln_eps;  // normalised only after all its tiles ran
+      g.ln.out = w.h; g.ln.ldo = D; g.ln.counters = w.ln_counters;
+    }
+    rc = gemm_bf16(g, stream);
+    g.ln = LnFuse();
+    if (rc) return rc;
     // --- feed-forward block: x += W2 . relu(W1 . LN2(x) + b1) + b2 ---
-    if ((rc = layernorm_bf16(w.x, L.ln2_g, L.ln2_b, e->cfg.ln_eps, w.h, T, D, stream))) return rc;
+    if (!fuse_ln2)
+      if ((rc = layernorm_bf16(w.x, L.ln2_g, L.ln2_b, e->cfg.ln_eps, w.h, T, D, stream))) return rc;
     g.A = w.h; g.lda = D; g.W = reinterpret_cast<const __nv_bfloat16*>(L.w1); g.ldw = D;
     g.C = w.f; g.ldc = F; g.out_fp32 = 0; g.bias = L.b1; g.residual = nullptr; g.ldr = 0;
     g.N = F; g.K = D; g.epi = EPI_BIAS_RELU;
@@ -266,7 +292,14 @@ int sb_encoder_forward(SbEncoder* e, const int64_t* ids, int64_t ids_row_stride,
     g.A = w.f; g.lda = F; g.W = reinterpret_cast<const __nv_bfloat16*>(L.w2); g.ldw = F;
     g.C = w.x; g.ldc = D; g.out_fp32 = 1; g.bias = L.b2; g.residual = w.x; g.ldr = D;
     g.N = D; g.K = F; g.epi = EPI_BIAS_RESIDUAL;
-    if ((rc = gemm_bf16(g, stream))) return rc;
+    if (fuse_ln && li + 1 < e->cfg.num_layers) {  // the next layer's LN1
+      const SbLayerWeights& Ln = e->layers[li + 1];
+      g.ln.gamma = Ln.ln1_g; g.ln.beta = Ln.ln1_b; g.ln.eps = e->cfg.ln_eps;
+      g.ln.out = w.h; g.ln.ldo = D; g.ln.counters = w.ln_counters;
+    }
+    rc = gemm_bf16(g, stream);
+    g.ln = LnFuse();
+    if (rc) return rc;
   }
   return ln_pool(w.x, w.cu, B, D, e->final_ln_g, e->final_ln_b, e->cfg.ln_eps, 1, e->cfg.pooling, out, encoded, S,
                  stream);
@@ -324,7 +357,9 @@ int sb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C
   g.A = reinterpret_cast<const __nv_bfloat16*>(A); g.lda = lda;
   g.W = reinterpret_cast<const __nv_bfloat16*>(W); g.ldw = ldw;
   g.C = C; g.ldc = ldc; g.out_fp32 = out_fp32; g.bias = bias; g.residual = residual; g.ldr = ldr;
-  g.M = M; g.N = N; g.K = K; g.epi = epi; g.cta_group = cta_group;
+  g.M = M; g.N = N; g.K = K; g.epi = epi;
+  g.cta_group = cta_group == 1 ? 1 : 2;
+  g.allow_skinny = (cta_group == 0);  // 0 = automatic: M <= 64 may take the weight-streaming path
   int dev = 0, sms = 0;
   SB_CUDA_CHECK(cudaGetDevice(&dev));
   SB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

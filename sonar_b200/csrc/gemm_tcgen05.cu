@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(256, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                          const __grid_constant__ CUtensorMap tm_c, const float* __restrict__ bias,
                          const OutT* residual, long long ldr, int M, int N, int K, float* __restrict__ cand_val,
-                         int* __restrict__ cand_idx, float* __restrict__ lse_part, int n_chunks) {
+                         int* __restrict__ cand_idx, float* __restrict__ lse_part, int n_chunks, const LnFuse ln,
+                         const float* ln_x, long long ln_ldx) {
   constexpr bool kSweep = (kEpi == EPI_TOPK);
   using Cfg = GemmCfg<kCtaGroup>;
   extern __shared__ uint8_t smem_raw[];
@@ -118,6 +119,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  [[maybe_unused]] const bool ln_on = (kEpi == EPI_BIAS_ACCUM) && ln.out != nullptr;
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -231,6 +233,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     [[maybe_unused]] float tv[KC];
     [[maybe_unused]] int ti[KC];
     [[maybe_unused]] float run_max = -CUDART_INF_F, run_sum = 0.f;  // online log-sum-exp of the row (optional)
+    [[maybe_unused]] int ln_pending_blk = -1;  // store thread: 128-row block whose reduce-adds are still in flight
     for (uint32_t iter = 0; sched.next(m_blk, n_blk, chunk, first_in_item, last_in_item); ++iter) {
       const int m0 = m_blk * tile_m + int(cta_rank) * Cfg::BLOCK_M;
       const int n0 = n_blk * Cfg::BLOCK_N;
@@ -394,11 +397,76 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           else
             tma_store_2d(&tm_c, smem_cd + cd_stage * Cfg::CD_STAGE_BYTES, n0 + c * CHUNK_COLS, m0);
           tma_store_commit();
+          if constexpr (kEpi == EPI_BIAS_ACCUM) {
+            if (ln_on) {
+              // publish the PREVIOUS tile's rows: with at most the 4 groups of this tile pending, all of its
+              // reduce-adds have completed; release them to the GPU and count the n-tile in
+              if (c == 3 && ln_pending_blk >= 0) {
+                tma_store_wait_all<4>();
+                __threadfence();
+                atomicAdd(&ln.counters[ln_pending_blk], 1);
+                ln_pending_blk = -1;
+              }
+              if (c == NUM_CHUNKS - 1) ln_pending_blk = m0 >> 7;
+            }
+          }
         }
         cd_stage ^= 1;
       }
     }
-    if (ew == 0 && lane == 0) tma_store_wait_all<0>();
+    if (ew == 0 && lane == 0) {
+      tma_store_wait_all<0>();
+      if constexpr (kEpi == EPI_BIAS_ACCUM) {
+        if (ln_on) {
+          if (ln_pending_blk >= 0) {
+            __threadfence();
+            atomicAdd(&ln.counters[ln_pending_blk], 1);
+          }
+        }
+      }
+    }
+  } else if (kEpi == EPI_BIAS_ACCUM && ln_on) {
+    // ===================== fused LayerNorm (warps 2 and 3, otherwise idle) =====================
+    // Every warp role walks an identical copy of the tile schedule.  The CTA whose tile has n_blk == m_blk % num_n_tiles
+    // owns that 128-row block (ownership rotates over the n index so the blocks spread evenly over the CTAs); warp 2
+    // normalises its rows 0..63, warp 3 rows 64..127, once the block's arrival counter says every n-tile's
+    // reduce-add has completed.  Nothing ever waits on these warps, so the wait cannot deadlock.
+    const int nvec = N / 128;
+    while (sched.next(m_blk, n_blk, chunk, first_in_item, last_in_item)) {
+      const int m0 = m_blk * tile_m + int(cta_rank) * Cfg::BLOCK_M;
+      if (n_blk != m_blk % num_n_tiles || m0 >= M) continue;
+      const int blk = m0 >> 7;
+      const int r0 = m0 + (warp_idx - 2) * 64;
+      const long long t0 = clock64();
+      for (;;) {  // acquire pairs with the store threads' fence + add
+        int cnt;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(cnt) : "l"(ln.counters + blk) : "memory");
+        if (cnt >= num_n_tiles) break;
+        __nanosleep(128);
+        if (clock64() - t0 > SB_MBAR_TIMEOUT_CYCLES) { printf("sonar_b200: fused-LN counter timeout\n"); __trap(); }
+      }
+#pragma unroll 1
+      for (int r = 0; r < 64; r += 4) {
+        float4 v[4][kMaxVec];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (r0 + r + q < M) load_row<true>(ln_x + (long long)(r0 + r + q) * ln_ldx, nvec, lane, v[q]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int row = r0 + r + q;
+          if (row < M) {
+            normalize_row(v[q], nvec, lane, N, ln.gamma, ln.beta, ln.eps);
+            uint2* yrow = reinterpret_cast<uint2*>(ln.out + (long long)row * ln.ldo);
+#pragma unroll
+            for (int i = 0; i < kMaxVec; ++i)
+              if (i < nvec) yrow[i * 32 + lane] = make_uint2(pack_bf16x2(v[q][i].x, v[q][i].y), pack_bf16x2(v[q][i].z, v[q][i].w));
+          }
+        }
+      }
+      // the second of the block's two halves to finish re-arms the counter for the next launch
+      __syncwarp();
+      if (lane == 0 && atomicAdd(&ln.counters[blk], 16) >= num_n_tiles + 16) ln.counters[blk] = 0;
+    }
   }
 
   // ===================== teardown =====================
@@ -460,7 +528,7 @@ template <int kCtaGroup, int kEpi, typename OutT>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const float* bias,
                        const void* residual, long long ldr, int M, int N, int K, int num_sms, cudaStream_t stream,
                        float* cand_val = nullptr, int* cand_idx = nullptr, float* lse_part = nullptr,
-                       int n_chunks = 1) {
+                       int n_chunks = 1, const LnFuse& ln = LnFuse(), const float* ln_x = nullptr, long long ln_ldx = 0) {
   using Cfg = GemmCfg<kCtaGroup>;
   auto kern = gemm_bf16_tcgen05_kernel<kCtaGroup, kEpi, OutT>;
   static bool attr_set = false;
@@ -488,8 +556,16 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, bias, reinterpret_cast<const OutT*>(residual), ldr, M, N, K,
-                                   cand_val, cand_idx, lse_part, n_chunks));
+                                   cand_val, cand_idx, lse_part, n_chunks, ln, ln_x, ln_ldx));
   return 0;
+}
+
+bool gemm_ln_fusable(int M, int N, int cta_group, int num_sms) {
+  const int cg = (cta_group == 1) ? 1 : 2;
+  if (M <= 64 || N % 256 != 0 || N > 128 * kMaxVec) return false;
+  (void)cg;
+  (void)num_sms;
+  return true;
 }
 
 // Number of n-chunks the top-k sweep is split into so that (m-blocks x chunks) fills the clusters.
@@ -537,7 +613,7 @@ int gemm_bf16_topk(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W
 
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   if (g.M <= 0) return 0;
-  if (gemm_skinny_eligible(g)) return gemm_skinny(g, stream);
+  if (g.allow_skinny && gemm_skinny_eligible(g)) return gemm_skinny(g, stream);
   if (g.N % 256 != 0 || g.K % 64 != 0 || g.K <= 0 || g.N <= 0) {
     set_last_error("gemm_bf16: need N %% 256 == 0 and K %% 64 == 0 (got M=%d N=%d K=%d)", g.M, g.N, g.K);
     return -1;
@@ -565,8 +641,16 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     return -1;
   }
 
-#define SB_DISPATCH(CG, EPI, T) \
-  return launch_inst<CG, EPI, T>(ta, tb, tc, g.bias, g.residual, g.ldr, g.M, g.N, g.K, sms, stream)
+  if (g.ln.out != nullptr) {
+    if (epi != EPI_BIAS_ACCUM || !gemm_ln_fusable(g.M, g.N, cg, sms) || !g.ln.counters || !g.ln.gamma || !g.ln.beta) {
+      set_last_error("gemm_bf16: fused LayerNorm needs the in-place fp32 accumulate epilogue over full rows (M=%d N=%d)", g.M, g.N);
+      return -1;
+    }
+  }
+
+#define SB_DISPATCH(CG, EPI, T)                                                                                   \
+  return launch_inst<CG, EPI, T>(ta, tb, tc, g.bias, g.residual, g.ldr, g.M, g.N, g.K, sms, stream, nullptr, nullptr, \
+                                 nullptr, 1, g.ln, reinterpret_cast<const float*>(g.C), g.ldc)
 #define SB_DISPATCH_EPI(CG, T)                                              \
   switch (epi) {                                                            \
     case EPI_BIAS: SB_DISPATCH(CG, EPI_BIAS, T);                            \

@@ -20,6 +20,19 @@ enum PoolMode { POOL_MAX = 1, POOL_MEAN = 2, POOL_LAST = 3 };  // = reference `P
 
 void set_last_error(const char* fmt, ...);
 
+// Optional LayerNorm fused behind an in-place fp32 accumulate GEMM (x += A.W^T + b over FULL rows, N == D): the idle
+// warps of the GEMM CTAs normalise each 128-row block as soon as its last n-tile has been reduced into x -- while those
+// rows are still in L2 -- and write the bf16 rows the next GEMM consumes.  `counters` is one int per 128-row block,
+// zero on entry, left zero on exit.  Same arithmetic as layernorm_bf16 (bitwise identical result).
+struct LnFuse {
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  float eps = 0.f;
+  __nv_bfloat16* out = nullptr;  // [M, D] bf16, leading dimension ldo; nullptr = no fusion
+  long long ldo = 0;
+  int* counters = nullptr;
+};
+
 struct GemmArgs {
   const __nv_bfloat16* A;  // [M,K] row-major, ld = lda
   long long lda;
@@ -35,9 +48,16 @@ struct GemmArgs {
   int epi;        // EpiMode
   int cta_group;  // 1 or 2
   int num_sms;    // 0 -> 148
+  LnFuse ln;      // only with the in-place fp32 accumulate epilogue
+  // Opt-in to the weight-streaming path for M <= 64 (gemm_skinny.cu).  It sums K in a different order than the tcgen05
+  // tiles, so a caller that promises results independent of the batch size across the M = 64 boundary (the text
+  // encoder: bitwise batch-composition invariance) leaves it off; the decoder step and the speech pooler turn it on.
+  int allow_skinny = 0;
 };
 
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
+// true if gemm_bf16 can run `ln` fused for this shape (otherwise the caller launches layernorm_bf16 itself)
+bool gemm_ln_fusable(int M, int N, int cta_group, int num_sms);
 
 // M <= 64 rows: weight-streaming mma.sync path (gemm_skinny.cu); gemm_bf16 dispatches to it when eligible
 bool gemm_skinny_eligible(const GemmArgs& g);

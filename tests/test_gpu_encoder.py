@@ -188,3 +188,29 @@ def test_pipeline_file_input_and_target_device(pipeline, tmp_path):
     b = pipeline.predict(SENTS, "eng_Latn", batch_size=4)
     assert a.device.type == "cpu"
     torch.testing.assert_close(a, b.cpu(), rtol=1.3e-6, atol=1e-5)
+
+
+@pytest.mark.parametrize("lens_kind", ["dense", "ragged_tail"])
+def test_fused_layernorm_is_bitwise_the_separate_kernel(native_lib, cuda_device, monkeypatch, lens_kind):
+    """(Opt-in path, SONAR_B200_FUSE_LN.)  LayerNorm fused behind the residual GEMMs (idle warps of the GEMM CTAs normalise each 128-row block out of L2 once
+    all of its n-tiles have been reduced into x) must reproduce the separate LayerNorm kernels bit for bit -- any missed
+    reduce-add or early read would show here.  Sizes: many more tiles than CTAs, a row count that is not a multiple of 128,
+    repeated to shake out ordering races."""
+    from sonar_b200 import PaddingMask, SequenceBatch
+
+    _, model = _build(3, cuda_device, seed=5)
+    g = torch.Generator().manual_seed(9)
+    if lens_kind == "dense":
+        lens = [128] * 320  # 40 960 rows = 160 pair tiles x 4 n-tiles
+    else:
+        lens = [int(v) for v in torch.randint(1, 129, (333,), generator=g)]
+        lens[-1] = 77
+    ids = _batch(lens, 128, seed=4).to(cuda_device)
+    mask = PaddingMask(torch.tensor(lens), 128, lens)
+    monkeypatch.setenv("SONAR_B200_FUSE_LN", "0")
+    want = model(SequenceBatch(ids, mask)).sentence_embeddings.clone()
+    for mode in ("2", "1"):  # behind both residual GEMMs / behind FFN2 only
+        monkeypatch.setenv("SONAR_B200_FUSE_LN", mode)
+        for _ in range(3):
+            got = model(SequenceBatch(ids, mask)).sentence_embeddings
+            assert torch.equal(got, want)

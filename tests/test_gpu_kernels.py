@@ -88,7 +88,7 @@ def test_gemm_skinny_rows(ops, cuda_device, m, n, k, epilogue):
     a = _rand((m, k), 1.0, 31, cuda_device, torch.bfloat16)
     w = _rand((n, k), 1.0 / math.sqrt(k), 32, cuda_device, torch.bfloat16)
     bias = _rand((n,), 0.5, 33, cuda_device)
-    out = ops.gemm_bf16(a, w, bias, epilogue=epilogue)
+    out = ops.gemm_bf16(a, w, bias, epilogue=epilogue, cta_group=0)  # 0 = automatic dispatch
     ref = a.float() @ w.float().T + bias
     if epilogue == "relu":
         ref = torch.relu(ref)
@@ -96,7 +96,7 @@ def test_gemm_skinny_rows(ops, cuda_device, m, n, k, epilogue):
         ref = torch.nn.functional.silu(ref)
     err = (out.float() - ref).abs()
     assert bool((err <= ref.abs() * (1.5 * 2 ** -8) + 2e-2).all()), f"max err {err.max().item()}"
-    out32 = ops.gemm_bf16(a, w, bias, epilogue=epilogue, out_dtype=torch.float32)
+    out32 = ops.gemm_bf16(a, w, bias, epilogue=epilogue, out_dtype=torch.float32, cta_group=0)
     tol = dict(rtol=1e-4, atol=2e-3) if epilogue != "silu" else dict(rtol=2e-3, atol=2e-3)  # tanh.approx in the SiLU
     torch.testing.assert_close(out32, ref, **tol)
 
@@ -109,15 +109,15 @@ def test_gemm_skinny_residual_inplace_and_reproducible(ops, cuda_device, m, n, k
     x0 = _rand((m, n), 2.0, 37, cuda_device)
     ref = x0 + a.float() @ w.float().T + bias
     x = x0.clone()
-    out = ops.gemm_bf16(a, w, bias, epilogue="residual", residual=x, out=x)
+    out = ops.gemm_bf16(a, w, bias, epilogue="residual", residual=x, out=x, cta_group=0)
     assert out.data_ptr() == x.data_ptr()
     torch.testing.assert_close(x, ref, rtol=1e-4, atol=2e-3)
     y = x0.clone()
-    ops.gemm_bf16(a, w, bias, epilogue="residual", residual=y, out=y)
+    ops.gemm_bf16(a, w, bias, epilogue="residual", residual=y, out=y, cta_group=0)
     assert torch.equal(x, y)  # fixed reduction order across the K-split warps
     # rows are independent of the batch they sit in (beam search relies on it): row 3 alone == row 3 of the batch
     z = x0[3:4].clone()
-    ops.gemm_bf16(a[3:4].contiguous(), w, bias, epilogue="residual", residual=z, out=z)
+    ops.gemm_bf16(a[3:4].contiguous(), w, bias, epilogue="residual", residual=z, out=z, cta_group=0)
     assert torch.equal(z[0], x[3])
 
 
