@@ -19,3 +19,8 @@ echo "=== compute-sanitizer --tool racecheck : speech encoder (rel-pos attention
 timeout 1500 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest -x -q -m gpu \
   tests/test_gpu_speech.py::test_speech_encoder_vs_oracle \
   tests/test_gpu_decoder.py::test_teacher_forced_steps_match_oracle 2>&1 | tail -15
+echo "=== compute-sanitizer --tool memcheck : skinny GEMM, fused-LayerNorm GEMM, graph-replayed beam search ==="
+timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest -x -q -m gpu \
+  tests/test_gpu_kernels.py -k "skinny" \
+  "tests/test_gpu_encoder.py::test_fused_layernorm_is_bitwise_the_separate_kernel" \
+  tests/test_gpu_decoder.py::test_cuda_graph_replay_equals_eager_generation 2>&1 | tail -15
