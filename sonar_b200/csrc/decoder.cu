@@ -135,28 +135,49 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  for (int base = 0; base < nk; base += 4) {
-    const int tp = base + grp;
-    const bool valid = tp < nk;
-    const int pr = (valid && tp != t) ? trow[tp] : r;
-    const long long off = ((long long)pr * Tmax + (valid ? tp : t)) * D + h * 64 + sub * 8;
-    float k8[8], v8[8];
-    unpack8(*reinterpret_cast<const uint4*>(kcache + off), k8);
-    unpack8(*reinterpret_cast<const uint4*>(vcache + off), v8);
-    float s = 0.f;
+  // 16 keys per pass (4 per 8-lane group): the ancestry-table entries, then all eight 16-byte K / V loads of a lane are
+  // in flight before the first dot product -- the loop is bound by loaded HBM latency, not by arithmetic.
+  constexpr int U = 4;
+  for (int base = 0; base < nk; base += 4 * U) {
+    int tpv[U];
+    bool val[U];
+    int prow[U];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) s = fmaf(q8[e], k8[e], s);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (valid) {  // uniform inside each 8-lane group
-      const float mn = fmaxf(m, s);
-      const float corr = exp2f((m - mn) * sl2);  // m = -inf on the group's first key -> 0
-      const float pj = exp2f((s - mn) * sl2);
-      l = l * corr + pj;
+    for (int u = 0; u < U; ++u) {
+      tpv[u] = base + 4 * u + grp;
+      val[u] = tpv[u] < nk;
+      prow[u] = (val[u] && tpv[u] != t) ? __ldg(trow + tpv[u]) : r;
+    }
+    uint4 kq[U], vq[U];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, v8[e], acc[e] * corr);
-      m = mn;
+    for (int u = 0; u < U; ++u) {
+      const long long off = ((long long)prow[u] * Tmax + (val[u] ? tpv[u] : t)) * D + h * 64 + sub * 8;
+      kq[u] = vq[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (val[u]) {
+        kq[u] = *reinterpret_cast<const uint4*>(kcache + off);
+        vq[u] = *reinterpret_cast<const uint4*>(vcache + off);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float k8[8], v8[8];
+      unpack8(kq[u], k8);
+      unpack8(vq[u], v8);
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s = fmaf(q8[e], k8[e], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (val[u]) {  // uniform inside each 8-lane group
+        const float mn = fmaxf(m, s);
+        const float corr = exp2f((m - mn) * sl2);  // m = -inf on the group's first key -> 0
+        const float pj = exp2f((s - mn) * sl2);
+        l = l * corr + pj;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, v8[e], acc[e] * corr);
+        m = mn;
+      }
     }
   }
   // merge the four group states (a group that saw no key has m = -inf, l = 0)
