@@ -248,10 +248,9 @@ int attention_packed_tc(const __nv_bfloat16* qkv, const int32_t* cu_seqlens, int
   CUtensorMap tm;
   int rc = make_tmap_2d(&tm, qkv, 2, total_tokens, 3ll * H * 64, 3ll * H * 64, 128, 64);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     SB_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
   }
   long long items = (long long)B * H;
   long long grid = 2ll * (num_sms > 0 ? num_sms : 148);

@@ -705,10 +705,9 @@ int sb_speech_encoder_forward(SbSpeechEncoder* e, const float* fbank, int32_t pa
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   const int D = e->cfg.model_dim, F = e->cfg.ffn_inner_dim, H = e->cfg.num_heads, Fp = e->cfg.pooler_ffn_inner_dim;
   const float eps = e->cfg.ln_eps;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     SB_CUDA_CHECK(cudaFuncSetAttribute(attention_relpos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRpSmem));
-    attr_set = true;
   }
   int rc;
   // TMA views for the rel-pos attention: 64 x 64 boxes of the packed qkv rows [T, 3D] and of the projected table [Npad, D]

@@ -531,10 +531,9 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
                        int n_chunks = 1, const LnFuse& ln = LnFuse(), const float* ln_x = nullptr, long long ln_ldx = 0) {
   using Cfg = GemmCfg<kCtaGroup>;
   auto kern = gemm_bf16_tcgen05_kernel<kCtaGroup, kEpi, OutT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     SB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
   }
   const int tile_m = Cfg::BLOCK_M * kCtaGroup;
   const long long num_m_tiles = (M + tile_m - 1) / tile_m;

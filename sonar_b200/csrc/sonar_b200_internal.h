@@ -20,6 +20,16 @@ enum PoolMode { POOL_MAX = 1, POOL_MEAN = 2, POOL_LAST = 3 };  // = reference `P
 
 void set_last_error(const char* fmt, ...);
 
+// cudaFuncSetAttribute is per device: returns true the first time `flags` (a per-call-site static array of 64 bools)
+// is consulted for the current device.
+inline bool first_use_on_device(bool (&flags)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
+
 // Optional LayerNorm fused behind an in-place fp32 accumulate GEMM (x += A.W^T + b over FULL rows, N == D): the idle
 // warps of the GEMM CTAs normalise each 128-row block as soon as its last n-tile has been reduced into x -- while those
 // rows are still in L2 -- and write the bf16 rows the next GEMM consumes.  `counters` is one int per 128-row block,
