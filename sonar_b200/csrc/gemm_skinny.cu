@@ -16,8 +16,24 @@
 namespace sb {
 namespace {
 
+// The kernel is bound by loaded HBM latency (~2 us), so what matters is bytes in flight.  A CTA's 8 warps cover 1024
+// elements of K in one shot (8 rows x 2 KB of W, all loads issued before the first mma); longer K is split over a
+// thread-block CLUSTER of K/1024 CTAs along grid.y whose partial tiles meet in the leader CTA's shared memory (DSMEM
+// stores + one cluster barrier) and are summed there in rank order -- still deterministic, still one launch.
 constexpr int kSkinnyWarps = 8;
 constexpr int kSkinnyThreads = kSkinnyWarps * 32;
+constexpr int kSkinnyMaxSplit = 8;  // portable cluster size
+
+__device__ __forceinline__ void st_shared_cluster_f32(const float* local_addr, uint32_t cta, float v) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.f32 [ra], %2;\n\t"
+      "}\n" ::"r"(smem_u32(local_addr)),
+      "r"(cta), "f"(v)
+      : "memory");
+}
 
 __device__ __forceinline__ void mma16816_f32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                              uint32_t b1) {
@@ -26,17 +42,22 @@ __device__ __forceinline__ void mma16816_f32(float (&d)[4], uint32_t a0, uint32_
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// MT = number of 16-row activation tiles (M <= 16 * MT)
-template <int MT, typename OutT>
+// MT = number of 16-row activation tiles (M <= 16 * MT); UNROLL = 32-element chunks in flight per lane;
+// gridDim.y = cluster size = number of K splits (1..8)
+template <int MT, int UNROLL, typename OutT>
 __global__ void __launch_bounds__(kSkinnyThreads)
 gemm_skinny_kernel(const __nv_bfloat16* __restrict__ A, long long lda, const __nv_bfloat16* __restrict__ W, long long ldw,
                    OutT* C, long long ldc, const float* __restrict__ bias, int M, int N, int K, int epi) {
   __shared__ float part[kSkinnyWarps][MT * 16][8 + 1];
+  __shared__ float split_part[kSkinnyMaxSplit][MT * 16][8];  // leader CTA: one partial tile per cluster rank
+  const int nsplit = gridDim.y;
+  const uint32_t rank = (nsplit > 1) ? cluster_ctarank() : 0u;
+  if (nsplit > 1) cluster_sync_all();  // every CTA of the cluster is running before anyone stores into the leader's shared memory
   const int n0 = blockIdx.x * 8;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int kslice = K / kSkinnyWarps;  // multiple of 32 (host checks K % 256 == 0)
-  const int kbeg = warp * kslice;
+  const int kslice = K / (kSkinnyWarps * nsplit);  // multiple of 32 (host checks)
+  const int kbeg = (int(rank) * kSkinnyWarps + warp) * kslice;
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
   const __nv_bfloat16* wrow = W + (long long)(n0 + g) * ldw + kbeg + 8 * t;
   const __nv_bfloat16* arow[MT][2];
@@ -52,7 +73,7 @@ gemm_skinny_kernel(const __nv_bfloat16* __restrict__ A, long long lda, const __n
   float acc[MT][4];
 #pragma unroll
   for (int i = 0; i < MT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-  constexpr int kUnroll = 4;  // 32-element chunks in flight per lane
+  constexpr int kUnroll = UNROLL;
   for (int k = 0; k < kslice; k += 32 * kUnroll) {
     uint4 w4[kUnroll], a4[kUnroll][MT][2];
 #pragma unroll
@@ -65,6 +86,7 @@ gemm_skinny_kernel(const __nv_bfloat16* __restrict__ A, long long lda, const __n
         for (int hh = 0; hh < 2; ++hh)
           a4[u][i][hh] = (in && aok[i][hh]) ? __ldg(reinterpret_cast<const uint4*>(arow[i][hh] + k + 32 * u)) : zero4;
     }
+    asm volatile("" ::: "memory");  // scheduling fence: every load of the pass is issued before the first mma consumes one
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u)
 #pragma unroll
@@ -82,12 +104,28 @@ gemm_skinny_kernel(const __nv_bfloat16* __restrict__ A, long long lda, const __n
     part[warp][i * 16 + g + 8][2 * t + 1] = acc[i][3];
   }
   __syncthreads();
+  if (nsplit > 1) {
+    // every CTA of the cluster reduces its 8 warps in order and drops the tile into slot `rank` of the leader's buffer
+    for (int o = tid; o < MT * 16 * 8; o += kSkinnyThreads) {
+      const int r = o >> 3, c = o & 7;
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < kSkinnyWarps; ++w) v += part[w][r][c];
+      st_shared_cluster_f32(&split_part[rank][r][c], 0u, v);
+    }
+    cluster_sync_all();  // release/acquire at cluster scope: the leader sees every slot
+    if (rank != 0) return;
+  }
   for (int o = tid; o < MT * 16 * 8; o += kSkinnyThreads) {
     const int r = o >> 3, c = o & 7;
     if (r >= M) continue;
     float v = 0.f;
+    if (nsplit > 1) {
+      for (int q = 0; q < nsplit; ++q) v += split_part[q][r][c];  // rank order: bitwise reproducible
+    } else {
 #pragma unroll
-    for (int w = 0; w < kSkinnyWarps; ++w) v += part[w][r][c];  // fixed order: bitwise reproducible
+      for (int w = 0; w < kSkinnyWarps; ++w) v += part[w][r][c];  // fixed order: bitwise reproducible
+    }
     if (bias) v += bias[n0 + c];
     if (epi == EPI_BIAS_RELU) v = fmaxf(v, 0.f);
     if (epi == EPI_BIAS_SILU) v = silu_fast(v);
@@ -101,16 +139,32 @@ gemm_skinny_kernel(const __nv_bfloat16* __restrict__ A, long long lda, const __n
   }
 }
 
-template <int MT>
+template <int MT, int UNROLL>
 int launch_skinny(const GemmArgs& g, cudaStream_t stream) {
-  const dim3 grid((unsigned)(g.N / 8));
+  // K splits: one CTA per 1024 elements of K (cluster along grid.y, at most 8), each warp's slice a multiple of 32
+  int nsplit = g.K / 1024;
+  if (nsplit > kSkinnyMaxSplit) nsplit = kSkinnyMaxSplit;
+  while (nsplit > 1 && g.K % (nsplit * kSkinnyWarps * 32) != 0) --nsplit;
+  if (nsplit < 1) nsplit = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(g.N / 8), (unsigned)nsplit, 1);
+  cfg.blockDim = dim3(kSkinnyThreads, 1, 1);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = (unsigned)nsplit;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e;
   if (g.out_fp32)
-    gemm_skinny_kernel<MT, float><<<grid, kSkinnyThreads, 0, stream>>>(g.A, g.lda, g.W, g.ldw, reinterpret_cast<float*>(g.C),
-                                                                         g.ldc, g.bias, g.M, g.N, g.K, g.epi);
+    e = cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<MT, UNROLL, float>, g.A, g.lda, g.W, g.ldw,
+                           reinterpret_cast<float*>(g.C), g.ldc, g.bias, g.M, g.N, g.K, g.epi);
   else
-    gemm_skinny_kernel<MT, __nv_bfloat16><<<grid, kSkinnyThreads, 0, stream>>>(
-        g.A, g.lda, g.W, g.ldw, reinterpret_cast<__nv_bfloat16*>(g.C), g.ldc, g.bias, g.M, g.N, g.K, g.epi);
-  cudaError_t e = cudaGetLastError();
+    e = cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<MT, UNROLL, __nv_bfloat16>, g.A, g.lda, g.W, g.ldw,
+                           reinterpret_cast<__nv_bfloat16*>(g.C), g.ldc, g.bias, g.M, g.N, g.K, g.epi);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_last_error("gemm_skinny launch failed: %s", cudaGetErrorString(e));
     return -2;
@@ -138,9 +192,9 @@ bool gemm_skinny_eligible(const GemmArgs& g) {
 }
 
 int gemm_skinny(const GemmArgs& g, cudaStream_t stream) {
-  if (g.M <= 16) return launch_skinny<1>(g, stream);
-  if (g.M <= 32) return launch_skinny<2>(g, stream);
-  return launch_skinny<4>(g, stream);
+  if (g.M <= 16) return launch_skinny<1, 4>(g, stream);
+  if (g.M <= 32) return launch_skinny<2, 4>(g, stream);
+  return launch_skinny<4, 4>(g, stream);
 }
 
 }  // namespace sb
