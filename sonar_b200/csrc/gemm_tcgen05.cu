@@ -12,7 +12,8 @@
 //   buffered (2 x 256 = all 512 columns) so the epilogue of tile i overlaps the
 //   mainloop of tile i+1.  cta_group::1 variant: 128 x 256 x 64 per CTA.
 // Warp roles (256 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM alloc/dealloc,
-//   w3 idle, w4-7 epilogue (TMEM -> regs -> bias/ReLU/residual -> swizzled smem -> TMA store).
+//   w3 idle, w4-7 epilogue (TMEM -> regs -> bias/ReLU/residual -> swizzled smem -> TMA store).  With the optional
+//   fused LayerNorm (LnFuse, accumulate epilogue only) warps 2 and 3 normalise completed 128-row blocks out of L2.
 // Operand smem layout: K-major, 128-byte rows, SWIZZLE_128B (TMA writes it, UMMA reads it).
 
 #include "common.cuh"
