@@ -332,6 +332,20 @@ int sb_xsim_knn(const float* x, const float* y, int32_t n, int32_t m, int32_t d,
 int sb_xsim_margin_predict(const double* val_xy, const int32_t* idx_xy, const double* val_yx, int32_t n, int32_t m,
                            int32_t k, int32_t margin_mode, int32_t* pred, void* stream);
 
+/* ---- beam search bookkeeping (one step, one launch) ----
+ * The state transition of fairseq2's BeamSearchSeq2SeqGenerator [fs2] as the reference drives it
+ * (sonar/inference_pipelines/text.py:315-333): from the decoder step's 16 best continuations per hypothesis
+ * (lp / tok [N*beam,16], eos_lp [N*beam]) select the 2*beam best per sentence (score desc, then beam*vocab+token asc),
+ * retire the EOS-terminated ones ranked inside the beam into fin_* (slot CAP = 2*beam is scratch), and let the first
+ * `beam` others continue: seqs [N,beam,Tmax], the KV-cache ancestry table [N*beam,Tmax], tokens [N*beam], cum / alive
+ * [N,beam] and done [N] are updated in place (alive / done: one byte per flag).  t = position of the step's input token,
+ * g = number of tokens generated before this step; score_div = (g+1)^len_penalty.  beam <= 7. */
+int sb_beam_step(const float* lp, const int32_t* tok, const float* eos_lp, int64_t* seqs, int32_t* table,
+                 int64_t* tokens, float* cum, uint8_t* alive, uint8_t* done, float* fin_score, int64_t* fin_seq,
+                 int64_t* fin_len, int64_t* fin_count, int32_t N, int32_t beam, int32_t Tmax, int32_t t, int32_t g,
+                 int32_t min_gen, int32_t max_gen, int64_t vocab, int32_t eos, int32_t unk, int32_t pad,
+                 float unk_penalty, float score_div, int32_t normalize, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,8 +117,9 @@ def bench_decoder(peaks):
     # the pipelines' default batch (5 sentences x beam 5 = 25 hypothesis rows): launch-bound unless the step is a CUDA graph
     small = {}
     emb5 = emb[:5].contiguous()
-    for label, flag in (("eager", False), ("cuda_graphs", True)):
-        gsm = BeamSearchSeq2SeqGenerator(model, beam_size=beam, max_seq_len=max_seq_len, pad_idx=0, cuda_graphs=flag)
+    for label, flag, fused in (("eager_torch_beam_ops", False, False), ("eager", False, True), ("cuda_graphs", True, True)):
+        gsm = BeamSearchSeq2SeqGenerator(model, beam_size=beam, max_seq_len=max_seq_len, pad_idx=0, cuda_graphs=flag,
+                                         fused_beam_step=fused)
         gsm(emb5, None, prompt, None)  # warm-up (records the graphs)
         torch.cuda.synchronize()
         t1 = time.perf_counter()

@@ -79,6 +79,33 @@ add_sentence_const_kernel(float* __restrict__ x, const float* __restrict__ c, in
   }
 }
 
+// x[r,:] += c[r / beam, :], then h[r,:] = LayerNorm(x[r,:]) in bf16: the collapsed cross-attention residual and the FFN
+// LayerNorm in one pass over the row (bit-identical to add_sentence_const_kernel followed by layernorm_bf16).
+__global__ void __launch_bounds__(256)
+add_const_layernorm_kernel(float* __restrict__ x, const float* __restrict__ c, int R, int beam, int D,
+                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                           __nv_bfloat16* __restrict__ h) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const int nvec = D / 128;
+  float4 v[kMaxVec], cv[kMaxVec];
+  load_row(x + (long long)r * D, nvec, lane, v);
+  load_row(c + (long long)(r / beam) * D, nvec, lane, cv);
+  float4* xr = reinterpret_cast<float4*>(x + (long long)r * D);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i)
+    if (i < nvec) {
+      v[i].x += cv[i].x; v[i].y += cv[i].y; v[i].z += cv[i].z; v[i].w += cv[i].w;
+      xr[i * 32 + lane] = v[i];
+    }
+  normalize_row(v, nvec, lane, D, gamma, beta, eps);
+  uint2* hr = reinterpret_cast<uint2*>(h + (long long)r * D);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i)
+    if (i < nvec) hr[i * 32 + lane] = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+}
+
 // fp32 [n, D] -> bf16 (plain cast; A operand of the cross-attention constant GEMMs)
 __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -494,9 +521,15 @@ int sb_decoder_step(SbDecoder* d, const int64_t* tokens, const int32_t* table, i
     g.C = w.x; g.ldc = D; g.out_fp32 = 1; g.bias = L.bo; g.residual = w.x; g.ldr = D;
     g.N = D; g.K = D; g.epi = EPI_BIAS_RESIDUAL;
     if ((rc = gemm_bf16(g, stream))) return rc;
-    add_sentence_const_kernel<<<row_blocks, 256, 0, stream>>>(w.x, w.cross + (size_t)li * N * D, R, beam, D);
-    SB_CUDA_CHECK(cudaGetLastError());
-    if ((rc = layernorm_bf16(w.x, L.ln3_g, L.ln3_b, d->cfg.ln_eps, w.h, R, D, stream))) return rc;
+    if (D % 128 == 0 && D <= 128 * kMaxVec) {
+      add_const_layernorm_kernel<<<row_blocks, 256, 0, stream>>>(w.x, w.cross + (size_t)li * N * D, R, beam, D, L.ln3_g,
+                                                                 L.ln3_b, d->cfg.ln_eps, w.h);
+      SB_CUDA_CHECK(cudaGetLastError());
+    } else {
+      add_sentence_const_kernel<<<row_blocks, 256, 0, stream>>>(w.x, w.cross + (size_t)li * N * D, R, beam, D);
+      SB_CUDA_CHECK(cudaGetLastError());
+      if ((rc = layernorm_bf16(w.x, L.ln3_g, L.ln3_b, d->cfg.ln_eps, w.h, R, D, stream))) return rc;
+    }
     g.A = w.h; g.lda = D; g.W = reinterpret_cast<const __nv_bfloat16*>(L.w1); g.ldw = D;
     g.C = w.f; g.ldc = F; g.out_fp32 = 0; g.bias = L.b1; g.residual = nullptr; g.ldr = 0;
     g.N = F; g.K = D; g.epi = EPI_BIAS_RELU;

@@ -18,6 +18,7 @@ from typing import List, Optional, Sequence, Tuple, Union
 import torch
 from torch import Tensor
 
+from . import _lib
 from .text_decoder import TOPK, B200TextDecoderModel
 
 NEG_INF = float("-inf")
@@ -103,11 +104,14 @@ class BeamSearchSeq2SeqGenerator:
                  max_gen_len: Tuple[int, int] = (1, 128), max_seq_len: Optional[int] = None, echo_prompt: bool = False,
                  normalize_scores: bool = True, temperature: float = 1.0, unk_penalty: float = 0.0,
                  len_penalty: float = 1.0, pad_idx: int = 0, sync_every: int = 8,
-                 cuda_graphs: Optional[bool] = None) -> None:
+                 cuda_graphs: Optional[bool] = None, fused_beam_step: Optional[bool] = None) -> None:
         """``cuda_graphs``: replay each decode step (the ~290 engine launches + the beam bookkeeping) as one CUDA graph.
         A small batch -- the pipelines' default ``batch_size=5`` is 25 hypotheses -- is launch-bound otherwise.  ``None``
         (default) turns it on for up to 512 hypothesis rows unless ``SONAR_B200_DECODE_GRAPHS=0``; graphs are captured the
-        first time a (batch shape, step) is seen and cached on the model, so only repeated shapes benefit."""
+        first time a (batch shape, step) is seen and cached on the model, so only repeated shapes benefit.
+        ``fused_beam_step``: run the bookkeeping of a step as the single ``sb_beam_step`` kernel instead of the ~60 torch
+        ops below (same state transition bit for bit; the torch ops remain the definition the CPU tests check against the
+        oracle).  ``None`` = on for CUDA models unless ``SONAR_B200_FUSED_BEAM=0``."""
         if beam_size < 1:
             raise ValueError("`beam_size` must be greater than or equal to 1")
         if 2 * beam_size > TOPK:
@@ -128,6 +132,7 @@ class BeamSearchSeq2SeqGenerator:
         self.pad_idx = pad_idx
         self.sync_every = sync_every
         self.cuda_graphs = cuda_graphs
+        self.fused_beam_step = fused_beam_step
 
     def _advance(self, st: _DecodeState, g: int, P: int, min_gen: int, max_gen: int) -> None:
         """One decode step: position t = P-1+g of every live hypothesis -> the next beam, all state updated in place."""
@@ -139,6 +144,20 @@ class BeamSearchSeq2SeqGenerator:
         dev = st.seqs.device
         t = P - 1 + g  # position of the input token; the new token lands at t + 1
         lp, tok, eos_lp = m.step(st.tokens, st.table, t)
+        fused = self.fused_beam_step
+        if fused is None:
+            fused = os.environ.get("SONAR_B200_FUSED_BEAM", "1") != "0"
+        if fused and dev.type == "cuda" and B <= 7 and TOPK == 16:
+            div = float(g + 1) ** self.len_penalty
+            with torch.cuda.device(dev):
+                rc = m._lib.sb_beam_step(
+                    lp.data_ptr(), tok.data_ptr(), eos_lp.data_ptr(), st.seqs.data_ptr(), st.table.data_ptr(),
+                    st.tokens.data_ptr(), st.cum.data_ptr(), st.alive.data_ptr(), st.done.data_ptr(),
+                    st.fin_score.data_ptr(), st.fin_seq.data_ptr(), st.fin_len.data_ptr(), st.fin_count.data_ptr(),
+                    N, B, Tmax, t, g, min_gen, max_gen, V, eos, unk, pad, float(self.unk_penalty), div,
+                    1 if self.normalize_scores else 0, torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(rc, "sb_beam_step")
+            return
         lp = lp.view(N, B, TOPK)
         tok = tok.view(N, B, TOPK).long()
         lp = lp.masked_fill((tok < 0) | (tok == pad), NEG_INF)
@@ -164,7 +183,10 @@ class BeamSearchSeq2SeqGenerator:
         fin_ok = fin_mask & (fin_pos < CAP)
         dest = torch.where(fin_ok, fin_pos, torch.full_like(fin_pos, CAP))
         gen_len = g + 1
-        fscore = c_score / (float(gen_len) ** self.len_penalty) if self.normalize_scores else c_score
+        # divisor as a 0-dim tensor: IEEE division on every device (a Python-scalar divisor becomes a multiplication by the
+        # reciprocal in torch's CUDA kernel, one ulp away from the CPU result and from sb_beam_step)
+        fscore = c_score / torch.full((), float(gen_len) ** self.len_penalty, dtype=torch.float32, device=dev) \
+            if self.normalize_scores else c_score
         st.fin_score.scatter_(1, dest, torch.where(fin_ok, fscore, torch.full_like(fscore, NEG_INF)))
         cand_seqs = torch.gather(st.seqs, 1, c_beam[:, :, None].expand(N, 2 * B, Tmax)).clone()
         cand_seqs[:, :, t + 1] = c_tok

@@ -153,3 +153,64 @@ def test_cuda_graph_replay_equals_eager_generation(small, cuda_device):
     for ha, hc in zip(a.hypotheses, c.hypotheses):
         for x, y in zip(ha, hc):
             assert torch.equal(x.seq, y.seq) and x.score == y.score
+
+
+@pytest.mark.parametrize("kw", [
+    dict(beam_size=5, max_seq_len=20),
+    dict(beam_size=3, max_seq_len=9, min_gen_len=3),
+    dict(beam_size=1, max_seq_len=12),
+    dict(beam_size=4, max_seq_len=16, unk_penalty=0.7, len_penalty=0.6),
+    dict(beam_size=7, max_seq_len=10, normalize_scores=False),
+])
+def test_fused_beam_step_equals_the_torch_bookkeeping(native_lib, cuda_device, kw):
+    """`sb_beam_step` (one launch per step) must make exactly the state transition of the vectorised torch ops in
+    `generation.py::_advance` -- the version the CPU tests hold to the oracle.  A decoder whose EOS embedding is inflated
+    finishes hypotheses at every step, so finalisation, the 2*beam cap, `done` and the forced EOS at the length limit are
+    all exercised; hypotheses (tokens and scores) and the whole search state are compared bit for bit."""
+    from sonar_b200 import B200TextDecoderModel, VocabularyInfo, sonar_text_decoder_config
+    from sonar_b200 import generation as G
+
+    ocfg = OracleDecoderConfig(vocab_size=VOCAB, num_layers=2, max_seq_len=64)
+    sd = make_synthetic_decoder_state_dict(ocfg, seed=7)
+    sd["decoder_frontend.embed.weight"] *= 3.0
+    sd["decoder_frontend.embed.weight"][3] *= 2.5  # EOS (idx 3) competes at every step
+    sd["decoder_frontend.embed.weight"][1] *= 2.0  # and so does UNK / PAD (idx 1): penalties and pad masking matter
+    sd["final_proj.weight"] = sd["decoder_frontend.embed.weight"]
+    cfg = sonar_text_decoder_config("basic", num_decoder_layers=2, max_seq_len=64,
+                                    vocab_info=VocabularyInfo(size=VOCAB, unk_idx=1, bos_idx=2, eos_idx=3, pad_idx=0))
+    model = B200TextDecoderModel(cfg, sd, cuda_device)
+    prompt = torch.tensor([2, 9])
+    emb = _emb(6, seed=31).to(cuda_device)
+    states = {}
+    orig_reset = G._DecodeState.reset
+
+    outs = {}
+    for fused in (False, True):
+        gen = G.BeamSearchSeq2SeqGenerator(model, cuda_graphs=False, fused_beam_step=fused, pad_idx=0, **kw)
+        captured = []
+
+        def spy(self, prompt_, pad_, _c=captured):
+            _c.append(self)
+            return orig_reset(self, prompt_, pad_)
+
+        G._DecodeState.reset = spy
+        try:
+            outs[fused] = gen(emb, None, prompt, None)
+        finally:
+            G._DecodeState.reset = orig_reset
+        states[fused] = captured[0]
+    a, b = outs[False], outs[True]
+    n_finished = 0
+    for ha, hb in zip(a.hypotheses, b.hypotheses):
+        assert len(ha) == len(hb)
+        n_finished += len(ha)
+        for x, y in zip(ha, hb):
+            assert torch.equal(x.seq, y.seq) and x.score == y.score
+    assert n_finished > 0
+    sa, sb_ = states[False], states[True]
+    cap = sa.CAP
+    for name in ("seqs", "table", "tokens", "cum", "alive", "done", "fin_count"):
+        assert torch.equal(getattr(sa, name), getattr(sb_, name)), name
+    assert torch.equal(sa.fin_score[:, :cap], sb_.fin_score[:, :cap])
+    assert torch.equal(sa.fin_len[:, :cap], sb_.fin_len[:, :cap])
+    assert torch.equal(sa.fin_seq[:, :cap], sb_.fin_seq[:, :cap])
