@@ -34,9 +34,11 @@ def _emb(n, seed=0):
     return torch.randn((n, 1024), generator=g) * 0.25 / math.sqrt(1024) * 32.0
 
 
-def test_teacher_forced_steps_match_oracle(small, cuda_device):
+@pytest.mark.parametrize("n,beam,steps", [(3, 2, 9), (26, 3, 5)])
+def test_teacher_forced_steps_match_oracle(small, cuda_device, n, beam, steps):
+    """6 hypothesis rows take the few-rows schedule (skinny GEMMs with the LayerNorms and the cross-attention constant folded
+    in); 78 rows take the tcgen05 tiles with the separate LayerNorm / add kernels."""
     oracle, model = small
-    n, beam, steps = 3, 2, 9
     emb = _emb(n)
     g = torch.Generator().manual_seed(1)
     toks = torch.randint(4, VOCAB, (n * beam, steps), generator=g)
