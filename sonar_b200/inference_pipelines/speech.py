@@ -123,3 +123,108 @@ class SpeechToTextModelPipeline(SpeechToEmbeddingModelPipeline):
             pipeline = add_progress_bar(pipeline, inputs=input, batch_size=batch_size)
         results: List[List[str]] = list(iter(pipeline))
         return [x for y in results for x in y]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# TSV-driven pipelines (reference ``speech.py:42-274``): a manifest whose column ``audio_path_index`` names audio files
+# under ``audio_root_dir``; the first line is a header.  ``build_pipeline(context)`` returns an iterable with one item per
+# bucket of ``batch_size`` lines -- the model output the reference's ``DataPipeline`` yields under ``audio.data``.
+# ---------------------------------------------------------------------------------------------------------------------
+from dataclasses import dataclass  # noqa: E402
+from typing import Iterator, Optional  # noqa: E402
+
+
+@dataclass
+class SpeechInferenceParams:
+    """Same fields and defaults as the reference dataclass (``speech.py:42-77``)."""
+
+    data_file: Path
+    audio_root_dir: Path
+    audio_path_index: int
+    batch_size: int
+    fbank_dtype: torch.dtype = torch.float32
+    target_lang: Optional[str] = None
+    pad_idx: int = 0
+    device: Device = CPU_DEVICE
+    n_parallel: int = 4
+    n_prefetched_batches: int = 4
+
+
+def read_tsv_audio_paths(data_file: Union[str, Path], audio_path_index: int) -> Iterator[str]:
+    """``read_text(rtrim=True).skip(1).map(StrSplitter(indices=[audio_path_index]))`` (``speech.py:103-109``)."""
+    with open(data_file, "r", encoding="utf-8") as f:
+        for lineno, line in enumerate(f):
+            if lineno == 0:
+                continue  # header
+            line = line.rstrip()
+            if not line:
+                continue
+            fields = line.split("\t")
+            if audio_path_index >= len(fields):
+                raise ValueError(f"{data_file}:{lineno + 1}: no column {audio_path_index}")
+            yield fields[audio_path_index]
+
+
+class AudioToFbankDataPipelineBuilder:
+    """Manifest -> buckets of waveforms -> (fbank ``SequenceBatch``) per bucket (``speech.py:94-147``); the fbank runs on the
+    device of ``context``."""
+
+    def build_pipeline(self, context: SpeechInferenceParams) -> Iterator[SequenceBatch]:
+        if context.pad_idx != 0:
+            raise NotImplementedError("fbank batches are zero padded (the reference default)")
+        if context.fbank_dtype != torch.float32:
+            raise NotImplementedError("the B200 frontend produces fp32 features")
+        frontend = WaveformToFbank(torch.device(context.device))
+        root = Path(context.audio_root_dir)
+        waves = (_read_wav(root / p) for p in read_tsv_audio_paths(context.data_file, context.audio_path_index))
+
+        def batches():  # file decoding runs ahead on the prefetch thread; the fbank kernels stay on the caller's thread
+            for group in prefetch(bucket(waves, context.batch_size), context.n_prefetched_batches):
+                fb, frames = frontend(group)
+                yield SequenceBatch(fb, PaddingMask(torch.tensor(frames), fb.shape[1], seq_lens_host=frames))
+
+        return batches()
+
+
+class SpeechToEmbeddingPipeline:
+    """``SpeechToEmbeddingPipeline`` (``speech.py:150-201``): yields the encoder output of every bucket."""
+
+    def __init__(self, model: B200SpeechEncoderModel) -> None:
+        self.model = model.eval()
+        self.audio_to_fbank_dp_builder = AudioToFbankDataPipelineBuilder()
+
+    @classmethod
+    def load_model_from_name(cls, encoder_name: str) -> "SpeechToEmbeddingPipeline":
+        raise FileNotFoundError(f"speech encoder card {encoder_name!r} cannot be resolved offline; construct with a model object")
+
+    def build_pipeline(self, context: SpeechInferenceParams):
+        @torch.inference_mode()
+        def run():
+            for batch in self.audio_to_fbank_dp_builder.build_pipeline(context):
+                yield self.model(batch)
+
+        return run()
+
+
+class SpeechToTextPipeline:
+    """``SpeechToTextPipeline`` (``speech.py:204-274``): yields the translated texts of every bucket."""
+
+    def __init__(self, encoder: B200SpeechEncoderModel, decoder: B200TextDecoderModel, tokenizer) -> None:
+        self.encoder = encoder.eval()
+        self.decoder = decoder.eval()  # type: ignore
+        self.tokenizer = tokenizer
+        self.audio_to_fbank_dp_builder = AudioToFbankDataPipelineBuilder()
+
+    def build_pipeline(self, context: SpeechInferenceParams, **generator_kwargs):
+        assert context.target_lang is not None
+        generator_kwargs.setdefault("pad_idx", self.tokenizer.vocab_info.pad_idx)
+        generator = BeamSearchSeq2SeqGenerator(self.decoder, **generator_kwargs)
+        converter = SequenceToTextConverter(generator, self.tokenizer, task="translation", target_lang=context.target_lang)
+
+        @torch.inference_mode()
+        def run():
+            for batch in self.audio_to_fbank_dp_builder.build_pipeline(context):
+                texts, _ = converter.batch_convert(self.encoder(batch).sentence_embeddings, None)
+                yield texts
+
+        return run()

@@ -159,3 +159,44 @@ def test_speech_to_text_pipeline_composes_encoder_and_decoder(speech_small, cuda
     want = EmbeddingToTextModelPipeline(dec, tok, device=cuda_device).predict(emb, target_lang="fra_Latn", batch_size=2,
                                                                               max_seq_len=10)
     assert texts == want
+
+
+def test_tsv_pipelines_match_the_model_pipelines(speech_small, cuda_device, tmp_path):
+    """`SpeechToEmbeddingPipeline` / `SpeechToTextPipeline` (reference speech.py:150-274): a TSV manifest naming WAV files
+    under a root directory gives, bucket by bucket, what the tensor-driven pipelines give for the same waveforms."""
+    import wave
+
+    from oracle.text_decoder import OracleDecoderConfig, make_synthetic_decoder_state_dict
+    from sonar_b200 import B200TextDecoderModel, VocabularyInfo, sonar_text_decoder_config
+    from sonar_b200.inference_pipelines import (SpeechInferenceParams, SpeechToEmbeddingModelPipeline,
+                                                SpeechToEmbeddingPipeline, SpeechToTextModelPipeline, SpeechToTextPipeline)
+    from sonar_b200.tokenizer import SyntheticTokenizer
+
+    _, enc = speech_small
+    g = torch.Generator().manual_seed(13)
+    (tmp_path / "clips").mkdir()
+    lines, waves = ["id\taudio\tnote"], []
+    for i in range(5):
+        pcm = ((torch.randn(9000 + 640 * i, generator=g) * 0.1).clamp(-1, 1) * 32767).round().to(torch.int16)
+        with wave.open(str(tmp_path / "clips" / f"u{i}.wav"), "wb") as f:
+            f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(pcm.numpy().tobytes())
+        lines.append(f"{i}\tclips/u{i}.wav\tx")
+        waves.append((pcm.float() / 32768.0)[None, :])
+    manifest = tmp_path / "test.tsv"
+    manifest.write_text("\n".join(lines) + "\n")
+    ctx = SpeechInferenceParams(data_file=manifest, audio_root_dir=tmp_path, audio_path_index=1, batch_size=2,
+                                device=cuda_device, target_lang="fra_Latn")
+    outs = list(SpeechToEmbeddingPipeline(enc).build_pipeline(ctx))
+    assert [o.sentence_embeddings.shape[0] for o in outs] == [2, 2, 1]
+    want = SpeechToEmbeddingModelPipeline(enc, device=cuda_device).predict(waves, batch_size=2)
+    assert torch.equal(torch.cat([o.sentence_embeddings for o in outs]), want)
+
+    vocab = 4096
+    sd = make_synthetic_decoder_state_dict(OracleDecoderConfig(vocab_size=vocab, num_layers=2, max_seq_len=64), seed=4)
+    cfg = sonar_text_decoder_config("basic", num_decoder_layers=2, max_seq_len=64,
+                                    vocab_info=VocabularyInfo(size=vocab, unk_idx=1, bos_idx=2, eos_idx=3, pad_idx=1))
+    dec = B200TextDecoderModel(cfg, sd, cuda_device)
+    tok = SyntheticTokenizer(vocab_size=vocab)
+    texts = [t for bucket_texts in SpeechToTextPipeline(enc, dec, tok).build_pipeline(ctx, max_seq_len=10) for t in bucket_texts]
+    assert texts == SpeechToTextModelPipeline(enc, dec, tok, device=cuda_device).predict(waves, target_lang="fra_Latn",
+                                                                                       batch_size=2, max_seq_len=10)

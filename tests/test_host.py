@@ -133,3 +133,17 @@ def test_no_cpu_fallback_in_product():
 
     with pytest.raises(RuntimeError, match="CUDA"):
         B200TextEncoderModel(sonar_text_encoder_config("basic"), {}, device="cpu")
+
+
+def test_tsv_manifest_reader(tmp_path):
+    """`read_tsv_audio_paths`: skip the header, right-trim, take one column (reference speech.py:103-109)."""
+    from sonar_b200.inference_pipelines import SpeechInferenceParams, read_tsv_audio_paths
+
+    f = tmp_path / "m.tsv"
+    f.write_text("id\ttext\taudio\n1\thello\ta.wav  \n2\tworld\tsub/b.wav\n\n")
+    assert list(read_tsv_audio_paths(f, 2)) == ["a.wav", "sub/b.wav"]
+    assert list(read_tsv_audio_paths(f, 0)) == ["1", "2"]
+    with pytest.raises(ValueError):
+        list(read_tsv_audio_paths(f, 5))
+    ctx = SpeechInferenceParams(data_file=f, audio_root_dir=tmp_path, audio_path_index=2, batch_size=4)
+    assert ctx.pad_idx == 0 and ctx.n_parallel == 4 and ctx.n_prefetched_batches == 4 and ctx.target_lang is None
