@@ -82,7 +82,7 @@ class ClockSampler:
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,power.limit")
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
@@ -108,7 +108,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, pw, plim = [], None, set(), [], None
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 8:
@@ -118,12 +118,19 @@ class ClockSampler:
                 mx = float(f[2])
             except ValueError:
                 continue
+            try:  # board power next to the clocks: the step runs under sw_power_cap, this says how close to the limit
+                pw.append(float(f[3]))
+                if len(f) > 8:
+                    plim = float(f[8])
+            except ValueError:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
+        pw.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w": pw[len(pw) // 2] if pw else None, "power_limit_w": plim}
 
 
 def dist_env():
