@@ -147,3 +147,42 @@ def test_tsv_manifest_reader(tmp_path):
         list(read_tsv_audio_paths(f, 5))
     ctx = SpeechInferenceParams(data_file=f, audio_root_dir=tmp_path, audio_path_index=2, batch_size=4)
     assert ctx.pad_idx == 0 and ctx.n_parallel == 4 and ctx.n_prefetched_batches == 4 and ctx.target_lang is None
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU restatement timed on host cores) needs no GPU: exactly one JSON line on stdout
+    carrying the driver's keys."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "sentences/sec->1024-d" and d["unit"] == "sentences/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_clock_sampler_parses_power_and_reasons():
+    import bench
+
+    class _P:
+        def terminate(self):
+            pass
+
+    c = bench.ClockSampler(0)
+    c.proc = _P()
+    c.rows = ["0, 1290, 1965, 987.5, Not Active, Not Active, Not Active, Active, 1000.00",
+              "0, 1305, 1965, 991.2, Not Active, Not Active, Not Active, Active, 1000.00", "garbage"]
+    out = c.stop()
+    assert out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"] and out["samples"] == 2
+    assert out["power_w"] == 991.2 and out["power_limit_w"] == 1000.0
+    c.rows = ["0, 1290, 1965, [N/A], Not Active, Active, Not Active, Not Active"]
+    out = c.stop()
+    assert out["reasons"] == ["hw_thermal_slowdown"] and out["power_w"] is None
