@@ -186,3 +186,17 @@ def test_clock_sampler_parses_power_and_reasons():
     c.rows = ["0, 1290, 1965, [N/A], Not Active, Active, Not Active, Not Active"]
     out = c.stop()
     assert out["reasons"] == ["hw_thermal_slowdown"] and out["power_w"] is None
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_bench_product_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback: without a CUDA device the product arm exits with an error instead of timing anything."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], capture_output=True, text=True,
+                       timeout=300, cwd=root)
+    assert p.returncode != 0
+    assert "no CUDA device" in (p.stderr + p.stdout)
+    assert not [l for l in p.stdout.splitlines() if l.startswith("{")]
