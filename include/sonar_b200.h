@@ -223,10 +223,13 @@ int sb_decoder_begin(SbDecoder* dec, const float* embeddings, int32_t num_senten
  *   table   DEVICE int32 [R, max_len]  table[r, t'] = physical cache row holding position t' < t of hypothesis r
  *   out_lprob / out_tok DEVICE [R, 16] the 16 most probable next tokens (fp32 log-softmax over the whole vocabulary),
  *                                      ordered by (log-prob desc, token asc)
- *   out_eos_lprob DEVICE fp32 [R]      log P(eos) */
+ *   out_eos_lprob DEVICE fp32 [R]      log P(eos)
+ *   probe_tokens  DEVICE int64 [R] or NULL; with it out_probe_lprob DEVICE fp32 [R] = log P(probe_tokens[r]) -- the
+ *                                      prompt-token scores fairseq2's generator accumulates while prefilling [fs2 _prefill] */
 int sb_decoder_step(SbDecoder* dec, const int64_t* tokens, const int32_t* table, int32_t t, int32_t num_sentences,
                     int32_t beam, int32_t max_len, float* out_lprob, int32_t* out_tok, float* out_eos_lprob,
-                    void* workspace, size_t workspace_bytes, void* stream);
+                    const int64_t* probe_tokens, float* out_probe_lprob, void* workspace, size_t workspace_bytes,
+                    void* stream);
 int sb_decoder_check_inputs(SbDecoder* dec, void* workspace, void* stream);
 
 /* ---- speech feature frontend (BASELINE.json config 3, rows a9/a10) ----
@@ -336,14 +339,16 @@ int sb_xsim_margin_predict(const double* val_xy, const int32_t* idx_xy, const do
  * The state transition of fairseq2's BeamSearchSeq2SeqGenerator [fs2] as the reference drives it
  * (sonar/inference_pipelines/text.py:315-333): from the decoder step's 16 best continuations per hypothesis
  * (lp / tok [N*beam,16], eos_lp [N*beam]) select the 2*beam best per sentence (score desc, then beam*vocab+token asc),
- * retire the EOS-terminated ones ranked inside the beam into fin_* (slot CAP = 2*beam is scratch), and let the first
- * `beam` others continue: seqs [N,beam,Tmax], the KV-cache ancestry table [N*beam,Tmax], tokens [N*beam], cum / alive
+ * retire the EOS-terminated ones ranked inside the beam into fin_* until the sentence owns `beam` hypotheses (slot
+ * CAP = 2*beam is scratch), and let the first `beam` others continue: seqs [N,beam,Tmax], the KV-cache ancestry table [N*beam,Tmax], tokens [N*beam], cum / alive
  * [N,beam] and done [N] are updated in place (alive / done: one byte per flag).  t = position of the step's input token,
- * g = number of tokens generated before this step; score_div = (g+1)^len_penalty.  beam <= 7. */
+ * g = number of tokens generated before this step; EOS is forbidden while g < eos_block (= min_gen_len - 1: fairseq2's
+ * `step_nr < min_seq_len - 1`); score_div = (P+g)^len_penalty with P the prompt length (fairseq2 normalises by
+ * seq_len - 1 counting prompt and EOS).  beam <= 7. */
 int sb_beam_step(const float* lp, const int32_t* tok, const float* eos_lp, int64_t* seqs, int32_t* table,
                  int64_t* tokens, float* cum, uint8_t* alive, uint8_t* done, float* fin_score, int64_t* fin_seq,
                  int64_t* fin_len, int64_t* fin_count, int32_t N, int32_t beam, int32_t Tmax, int32_t t, int32_t g,
-                 int32_t min_gen, int32_t max_gen, int64_t vocab, int32_t eos, int32_t unk, int32_t pad,
+                 int32_t eos_block, int32_t max_gen, int64_t vocab, int32_t eos, int32_t unk, int32_t pad,
                  float unk_penalty, float score_div, int32_t normalize, void* stream);
 
 #ifdef __cplusplus

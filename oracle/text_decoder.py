@@ -14,8 +14,10 @@ Restates:
 
 Pinning: the layer maths is pinned against HuggingFace ``M2M100Decoder`` (independent implementation of the same
 fairseq lineage) through ``tests/golden/m2m100_decoder_small.pt`` (``tests/golden/make_m2m100_golden.py``).
-The beam-search bookkeeping is **parity unpinned**: fairseq2 is not installable here and the reference's only
-pins (exact output strings, ``tests/integration_tests/test_text_sonar.py:107-118``) need real weights.
+The beam-search bookkeeping restates fairseq2 0.4 from two independent recollections of its source (fairseq2 is not
+installable here; the reference's own pins -- exact output strings, ``tests/integration_tests/test_text_sonar.py:107-118`` --
+need real weights).  It is cross-checked against HuggingFace ``generate(num_beams=...)`` on a tiny M2M100 decoder in the
+regime where the two algorithms coincide (``tests/test_beam_vs_hf.py``); every divergence is listed there.
 """
 
 from __future__ import annotations
@@ -132,13 +134,27 @@ class OracleTextDecoder:
 
 
 # ----------------------------------------------------------------------------------------------------------
-# beam search (fairseq2 BeamSearchSeq2SeqGenerator + StandardBeamSearchAlgorithm semantics)
+# beam search (fairseq2 0.4 BeamSearchSeq2SeqGenerator + StandardBeamSearchAlgorithm semantics)
+#
+# Written in fairseq2's own terms (``step_nr`` = absolute index of the position being generated, prompt included)
+# so each rule can be read against ``fairseq2/generation/beam_search.py`` [fs2]:
+#   _prefill         the cumulative log-prob of prompt tokens 1..P-1 seeds every hypothesis score
+#                    (``step_scores[:, 1:P] = cumsum(lprob(prompt[s] | prompt[:s]))``)
+#   _step            PAD never; UNK -= unk_penalty; EOS forbidden while ``step_nr < min_seq_len - 1`` with
+#                    ``min_seq_len = P + min_gen_len`` (so ``min_gen_len=1`` allows an immediate EOS); on the last
+#                    step (``step_nr == max_seq_len - 1``) everything but EOS is -inf
+#   algorithm.step   scores = lprobs + cumulative score; top ``min(2*beam, V)`` over beam x V (first step: one beam)
+#   _search_beam     EOS candidates count only inside the top ``beam`` ranks; they are finished in rank order and the
+#                    sentence is closed the moment it owns ``beam`` hypotheses (later EOS candidates of that step are
+#                    dropped); the next beam = the first ``beam`` non-EOS candidates
+#   _finish_sequence score /= (seq_len - 1) ** len_penalty with seq_len = step_nr + 1 counting prompt and EOS
+#                    ("the first step's score is always 0, do not include it in the normalisation")
 # ----------------------------------------------------------------------------------------------------------
 @dataclass
 class BeamSearchConfig:
     beam_size: int = 5
     min_gen_len: int = 1
-    max_gen_len: int = 128      # generated tokens, prompt excluded (README.md:83 passes max_seq_len explicitly)
+    max_gen_len: int = 128      # generated tokens incl. EOS, prompt excluded (README.md:83 passes max_seq_len explicitly)
     normalize_scores: bool = True
     len_penalty: float = 1.0
     unk_penalty: float = 0.0
@@ -164,17 +180,18 @@ def beam_search_step(lprobs: Tensor, cum: Tensor, step: int, cfg: BeamSearchConf
 
 
 def constrain_lprobs(lprobs: Tensor, gen_len: int, cfg: BeamSearchConfig) -> Tensor:
-    """gen_len = number of tokens generated so far (0 at the first expansion)."""
+    """gen_len = number of tokens generated so far (0 at the first expansion) = step_nr - P."""
     lp = lprobs.clone()
-    lp[..., cfg.pad_idx] = -torch.inf
-    if cfg.unk_penalty:
-        lp[..., cfg.unk_idx] -= cfg.unk_penalty
-    if gen_len < cfg.min_gen_len:
-        lp[..., cfg.eos_idx] = -torch.inf
-    if gen_len >= cfg.max_gen_len - 1:  # last allowed token must be EOS
+    if gen_len >= cfg.max_gen_len - 1:  # step_nr == max_seq_len - 1: the last allowed token must be EOS
         eos = lp[..., cfg.eos_idx].clone()
         lp[...] = -torch.inf
         lp[..., cfg.eos_idx] = eos
+        return lp
+    lp[..., cfg.pad_idx] = -torch.inf
+    if cfg.unk_penalty:
+        lp[..., cfg.unk_idx] -= cfg.unk_penalty
+    if gen_len < cfg.min_gen_len - 1:  # step_nr < min_seq_len - 1
+        lp[..., cfg.eos_idx] = -torch.inf
     return lp
 
 
@@ -183,12 +200,17 @@ def beam_search(lprob_fn, prompt: Tensor, n: int, cfg: BeamSearchConfig) -> List
     ``prompt`` int64 [P] (SONAR target mode: [</s>, __lang__]).  Returns, per sentence, its finished hypotheses
     sorted best first as (score, generated tokens incl. the final EOS)."""
     beam = cfg.beam_size
+    P = prompt.numel()
     seqs = prompt[None, None, :].repeat(n, beam, 1)  # [N, beam, S]
     cum = torch.zeros(n, beam)
+    for p in range(1, P):  # _prefill: score of the prompt itself
+        lp = lprob_fn(seqs[:, :, :p].reshape(n * beam, -1)).reshape(n, beam, -1).float()
+        cum = cum + lp[:, :, int(prompt[p])]
     finished: List[List[Tuple[float, List[int]]]] = [[] for _ in range(n)]
     done = [False] * n
     alive = torch.ones(n, beam, dtype=torch.bool)
     for gen_len in range(cfg.max_gen_len):
+        step_nr = P + gen_len
         lp = lprob_fn(seqs.reshape(n * beam, -1)).reshape(n, beam, -1).float()
         lp = constrain_lprobs(lp, gen_len, cfg)
         lp = torch.where(alive[:, :, None], lp, torch.full_like(lp, -torch.inf))
@@ -207,9 +229,13 @@ def beam_search(lprob_fn, prompt: Tensor, n: int, cfg: BeamSearchConfig) -> List
                     break
                 b, t = int(cbeam[i, r]), int(ctok[i, r])
                 if t == cfg.eos_idx:
-                    if r < beam:  # only EOS candidates ranked inside the beam finalise a hypothesis
-                        toks = seqs[i, b, prompt.numel():].tolist() + [t]
-                        fs = s / (len(toks) ** cfg.len_penalty) if cfg.normalize_scores else s
+                    # only EOS candidates ranked inside the beam finish a hypothesis, and only until the sentence owns `beam`
+                    if r < beam and len(finished[i]) < beam:
+                        toks = seqs[i, b, P:].tolist() + [t]
+                        # IEEE float32 division, like the product (torch / CUDA)
+                        fs = float(torch.tensor(s, dtype=torch.float32) /
+                                   torch.tensor(float(step_nr) ** cfg.len_penalty, dtype=torch.float32)) \
+                            if cfg.normalize_scores else s
                         finished[i].append((fs, toks))
                     continue
                 if slot < beam:

@@ -116,7 +116,8 @@ _SIGNATURES = {
     "sb_decoder_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
                                    C.c_void_p]),
     "sb_decoder_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                  C.c_void_p]),
     "sb_decoder_check_inputs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sb_fbank_tables_bytes": (C.c_size_t, []),
     "sb_fbank_build_tables": (C.c_int, [C.c_void_p]),

@@ -37,7 +37,7 @@ struct BeamStepParams {
   int64_t* fin_seq;      // [N, CAP + 1, Tmax]
   int64_t* fin_len;      // [N, CAP + 1]
   int64_t* fin_count;    // [N]
-  int N, B, Tmax, t, g, min_gen, max_gen;
+  int N, B, Tmax, t, g, eos_block, max_gen;  // EOS is forbidden while g < eos_block (= min_gen_len - 1, [fs2] min_seq_len)
   long long vocab;
   int eos, unk, pad;
   float unk_penalty, score_div;
@@ -75,7 +75,7 @@ beam_step_kernel(const BeamStepParams p) {
     float v = p.lp[(size_t)r * kBeamCand + c];
     if (tk < 0 || tk == p.pad) v = -CUDART_INF_F;
     if (p.unk_penalty != 0.f && tk == p.unk) v = v - p.unk_penalty;
-    if (p.g < p.min_gen && tk == p.eos) v = -CUDART_INF_F;
+    if (p.g < p.eos_block && tk == p.eos) v = -CUDART_INF_F;
     if (p.g >= p.max_gen - 1) {  // the last allowed token must be EOS
       v = -CUDART_INF_F;
       if (c == 0) { v = p.eos_lp[r]; tk = p.eos; }
@@ -113,7 +113,7 @@ beam_step_kernel(const BeamStepParams p) {
       if (is_eos && j < B && !was_done) {  // finalise EOS candidates ranked inside the beam
         const long long pos = fcount + nfin;
         ++nfin;
-        if (pos < CAP) fin_dest[j] = (int)pos;
+        if (pos < B) fin_dest[j] = (int)pos;  // the sentence closes the moment it owns `beam` hypotheses [fs2 _search_beam]
       }
       if (valid && !is_eos && !was_done) {  // next beam: the first B non-EOS candidates
         if (nkeep < B) {
@@ -169,7 +169,7 @@ beam_step_kernel(const BeamStepParams p) {
 extern "C" int sb_beam_step(const float* lp, const int32_t* tok, const float* eos_lp, int64_t* seqs, int32_t* table,
                             int64_t* tokens, float* cum, uint8_t* alive, uint8_t* done, float* fin_score,
                             int64_t* fin_seq, int64_t* fin_len, int64_t* fin_count, int32_t N, int32_t B, int32_t Tmax,
-                            int32_t t, int32_t g, int32_t min_gen, int32_t max_gen, int64_t vocab, int32_t eos,
+                            int32_t t, int32_t g, int32_t eos_block, int32_t max_gen, int64_t vocab, int32_t eos,
                             int32_t unk, int32_t pad, float unk_penalty, float score_div, int32_t normalize,
                             void* stream) {
   using namespace sb;
@@ -183,7 +183,7 @@ extern "C" int sb_beam_step(const float* lp, const int32_t* tok, const float* eo
     return SB_ERR_INVALID;
   }
   BeamStepParams p{lp, tok, eos_lp, seqs, table, tokens, cum, alive, done, fin_score, fin_seq, fin_len, fin_count,
-                   N, B, Tmax, t, g, min_gen, max_gen, (long long)vocab, eos, unk, pad, unk_penalty, score_div, normalize};
+                   N, B, Tmax, t, g, eos_block, max_gen, (long long)vocab, eos, unk, pad, unk_penalty, score_div, normalize};
   const size_t smem = (size_t)B * Tmax * (sizeof(int64_t) + sizeof(int32_t));
   if (smem > 48 * 1024) {
     set_last_error("sb_beam_step: beam * max_seq_len too large for the staging buffer (%zu bytes)", smem);

@@ -237,7 +237,8 @@ __global__ void __launch_bounds__(256)
 vocab_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, const float* __restrict__ lse_part,
                    int n_chunks, const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ embed, int D,
                    int eos_idx, int R, float* __restrict__ out_lprob, int* __restrict__ out_tok,
-                   float* __restrict__ out_eos) {
+                   float* __restrict__ out_eos, const int64_t* __restrict__ probe_tokens, long long vocab,
+                   float* __restrict__ out_probe) {
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= R) return;
@@ -296,6 +297,20 @@ vocab_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ c
   }
   dot = warp_sum(dot);
   if (lane == 0) out_eos[r] = dot - lse;
+  // ---- log P(probe token): the prompt scores the generator's prefill accumulates ----
+  if (probe_tokens != nullptr) {
+    long long pt = probe_tokens[r];
+    if (pt < 0 || pt >= vocab) pt = 0;  // out-of-range ids are reported by decode_embed_kernel when they are fed back
+    const __nv_bfloat16* pr = embed + pt * (long long)D;
+    float pd = 0.f;
+    for (int q = lane * 2; q < D; q += 64) {
+      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(hr + q);
+      const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(pr + q);
+      pd += __low2float(a) * __low2float(b) + __high2float(a) * __high2float(b);
+    }
+    pd = warp_sum(pd);
+    if (lane == 0) out_probe[r] = pd - lse;
+  }
 }
 
 }  // namespace sb
@@ -484,12 +499,17 @@ int sb_decoder_begin(SbDecoder* d, const float* embeddings, int32_t N, int32_t b
 }
 
 int sb_decoder_step(SbDecoder* d, const int64_t* tokens, const int32_t* table, int32_t t, int32_t N, int32_t beam,
-                    int32_t max_len, float* out_lprob, int32_t* out_tok, float* out_eos_lprob, void* workspace,
-                    size_t workspace_bytes, void* stream_v) {
+                    int32_t max_len, float* out_lprob, int32_t* out_tok, float* out_eos_lprob,
+                    const int64_t* probe_tokens, float* out_probe_lprob, void* workspace, size_t workspace_bytes,
+                    void* stream_v) {
   DecWs w;
   int rc = check_ws(d, N, beam, max_len, workspace, workspace_bytes, &w);
   if (rc) return rc;
   if (!tokens || !table || !out_lprob || !out_tok || !out_eos_lprob) { set_last_error("sb_decoder_step: null pointer"); return SB_ERR_INVALID; }
+  if ((probe_tokens != nullptr) != (out_probe_lprob != nullptr)) {
+    set_last_error("sb_decoder_step: probe_tokens and out_probe_lprob go together");
+    return SB_ERR_INVALID;
+  }
   if (t < 0 || t >= max_len) { set_last_error("sb_decoder_step: position %d outside [0,%d)", t, max_len); return SB_ERR_INVALID; }
   if (max_len > kMaxDecodeLen) { set_last_error("sb_decoder_step: max_len %d > %d", max_len, kMaxDecodeLen); return SB_ERR_INVALID; }
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
@@ -545,7 +565,7 @@ int sb_decoder_step(SbDecoder* d, const int64_t* tokens, const int32_t* table, i
     return rc;
   vocab_merge_kernel<kTopkCandidates><<<row_blocks, 256, 0, stream>>>(
       w.cand_val, w.cand_idx, w.lse_part, w.n_chunks, w.h, reinterpret_cast<const __nv_bfloat16*>(d->embed), D,
-      d->cfg.eos_idx, R, out_lprob, out_tok, out_eos_lprob);
+      d->cfg.eos_idx, R, out_lprob, out_tok, out_eos_lprob, probe_tokens, (long long)d->cfg.vocab_size, out_probe_lprob);
   SB_CUDA_CHECK(cudaGetLastError());
   return SB_OK;
 }

@@ -114,8 +114,13 @@ class BeamSearchSeq2SeqGenerator:
         oracle).  ``None`` = on for CUDA models unless ``SONAR_B200_FUSED_BEAM=0``."""
         if beam_size < 1:
             raise ValueError("`beam_size` must be greater than or equal to 1")
-        if 2 * beam_size > TOPK:
-            raise ValueError(f"`beam_size` must be <= {TOPK // 2 - 1} (the decoder step returns the top-{TOPK} tokens per row)")
+        # the decoder step returns the TOPK best tokens per row BEFORE the generator masks PAD, masks EOS (min length) and
+        # demotes UNK: the exact 2*beam best of the constrained distribution lie inside the raw top 2*beam + (#tokens touched)
+        need = 2 * beam_size + 2 + (1 if unk_penalty != 0.0 else 0)
+        if need > TOPK:
+            raise ValueError(f"`beam_size` must be <= {(TOPK - 2 - (1 if unk_penalty != 0.0 else 0)) // 2} "
+                             f"(the decoder step returns the top-{TOPK} tokens per row; 2*beam_size + {need - 2 * beam_size} "
+                             f"of them are needed{' with an UNK penalty' if unk_penalty != 0.0 else ''})")
         if min_gen_len < 1:
             raise ValueError("`min_gen_len` must be greater than or equal to 1")
         if temperature != 1.0:
@@ -135,7 +140,10 @@ class BeamSearchSeq2SeqGenerator:
         self.fused_beam_step = fused_beam_step
 
     def _advance(self, st: _DecodeState, g: int, P: int, min_gen: int, max_gen: int) -> None:
-        """One decode step: position t = P-1+g of every live hypothesis -> the next beam, all state updated in place."""
+        """One decode step: position t = P-1+g of every live hypothesis -> the next beam, all state updated in place.
+        fairseq2 names [fs2]: ``step_nr = P + g`` is the absolute index of the token being generated; EOS is forbidden while
+        ``step_nr < min_seq_len - 1`` (``min_seq_len = P + min_gen``), forced when ``step_nr == max_seq_len - 1``; a finished
+        hypothesis scores ``cum / step_nr ** len_penalty`` (``seq_len - 1``: prompt and EOS counted, first step excluded)."""
         m = self.model
         vi = m.target_vocab_info
         eos, unk, pad, V = vi.eos_idx, vi.unk_idx, self.pad_idx, vi.size
@@ -148,13 +156,13 @@ class BeamSearchSeq2SeqGenerator:
         if fused is None:
             fused = os.environ.get("SONAR_B200_FUSED_BEAM", "1") != "0"
         if fused and dev.type == "cuda" and B <= 7 and TOPK == 16:
-            div = float(g + 1) ** self.len_penalty
+            div = float(P + g) ** self.len_penalty
             with torch.cuda.device(dev):
                 rc = m._lib.sb_beam_step(
                     lp.data_ptr(), tok.data_ptr(), eos_lp.data_ptr(), st.seqs.data_ptr(), st.table.data_ptr(),
                     st.tokens.data_ptr(), st.cum.data_ptr(), st.alive.data_ptr(), st.done.data_ptr(),
                     st.fin_score.data_ptr(), st.fin_seq.data_ptr(), st.fin_len.data_ptr(), st.fin_count.data_ptr(),
-                    N, B, Tmax, t, g, min_gen, max_gen, V, eos, unk, pad, float(self.unk_penalty), div,
+                    N, B, Tmax, t, g, min_gen - 1, max_gen, V, eos, unk, pad, float(self.unk_penalty), div,
                     1 if self.normalize_scores else 0, torch.cuda.current_stream(dev).cuda_stream)
             _lib.check(rc, "sb_beam_step")
             return
@@ -163,7 +171,7 @@ class BeamSearchSeq2SeqGenerator:
         lp = lp.masked_fill((tok < 0) | (tok == pad), NEG_INF)
         if self.unk_penalty:
             lp = torch.where(tok == unk, lp - self.unk_penalty, lp)
-        if g < min_gen:
+        if g < min_gen - 1:
             lp = lp.masked_fill(tok == eos, NEG_INF)
         if g >= max_gen - 1:  # the last allowed token must be EOS
             lp = torch.full_like(lp, NEG_INF)
@@ -180,12 +188,11 @@ class BeamSearchSeq2SeqGenerator:
         # ---- finalise EOS candidates ranked inside the beam ----
         fin_mask = is_eos & (st.rank < B) & ~st.done[:, None]
         fin_pos = st.fin_count[:, None] + torch.cumsum(fin_mask, 1) - 1
-        fin_ok = fin_mask & (fin_pos < CAP)
+        fin_ok = fin_mask & (fin_pos < B)  # the sentence closes the moment it owns `beam` hypotheses
         dest = torch.where(fin_ok, fin_pos, torch.full_like(fin_pos, CAP))
-        gen_len = g + 1
         # divisor as a 0-dim tensor: IEEE division on every device (a Python-scalar divisor becomes a multiplication by the
         # reciprocal in torch's CUDA kernel, one ulp away from the CPU result and from sb_beam_step)
-        fscore = c_score / torch.full((), float(gen_len) ** self.len_penalty, dtype=torch.float32, device=dev) \
+        fscore = c_score / torch.full((), float(P + g) ** self.len_penalty, dtype=torch.float32, device=dev) \
             if self.normalize_scores else c_score
         st.fin_score.scatter_(1, dest, torch.where(fin_ok, fscore, torch.full_like(fscore, NEG_INF)))
         cand_seqs = torch.gather(st.seqs, 1, c_beam[:, :, None].expand(N, 2 * B, Tmax)).clone()
@@ -273,9 +280,13 @@ class BeamSearchSeq2SeqGenerator:
             st = _DecodeState(N, B, Tmax, dev)
         st.reset(prompt, self.pad_idx)
 
-        # prefill: every prompt position but the last only feeds the KV cache
+        # prefill [fs2 `_prefill`]: every prompt position but the last feeds the KV cache, and the log-prob of the NEXT prompt
+        # token given the prefix seeds the hypothesis scores (a per-sentence constant that still matters once scores of
+        # different lengths are normalised)
         for p in range(P - 1):
-            m.step(st.seqs[:, :, p].reshape(R).contiguous(), st.table, p)
+            probe = st.seqs[:, :, p + 1].reshape(R).contiguous()
+            out = m.step(st.seqs[:, :, p].reshape(R).contiguous(), st.table, p, probe)
+            st.cum.add_(out[3].view(N, B))
         st.tokens.copy_(st.seqs[:, :, P - 1].reshape(R))
         for g in range(max_gen):
             if ent is None:

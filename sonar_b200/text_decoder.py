@@ -204,9 +204,10 @@ class B200TextDecoderModel(torch.nn.Module):
         _lib.check(rc, "sb_decoder_begin")
 
     @torch.inference_mode()
-    def step(self, tokens: Tensor, table: Tensor, t: int) -> Tuple[Tensor, Tensor, Tensor]:
+    def step(self, tokens: Tensor, table: Tensor, t: int, probe: Optional[Tensor] = None):
         """tokens int64 [R] at position t, ancestry table int32 [R, max_len] ->
-        (top-16 log-probs [R,16], their token ids int32 [R,16], log P(eos) [R])."""
+        (top-16 log-probs [R,16], their token ids int32 [R,16], log P(eos) [R]) and, when ``probe`` (int64 [R]) is given,
+        a fourth tensor log P(probe[r]) [R]."""
         n, beam, max_len = self._shape
         r = n * beam
         assert tokens.shape == (r,) and tokens.dtype == torch.int64 and tokens.is_cuda and tokens.is_contiguous()
@@ -214,12 +215,18 @@ class B200TextDecoderModel(torch.nn.Module):
         lp = torch.empty((r, TOPK), dtype=torch.float32, device=self.device)
         tok = torch.empty((r, TOPK), dtype=torch.int32, device=self.device)
         eos = torch.empty((r,), dtype=torch.float32, device=self.device)
+        probe_lp = None
+        if probe is not None:
+            assert probe.shape == (r,) and probe.dtype == torch.int64 and probe.is_cuda and probe.is_contiguous()
+            probe_lp = torch.empty((r,), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             rc = self._lib.sb_decoder_step(self._handle, tokens.data_ptr(), table.data_ptr(), t, n, beam, max_len,
-                                           lp.data_ptr(), tok.data_ptr(), eos.data_ptr(), self._workspace.data_ptr(),
-                                           self._workspace.numel(), self._stream())
+                                           lp.data_ptr(), tok.data_ptr(), eos.data_ptr(),
+                                           probe.data_ptr() if probe is not None else None,
+                                           probe_lp.data_ptr() if probe_lp is not None else None,
+                                           self._workspace.data_ptr(), self._workspace.numel(), self._stream())
         _lib.check(rc, "sb_decoder_step")
-        return lp, tok, eos
+        return (lp, tok, eos) if probe is None else (lp, tok, eos, probe_lp)
 
     def check_inputs(self) -> None:
         if self._workspace is not None:

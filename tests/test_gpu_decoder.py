@@ -47,9 +47,11 @@ def test_teacher_forced_steps_match_oracle(small, cuda_device, n, beam, steps):
     table = torch.arange(r, dtype=torch.int32, device=cuda_device)[:, None].expand(r, 16).contiguous()
     enc_rows = emb[:, None, :].repeat_interleave(beam, 0)
     for t in range(steps):
-        lp, tok, eos_lp = model.step(toks[:, t].contiguous().to(cuda_device), table, t)
+        probe = toks[:, (t + 1) % steps].contiguous()  # log P of an arbitrary token per row (the generator's prompt scores)
+        lp, tok, eos_lp, probe_lp = model.step(toks[:, t].contiguous().to(cuda_device), table, t, probe.to(cuda_device))
         ref = oracle.step_lprobs(toks[:, : t + 1], enc_rows)  # [R, V] fp32
         lp, tok, eos_lp = lp.cpu(), tok.cpu().long(), eos_lp.cpu()
+        torch.testing.assert_close(probe_lp.cpu(), torch.gather(ref, 1, probe[:, None])[:, 0], rtol=2e-3, atol=2e-2)
         # the returned candidates carry the right log-probs ...
         torch.testing.assert_close(lp, torch.gather(ref, 1, tok), rtol=2e-3, atol=2e-2)
         torch.testing.assert_close(eos_lp, ref[:, 3], rtol=2e-3, atol=2e-2)
@@ -103,7 +105,8 @@ def test_generation_is_near_optimal_and_scores_are_honest(small, cuda_device):
         for h in hyps:  # reported score == oracle score of that very sequence (teacher forced), within bf16 tolerance
             seq = torch.cat([prompt, h.seq])
             lps = torch.log_softmax(oracle.logits(seq[None, :-1], enc1[i : i + 1])[0].float(), -1)
-            s = sum(float(lps[p, seq[p + 1]]) for p in range(len(prompt) - 1, len(seq) - 1)) / len(h.seq)
+            # fairseq2 scoring: prompt log-prob included, normalised by seq_len - 1 (prompt and EOS counted)
+            s = sum(float(lps[p, seq[p + 1]]) for p in range(len(seq) - 1)) / (len(seq) - 1)
             assert abs(s - h.score) <= 2e-2 + 2e-3 * abs(s), (i, s, h.score)
         assert hyps[0].score >= ref[i][0][0] - (5e-2 + 4e-3 * abs(ref[i][0][0]))  # as good as the oracle's best hypothesis
         exact += int(hyps[0].seq.tolist() == ref[i][0][1])

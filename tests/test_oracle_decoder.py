@@ -60,19 +60,23 @@ class _OracleBackedModel:
         self.enc = emb.reshape(emb.shape[0], 1, -1).repeat_interleave(beam, 0)
         self.hist = {}
 
-    def step(self, tokens, table, t):
+    def step(self, tokens, table, t, probe=None):
         self.hist[t] = tokens.clone()
         r = tokens.shape[0]
         seq = torch.stack([self.hist[tp][table[:, tp].long()] for tp in range(t)] + [tokens], 1) if t > 0 else tokens[:, None]
         lp = self.dec.step_lprobs(seq, self.enc)
         order = torch.argsort(-lp, dim=1, stable=True)[:, :16]  # value desc, token asc
-        return torch.gather(lp, 1, order), order.to(torch.int32), lp[:, self.target_vocab_info.eos_idx].clone()
+        out = (torch.gather(lp, 1, order), order.to(torch.int32), lp[:, self.target_vocab_info.eos_idx].clone())
+        if probe is not None:
+            out = out + (torch.gather(lp, 1, probe[:, None])[:, 0],)
+        return out
 
     def check_inputs(self):
         pass
 
 
-@pytest.mark.parametrize("beam,min_len,max_len,unk_pen", [(1, 1, 6, 0.0), (3, 1, 7, 0.0), (5, 2, 9, 0.5), (4, 1, 3, 0.0)])
+@pytest.mark.parametrize("beam,min_len,max_len,unk_pen", [(1, 1, 6, 0.0), (3, 1, 7, 0.0), (5, 2, 9, 0.5), (4, 1, 3, 0.0),
+                                                          (5, 3, 12, 0.0), (7, 1, 8, 0.0)])
 def test_product_beam_search_equals_oracle(beam, min_len, max_len, unk_pen):
     torch.manual_seed(0)
     v = 40
@@ -108,6 +112,43 @@ def test_generator_argument_validation():
     with pytest.raises(ValueError):
         BeamSearchSeq2SeqGenerator(M(), beam_size=0)
     with pytest.raises(ValueError):
-        BeamSearchSeq2SeqGenerator(M(), beam_size=9)  # 2*beam must fit the 16 candidates per row
+        BeamSearchSeq2SeqGenerator(M(), beam_size=8)  # 2*beam + PAD + EOS must fit the 16 candidates per row
+    BeamSearchSeq2SeqGenerator(M(), beam_size=7)
+    with pytest.raises(ValueError):
+        BeamSearchSeq2SeqGenerator(M(), beam_size=7, unk_penalty=0.5)  # a demoted UNK needs one more candidate
     with pytest.raises(ValueError):
         BeamSearchSeq2SeqGenerator(M(), min_gen_len=0)
+
+
+def test_beam_search_follows_fairseq2_scoring_rules():
+    """Known-answer case for the four fairseq2 rules the round-1 restatement had wrong: the prompt's own
+    log-prob seeds the scores, an immediate EOS is legal with min_gen_len=1, a finished hypothesis is normalised by
+    step_nr = P + g (prompt and EOS counted, first step excluded), and a sentence closes at exactly `beam` hypotheses."""
+    v, eos = 6, 3
+    ln = math.log
+
+    def lprob_fn(tokens):  # next-token distribution depends on (length, last token) only
+        out = torch.full((tokens.shape[0], v), -30.0)
+        for r in range(tokens.shape[0]):
+            s, last = tokens.shape[1], int(tokens[r, -1])
+            if s == 1:      # after [</s>]: the prompt token 4 has probability 0.5
+                out[r, 4], out[r, 5] = ln(0.5), ln(0.5)
+            elif s == 2:    # first generated token
+                out[r, eos], out[r, 5], out[r, 4] = ln(0.6), ln(0.3), ln(0.1)
+            else:           # afterwards: EOS almost surely after a 5, rarely after a 4
+                out[r, eos], out[r, 4] = (ln(0.9), ln(0.1)) if last == 5 else (ln(0.2), ln(0.8))
+        return out
+
+    cfg = BeamSearchConfig(beam_size=2, min_gen_len=1, max_gen_len=6, pad_idx=0, unk_idx=1, eos_idx=eos)
+    (hyps,) = beam_search(lprob_fn, torch.tensor([3, 4]), 1, cfg)
+    c = ln(0.5)  # score of the prompt
+    # step_nr 2: EOS is rank 0 -> finished at once with (c + ln .6) / 2; beam continues with [5] and [4]
+    # step_nr 3: candidates [5,eos] c+ln(.3*.9), [4,4] c+ln(.1*.8), [5,4] c+ln(.3*.1), [4,eos] c+ln(.1*.2):
+    #            [5,eos] is rank 0 -> second hypothesis, (c + ln .27) / 3; the sentence closes at beam=2 hypotheses
+    assert [h[1] for h in hyps] == [[eos], [5, eos]]
+    assert hyps[0][0] == pytest.approx((c + ln(0.6)) / 2, rel=1e-6)
+    assert hyps[1][0] == pytest.approx((c + ln(0.27)) / 3, rel=1e-6)
+    # min_gen_len=2 forbids the immediate EOS (step_nr 2 < min_seq_len - 1 = 3)
+    cfg2 = BeamSearchConfig(beam_size=2, min_gen_len=2, max_gen_len=6, pad_idx=0, unk_idx=1, eos_idx=eos)
+    (h2,) = beam_search(lprob_fn, torch.tensor([3, 4]), 1, cfg2)
+    assert all(len(t) >= 2 for _, t in h2) and h2[0][1] == [5, eos]
