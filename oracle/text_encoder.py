@@ -21,7 +21,7 @@ checkpoint + SentencePiece model, which do not exist offline, and fairseq2
 cannot be imported here, so against the *reference itself* this oracle is
 "parity unpinned".  It IS pinned (a) by the reference's pooling known-answer
 tests (``tests/unit_tests/test_sonar_pooling.py:16-68``, restated in
-``tests/test_oracle_pooling.py``) and (b) against an independent implementation
+``tests/test_oracle.py``) and (b) against an independent implementation
 of the same network, HuggingFace ``M2M100Encoder`` -- the port the reference's
 own notebook uses as *the* SONAR text encoder
 (``examples/finetune_sonar_as_toxicity_classifier.ipynb`` cells 0/50/53) -- via

@@ -40,6 +40,18 @@ elif which == "layernorm":
     gg, bb = torch.ones(D, device=dev), torch.zeros(D, device=dev)
     for _ in range(4):
         ops.layernorm(x, gg, bb)
+elif which == "fbank":   # 256 x 10 s waveforms -> 80-bin fbank + standardise (BASELINE config 3 frontend)
+    from sonar_b200.speech_frontend import WaveformToFbank
+    conv = WaveformToFbank(dev)
+    waves = [(torch.randn(160000, device=dev, generator=g) * 0.05).clamp(-1, 1) for _ in range(256)]
+    for _ in range(3):
+        conv(waves)
+elif which == "xsim":    # k-NN of 65536 x 65536 (normalise, tcgen05 GEMM + running top-16, fp64 re-rank)
+    from sonar_b200 import xsim
+    y = torch.randn((65536, 1024), device=dev, generator=g)
+    x = y + 0.1 * torch.randn((65536, 1024), device=dev, generator=g)
+    for _ in range(3):
+        xsim.knn(x, y, 4)
 elif which == "speech":  # one full speech-encoder forward (64 x 10 s), for a launch list
     from oracle.speech_encoder import OracleSpeechConfig, make_synthetic_speech_state_dict
     from sonar_b200 import B200SpeechEncoderModel, PaddingMask, SequenceBatch, sonar_speech_encoder_config

@@ -51,13 +51,10 @@ def encode_sharded(predict: Callable[[Sequence[str]], Tensor], sentences: Sequen
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     s, e = shard_bounds(len(sentences), world, rank)
     local = predict(list(sentences[s:e])) if e > s else None
-    if local is None:  # empty shard: need the feature width from somewhere
-        width = torch.zeros(1, dtype=torch.int64)
-        dist.all_reduce(width, op=dist.ReduceOp.MAX, group=group)
-        local = torch.zeros((0, int(width.item())), dtype=torch.float32)
-    else:
-        width = torch.tensor([local.shape[1]], dtype=torch.int64, device="cpu")
-        if dist.get_backend(group) == "nccl":
-            width = width.to(local.device)
-        dist.all_reduce(width, op=dist.ReduceOp.MAX, group=group)
+    # collectives run on the rank's CUDA device under NCCL (also for a rank whose shard is empty), on CPU under gloo
+    coll_dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    width = torch.tensor([local.shape[1] if local is not None else 0], dtype=torch.int64, device=coll_dev)
+    dist.all_reduce(width, op=dist.ReduceOp.MAX, group=group)
+    if local is None:  # empty shard: the feature width comes from the other ranks
+        local = torch.zeros((0, int(width.item())), dtype=torch.float32, device=coll_dev)
     return gather_rows(local, len(sentences), group)

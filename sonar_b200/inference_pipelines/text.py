@@ -171,6 +171,11 @@ class TextToEmbeddingModelPipeline(torch.nn.Module):
 
         with precision_context(self.model.dtype):
             results: List[Tensor] = list(iter(pipeline))
+        # the reference's F.embedding raises on an id outside the table; the engine records it in a device flag --
+        # surface it once per call (one 4-byte D2H) so a tokenizer / vocabulary mismatch cannot pass silently
+        check = getattr(self.model, "check_inputs", None)
+        if check is not None:
+            check()
 
         if n_truncated:
             warnings.warn(

@@ -73,21 +73,13 @@ def xsim(x: Tensor, y: Tensor, margin: str = "ratio", k: int = 4) -> Tuple[int, 
     return err, n, pred
 
 
-def xsim_distributed(x_shard: Tensor, y_shard: Tensor, margin: str = "ratio", k: int = 4, group=None,
-                     _knn=None, _margin_predict=None):
-    """Every rank holds the same number of rows of x and y (its batch shard of the encoded sentences).
-    -> (global errors, global n, predictions for this rank's rows as GLOBAL y indices).
-
-    ``_knn`` / ``_margin_predict`` exist only so the collective plumbing can be exercised under ``gloo`` on a
-    machine without a GPU (tests inject a checker there); the product path always uses the CUDA kernels."""
+def _xsim_distributed_impl(x_shard: Tensor, y_shard: Tensor, margin: str, k: int, group, knn_fn, margin_fn):
+    """Collective plumbing of ``xsim_distributed`` with the two compute steps passed in as callables (the gloo test in
+    ``tests/test_distributed_gloo.py`` drives it with a CPU checker; the public function below binds the CUDA kernels)."""
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    if _knn is None:
-        x_shard, y_shard = _need_cuda_f32(x_shard), _need_cuda_f32(y_shard)
-    knn_fn = _knn or knn
-    margin_fn = _margin_predict or margin_predict
     ns, d = x_shard.shape
     x_all = torch.empty((world * ns, d), dtype=torch.float32, device=x_shard.device)
     y_all = torch.empty((world * ns, d), dtype=torch.float32, device=x_shard.device)
@@ -104,3 +96,12 @@ def xsim_distributed(x_shard: Tensor, y_shard: Tensor, margin: str = "ratio", k:
     err = (pred.long() != target).sum()
     dist.all_reduce(err, group=group)
     return int(err.item()), world * ns, pred
+
+
+def xsim_distributed(x_shard: Tensor, y_shard: Tensor, margin: str = "ratio", k: int = 4, group=None):
+    """Every rank holds the same number of rows of x and y (its batch shard of the encoded sentences).
+    -> (global errors, global n, predictions for this rank's rows as GLOBAL y indices).  CUDA tensors only."""
+    if margin not in _MARGINS:
+        raise ValueError(f"margin must be one of {sorted(_MARGINS)}")
+    x_shard, y_shard = _need_cuda_f32(x_shard), _need_cuda_f32(y_shard)
+    return _xsim_distributed_impl(x_shard, y_shard, margin, k, group, knn, margin_predict)

@@ -53,7 +53,7 @@ def _worker(rank, world, port, results):
 
         # --- xsim_distributed plumbing, oracle injected as the k-NN / margin checker ---
         from oracle import xsim as ox
-        from sonar_b200.xsim import xsim_distributed
+        from sonar_b200.xsim import _xsim_distributed_impl, xsim_distributed
 
         g = torch.Generator().manual_seed(3)
         y = torch.randn((64, 32), generator=g)
@@ -74,10 +74,15 @@ def _worker(rank, world, port, results):
         ns = 64 // world
         sl = slice(rank * ns, (rank + 1) * ns)
         for margin in ("ratio", "distance", "absolute"):
-            err, n_tot, pred = xsim_distributed(x[sl], y[sl], margin=margin, k=4, _knn=knn_cpu, _margin_predict=margin_cpu)
+            err, n_tot, pred = _xsim_distributed_impl(x[sl], y[sl], margin, 4, None, knn_cpu, margin_cpu)
             ref_err, ref_n, ref_pred = ox.xsim(x.numpy(), y.numpy(), margin=margin, k=4)
             assert n_tot == ref_n and err == ref_err, (margin, err, ref_err)
             assert np.array_equal(pred.numpy(), ref_pred[sl])
+        with pytest.raises(RuntimeError, match="CUDA"):  # the public function has no CPU path and no injection seam
+            xsim_distributed(x[sl], y[sl])
+        # --- more ranks than sentences: the empty shard must still take part in every collective ---
+        one = encode_sharded(fake_predict, sents[:1])
+        assert torch.equal(one, fake_predict(sents[:1]))
         results[rank] = "ok"
     finally:
         dist.destroy_process_group()
