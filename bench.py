@@ -603,6 +603,8 @@ def main():
     ap.add_argument("--seq-len", type=int, default=SEQ)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--cta-group", type=int, default=2)
+    ap.add_argument("--ln-fold", type=int, default=1, choices=[0, 1],
+                    help="1 = LayerNorm folded into the GEMMs (default schedule), 0 = separate LayerNorm kernels")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-secondary", action="store_true", help="N=1: skip the predict / speech / decoder / xsim blocks")
     ap.add_argument("--only", default="", help="N=1: comma list of secondary blocks to run (predict,speech,decoder,xsim)")
@@ -636,7 +638,12 @@ def main():
 
     B, S = args.batch, args.seq_len
     sd = synthetic_state_dict(dev)
-    model = B200TextEncoderModel(sonar_text_encoder_config("basic"), sd, dev, cta_group=args.cta_group)
+    model = B200TextEncoderModel(sonar_text_encoder_config("basic"), sd, dev, cta_group=args.cta_group,
+                                 ln_fold=bool(args.ln_fold))
+    model_alt = None
+    if rank == 0 and world == 1 and not args.skip_secondary:  # same-box A/B of the other LayerNorm schedule
+        model_alt = B200TextEncoderModel(sonar_text_encoder_config("basic"), sd, dev, cta_group=args.cta_group,
+                                         ln_fold=not bool(args.ln_fold))
     sd_cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         sd_cpu = {k: v.cpu() for k, v in sd.items()}
@@ -756,6 +763,34 @@ def main():
                     "whole_step_frac": (value / world) * flops_per_sentence(S) / 1e12 / peak}
         del a, f
 
+    # ---- same-box A/B: the other LayerNorm schedule, alternating 3-step blocks so clock drift hits both alike ----
+    ab = None
+    if model_alt is not None and (B, S) == (BATCH, SEQ):
+        def run_n(m, k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(k):
+                m(batch_dev)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / k
+
+        run_n(model_alt, 2)
+        t_main, t_alt = [], []
+        for _ in range(2):
+            t_main.append(run_n(model, 3))
+            t_alt.append(run_n(model_alt, 3))
+        got_a = model(batch_dev).sentence_embeddings[:256].double()
+        got_b = model_alt(batch_dev).sentence_embeddings[:256].double()
+        rel = float(((got_a - got_b).norm(dim=1) / got_b.norm(dim=1)).max())
+        name = {True: "ln_folded", False: "ln_separate"}
+        ab = {name[bool(args.ln_fold)] + "_ms": t_main, name[not bool(args.ln_fold)] + "_ms": t_alt,
+              "sentences_per_s": {name[bool(args.ln_fold)]: B / (sum(t_main) / len(t_main)) * 1e3,
+                                  name[not bool(args.ln_fold)]: B / (sum(t_alt) / len(t_alt)) * 1e3},
+              "rel_l2_between_schedules_max": rel}
+        model_alt = None
+        torch.cuda.empty_cache()
+
     # ---- ragged variant: lengths U{16..128}; the engine packs tokens, the reference would pad to 128 ----
     ragged = None
     if rank == 0 and world == 1 and (B, S) == (BATCH, SEQ):
@@ -826,7 +861,7 @@ def main():
             torch.cuda.empty_cache()
 
     if rank == 0:
-        launches_per_step = 1 + LAYERS * 7 + 1
+        launches_per_step = 1 + LAYERS * (5 if args.ln_fold else 7) + 1  # embed, per layer 4 GEMMs + attention (+ 2 LN), pool
         line = {
             "metric": "sentences/sec->1024-d", "value": value, "unit": "sentences/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -836,7 +871,9 @@ def main():
                                    f"batch {B} x seq_len {S} per GPU, random-init weights, synthetic ids",
                        "l2": "inputs larger than L2 (per-step activations ~15 GB vs 126 MB L2)",
                        "parallelism": f"dp{world}" + (" + all_gather of embeddings" if world > 1 else ""),
-                       "cta_group": args.cta_group},
+                       "cta_group": args.cta_group,
+                       "layernorm": "folded into the QKV / FFN1 GEMMs (statistics from the residual GEMMs' epilogues)"
+                                    if args.ln_fold else "separate kernels"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "sentences/s", "h2d_bytes_per_step": B * S * 8,
                     "d2h_bytes_per_step": B * D * 4, "ms_per_step": e2e_ms / args.steps},
@@ -844,6 +881,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "ragged": ragged,
+            "ab_layernorm_schedule": ab,
             **extra,
         }
         if config5 is not None:

@@ -69,6 +69,11 @@ typedef struct SbEncoderConfig {
   float embed_scale;     /* sqrt(model_dim) unless no_scale_embedding */
   int32_t cta_group;     /* 0/2 = paired-CTA tcgen05 tiles (default), 1 = single-CTA */
   int32_t num_sms;       /* 0 = query the device */
+  int32_t ln_fold;       /* 1 = fold every encoder-layer LayerNorm into the GEMMs around it (no LayerNorm kernel runs:
+                          *     the residual GEMMs emit per-row statistics + a bf16 copy of the stream, the QKV / FFN1 GEMMs
+                          *     apply (mean, rstd) in their epilogue on weights pre-multiplied by gamma; sb_encoder_create
+                          *     prepares those weights in device memory it owns -- the caller's weights are not modified);
+                          * 0 = separate LayerNorm kernels (the round-1 schedule) */
 } SbEncoderConfig;
 
 /* All pointers are DEVICE pointers and stay owned by the caller (must outlive the handle).
@@ -99,6 +104,8 @@ typedef struct SbEncoderWeights {
 const char* sb_last_error(void);
 int sb_version(void);
 
+/* Allocates the handle's own device memory (a 256-byte input-check flag; with cfg->ln_fold the folded copies of the QKV and
+ * FFN inner-projection weights, ~22 MB per layer) and synchronises the device once.  sb_encoder_forward never allocates. */
 int sb_encoder_create(const SbEncoderConfig* cfg, const SbEncoderWeights* w, SbEncoder** out);
 void sb_encoder_destroy(SbEncoder* enc);
 
@@ -135,6 +142,22 @@ int sb_encoder_check_inputs(SbEncoder* enc, void* workspace, void* stream);
 
 /* ---- individual kernels (used by the parity tests and the micro-benchmarks) ---- */
 
+/* LayerNorm folding (the schedule behind SbEncoderConfig.ln_fold; replaces F.layer_norm + F.linear pairs of the pre-LN
+ * encoder layer, sonar/models/sonar_text/factory.py:122-153):
+ *   LN(x; gamma, beta) . W^T + b  =  rstd * (x . Wf^T - mean * colsum) + bias_f
+ * sb_fold_layernorm prepares Wf = bf16(W diag(gamma)) [N,K], colsum[n] = sum_k Wf[n,k], bias_f = bias + W beta;
+ * sb_gemm_residual_stats computes x += A . W^T + bias (fp32, in place) and emits h_out = bf16(x) plus stats_out
+ *   [M, N/256, 2] = (mean, M2) of every 256-column chunk of the new rows;
+ * sb_gemm_ln_consumer computes C (bf16) = [relu](rstd * (A . Wf^T - mean * colsum) + bias_f) with A = the bf16 copy and
+ *   (mean, rstd) merged from `stats` [M, K/256, 2].  K = 256, 512, 768 or 1024. */
+int sb_fold_layernorm(const void* W, const float* bias, const float* gamma, const float* beta, int32_t N, int32_t K,
+                      void* Wf, float* colsum, float* bias_f, void* stream);
+int sb_gemm_ln_consumer(const void* A, int64_t lda, const void* Wf, int64_t ldw, void* C, int64_t ldc, const float* bias_f,
+                        const float* colsum, const float* stats, float eps, int32_t M, int32_t N, int32_t K, int32_t relu,
+                        void* stream);
+int sb_gemm_residual_stats(const void* A, int64_t lda, const void* W, int64_t ldw, float* x, int64_t ldx, const float* bias,
+                           void* h_out, int64_t ldh, float* stats_out, int32_t M, int32_t N, int32_t K, void* stream);
+
 /* C[M,N] = epi(A[M,K] * W[N,K]^T + bias[N]) ; A, W bf16 row-major; C bf16 (out_fp32=0) or fp32;
  * residual (SB_EPI_BIAS_RESIDUAL) has C's dtype and may alias C.  N % 256 == 0, K % 64 == 0.
  * cta_group: 2 = paired-CTA tcgen05 tiles, 1 = single-CTA tiles, 0 = automatic (paired tiles, except that M <= 64 with
@@ -148,7 +171,8 @@ int sb_layernorm(const float* x, const float* gamma, const float* beta, float ep
                  void* stream);
 
 /* packed self-attention: qkv bf16 [total_tokens, 3*64*H], cu_seqlens DEVICE int32 [B+1], out bf16 [total_tokens, 64*H].
- * impl 0 = auto (tcgen05 kernel when max_len <= 128, mma.sync flash kernel otherwise), 1 = mma.sync, 2 = tcgen05. */
+ * impl 0 = auto (= 2), 1 = mma.sync flash kernel (kept for tests / A-B timing), 2 = tcgen05 (any length; 128-key
+ * tiles with online softmax beyond 128 tokens). */
 int sb_attention(const void* qkv, const int32_t* cu_seqlens, int32_t B, int32_t max_len, int32_t H,
                  int64_t total_tokens, int32_t impl, void* out, void* stream);
 

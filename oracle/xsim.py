@@ -23,8 +23,18 @@ def topk_desc(sim: np.ndarray, k: int):
     """Row-wise top-k of a dense similarity block: (values, indices), sorted by (value desc, index asc)."""
     n, m = sim.shape
     k = min(k, m)
-    # stable argsort on -sim gives value-descending with index-ascending tie-break
-    idx = np.argsort(-sim, axis=1, kind="stable")[:, :k]
+    if m <= 4 * k:
+        # stable argsort on -sim gives value-descending with index-ascending tie-break
+        idx = np.argsort(-sim, axis=1, kind="stable")[:, :k]
+        return np.take_along_axis(sim, idx, axis=1), idx
+    # same result without sorting whole rows: every entry >= the row's k-th largest value survives (ties included), then the
+    # survivors are ordered by (value desc, index asc)
+    kth = np.partition(sim, m - k, axis=1)[:, m - k]
+    idx = np.empty((n, k), dtype=np.int64)
+    for r in range(n):
+        cand = np.flatnonzero(sim[r] >= kth[r])  # ascending indices
+        order = np.argsort(-sim[r, cand], kind="stable")[:k]
+        idx[r] = cand[order]
     val = np.take_along_axis(sim, idx, axis=1)
     return val, idx
 

@@ -23,7 +23,7 @@ class SbEncoderConfig(C.Structure):
         ("model_dim", C.c_int32), ("num_layers", C.c_int32), ("num_heads", C.c_int32),
         ("ffn_inner_dim", C.c_int32), ("vocab_size", C.c_int64), ("pos_rows", C.c_int32),
         ("pooling", C.c_int32), ("ln_eps", C.c_float), ("embed_scale", C.c_float),
-        ("cta_group", C.c_int32), ("num_sms", C.c_int32),
+        ("cta_group", C.c_int32), ("num_sms", C.c_int32), ("ln_fold", C.c_int32),
     ]
 
 
@@ -134,6 +134,12 @@ _SIGNATURES = {
                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sb_xsim_margin_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.c_void_p, C.c_void_p]),
+    "sb_fold_layernorm": (C.c_int, [C.c_void_p] * 4 + [C.c_int32, C.c_int32] + [C.c_void_p] * 4),
+    "sb_gemm_ln_consumer": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_void_p]),
+    "sb_gemm_residual_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                         C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "sb_beam_step": (C.c_int, [C.c_void_p] * 13 + [C.c_int32] * 7 + [C.c_int64] + [C.c_int32] * 3 +
                      [C.c_float, C.c_float, C.c_int32, C.c_void_p]),
 }

@@ -58,11 +58,20 @@ def collate(seqs: Sequence[Tensor], pad_value: int, *, pin_memory: bool = False)
     """-> (ids int64 [N, Smax] right-padded, seq_lens, is_ragged)."""
     lens = [int(t.shape[0]) for t in seqs]
     smax = max(lens) if lens else 0
-    out = torch.full((len(seqs), smax), int(pad_value), dtype=torch.int64,
-                     pin_memory=bool(pin_memory and torch.cuda.is_available()))
-    for i, t in enumerate(seqs):
-        out[i, : lens[i]] = t
-    return out, lens, any(n != smax for n in lens)
+    ragged = any(n != smax for n in lens)
+    pin = bool(pin_memory and torch.cuda.is_available())
+    if not ragged and seqs:  # one stack instead of a Python loop over rows
+        out = torch.empty((len(seqs), smax), dtype=torch.int64, pin_memory=pin)
+        torch.stack(list(seqs), out=out)
+        return out, lens, False
+    out = torch.full((len(seqs), smax), int(pad_value), dtype=torch.int64, pin_memory=pin)
+    if seqs:  # scatter the concatenated tokens to (row, position) in one indexed write
+        lt = torch.tensor(lens, dtype=torch.int64)
+        row = torch.repeat_interleave(torch.arange(len(seqs)), lt)
+        starts = torch.cumsum(lt, 0) - lt
+        pos = torch.arange(int(lt.sum())) - torch.repeat_interleave(starts, lt)
+        out[row, pos] = torch.cat(list(seqs))
+    return out, lens, ragged
 
 
 def to_sequence_batch(ids: Tensor, lens: List[int], is_ragged: bool, device) -> SequenceBatch:

@@ -1,19 +1,30 @@
-// tcgen05 self-attention for packed sequences of at most 128 tokens (the sentence regime of the SONAR
-// text encoder: BASELINE config 2 is S = 128; longer inputs use attention.cu).
+// tcgen05 self-attention over PACKED variable-length sequences (any length the position table allows).
 //
-// One work item = (sentence b, head h): S = Q K^T and O = P V are each ONE accumulator tile:
-//   S[128 x 128] = Q[128 x 64] . K[128 x 64]^T   4 x tcgen05.mma (M=128, N=128, K=16), both operands K-major
-//   O[128 x 64]  = P[128 x 128] . V[128 x 64]    8 x tcgen05.mma (M=128, N=64,  K=16), V is the MN-major B operand
-// Q/K/V tiles come straight out of the fused qkv activation [T, 3*D] with TMA (SWIZZLE_128B), accumulators
-// live in TMEM (S: 128 columns, O: 64 columns), and the softmax runs with ONE THREAD PER QUERY ROW reading its
-// row from TMEM (no shuffles, no shared-memory reductions); P is written back to shared memory as the bf16
-// K-major A operand.  Keys >= len get probability exactly 0 (exp2(-inf)), so whatever the TMA box picked up
-// beyond the sentence (the next sentence's rows, or zero fill past T) never contributes.
+// Reference semantics: fairseq2 StandardMultiheadAttention + create_default_sdpa
+// (sonar/models/sonar_text/factory.py:130-141) = F.scaled_dot_product_attention with a key-padding mask,
+// scale 1/sqrt(64), no causal mask.  Padded positions do not exist on the device, so the
+// "mask" is simply: keys >= len get probability exactly 0.
 //
-// CTA = 4 softmax/epilogue warps (TMEM lane quarter = warp index) + 1 control warp (TMA + MMA issue by one
-// elected lane).  Persistent over items; 2 CTAs per SM (80 KB smem, 256 TMEM columns each) overlap one CTA's
-// softmax with the other's loads and MMAs; within a CTA the next item's Q/K (and then V) are prefetched as
-// soon as the MMAs that read them have retired.
+// Work decomposition.  An ITEM is (sentence b, head h).  Its queries are cut into 128-row tiles, its keys into 128-key
+// tiles, and a UNIT is one (query tile, key tile) pair:
+//     S[128 x 128] = Q[128 x 64] . K[128 x 64]^T      4 x tcgen05.mma (M=128, N=128, K=16), operands K-major
+//     P            = exp2((S - m) * scale)            softmax numerators, ONE THREAD PER QUERY ROW reading TMEM
+//     O[128 x 64]  = P[128 x 128] . V[128 x 64]       <= 8 x tcgen05.mma (M=128, N=64, K=16), V is the MN-major B operand
+// For sentences of at most 128 tokens (BASELINE config 2) an item is exactly one unit; longer sentences run
+// nq x nkv units with the usual online-softmax rescaling of a register accumulator between key tiles.
+//
+// One persistent CTA per SM, warp-specialised, everything asynchronous:
+//   warp 0   TMA producer: Q, K, V tiles [128 x 64] bf16 (SWIZZLE_128B) of the next units into a 4-stage ring (192 KB),
+//            so up to ~100 KB of loads are in flight per SM at any time -- the op is HBM-bound (reads 6 B, writes 2 B per
+//            token and dim; 1.2 % of the encoder FLOPs)
+//   warp 1   MMA issuer (one elected lane): S for unit u, then P.V for unit u-1, so the tensor core always has the other
+//            softmax group's S queued while one group is busy with exponentials
+//   warp 2   TMEM allocator (512 columns: S0 | S1 | O0 | O1)
+//   warps 4-7 / 8-11   two softmax + epilogue warpgroups (TMEM lane quarter = warp % 4); group g owns the items with
+//            g = local item index & 1 and the TMEM buffers S[g], O[g]
+// The softmax is two-pass over TMEM (row maximum, then exponentials), 32 columns at a time, so a thread never holds more
+// than one chunk of the score row; P (bf16, K-major SW128) is written over the unit's own Q and K tiles, which are dead
+// once S has been computed.
 
 #include "common.cuh"
 #include "sonar_b200_internal.h"
@@ -23,9 +34,13 @@
 namespace sb {
 namespace {
 
-constexpr int kTile = 128 * 64 * 2;  // one [128 x 64] bf16 operand tile = 16 KB
-constexpr int kSmemBytes = 3 * kTile + 2 * kTile + 256 + 1024;  // Q,K,V + P(2 tiles) + barriers + align slack
-constexpr int kThreads = 160;
+constexpr int kTile = 128 * 64 * 2;    // one [128 x 64] bf16 operand tile = 16 KB
+constexpr int kStageBytes = 3 * kTile;  // Q | K | V
+constexpr int kStages = 4;
+constexpr int kBarBytes = 256;
+constexpr int kCuSmemInts = 8192;  // cu_seqlens is staged in shared memory when the batch has < 8192 sentences
+constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kCuSmemInts * 4 + 1024;  // + alignment slack
+constexpr int kThreads = 384;
 
 // MN-major B operand (V: rows = keys (K dim), 64 contiguous head dims = one 128 B swizzle row):
 // 8-key groups are 1024 B apart (SBO); a single 64-wide atom along MN, LBO = 128 keys * 128 B.
@@ -41,161 +56,254 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* __restrict__ cu, int B, int H,
+// The unit sequence of one softmax group inside this CTA: items blockIdx.x + (2*i + g) * gridDim.x, i = 0, 1, ...,
+// each expanded into its (query tile, key tile) units.  Every warp role walks identical copies.
+struct UnitStream {
+  const int32_t* cu;
+  int H, num_items, item, stride;
+  int b, h, tok0, len, nt, qt, kt;  // current item / unit
+  bool valid;
+  __device__ __forceinline__ void load_item() {
+    for (;;) {
+      valid = item < num_items;
+      if (!valid) return;
+      b = item / H;
+      h = item - b * H;
+      tok0 = cu[b];
+      len = cu[b + 1] - tok0;
+      nt = (len + 127) >> 7;
+      qt = kt = 0;
+      if (len > 0) return;
+      item += stride;  // empty sentence: no units (the pooling kernel writes zeros for it)
+    }
+  }
+  __device__ __forceinline__ void init(const int32_t* cu_, int H_, int num_items_, int first, int stride_) {
+    cu = cu_; H = H_; num_items = num_items_; item = first; stride = stride_;
+    load_item();
+  }
+  __device__ __forceinline__ void advance() {
+    if (++kt == nt) {
+      kt = 0;
+      if (++qt == nt) {
+        item += stride;
+        load_item();
+      }
+    }
+  }
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* cu, int B, int H,
                     __nv_bfloat16* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kTile;
-  uint8_t* sV = sK + kTile;
-  uint8_t* sP = sV + kTile;  // 2 tiles: keys 0-63, keys 64-127
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTile);
-  uint64_t* bar_qk = bars + 0;       // TMA: Q and K landed
-  uint64_t* bar_v = bars + 1;        // TMA: V landed
-  uint64_t* bar_s = bars + 2;        // MMA: S complete (Q, K smem free again)
-  uint64_t* bar_p = bars + 3;        // softmax: P written (4 warp arrivals); also means S has been read
-  uint64_t* bar_o = bars + 4;        // MMA: O complete (P, V smem free again)
-  uint64_t* bar_drained = bars + 5;  // epilogue: O has been read out of TMEM (4 warp arrivals)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full_qk = bars;               // [kStages] TMA: Q and K landed
+  uint64_t* full_v = bars + kStages;      // [kStages] TMA: V landed
+  uint64_t* empty = bars + 2 * kStages;   // [kStages] MMA: P.V retired -> the stage (and the P written over Q|K) is free
+  uint64_t* s_full = bars + 3 * kStages;  // [2] MMA: S[g] complete
+  uint64_t* p_ready = s_full + 2;         // [2] softmax group g: P written and S[g] fully read (4 warp arrivals)
+  uint64_t* o_full = s_full + 4;          // [2] MMA: O[g] complete
+  uint64_t* o_free = s_full + 6;          // [2] group g: O[g] read out of TMEM (4 warp arrivals)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_full + 8);
+  int32_t* cu_smem = reinterpret_cast<int32_t*>(smem + kStages * kStageBytes + kBarBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = H * 64;
-
-  if (warp == 4) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tm_qkv);
-      mbar_init(bar_qk, 1);
-      mbar_init(bar_v, 1);
-      mbar_init(bar_s, 1);
-      mbar_init(bar_p, 4);
-      mbar_init(bar_o, 1);
-      mbar_init(bar_drained, 4);
-      fence_mbar_init();
-    }
-    __syncwarp();
-    tmem_alloc<1>(tmem_ptr_smem, 256);
+  const int num_items = B * H;
+  // every role looks sentence boundaries up once per item: keep them in shared memory (one LDS instead of an L2 round trip)
+  const int32_t* cu_g = cu;
+  if (B + 1 <= kCuSmemInts) {
+    for (int i = threadIdx.x; i <= B; i += kThreads) cu_smem[i] = cu_g[i];
+    cu = cu_smem;
   }
+
+  if (warp == 1 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_qk[i], 1);
+      mbar_init(&full_v[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_ready[g], 4);
+      mbar_init(&o_full[g], 1);
+      mbar_init(&o_free[g], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<1>(tmem_ptr_smem, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tmem_s = tmem_base;        // columns [0,128)
-  const uint32_t tmem_o = tmem_base + 128;  // columns [128,192)
 
-  const int num_items = B * H;
-
-  if (warp == 4) {
-    // ============================ control warp: TMA + MMA issue ============================
+  if (warp == 0) {
+    // ============================ TMA producer ============================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16_f32(128, 128);
-      constexpr uint32_t idesc_o = umma_idesc_bf16_f32(128, 64) | (1u << 16);  // B operand MN-major
-      auto load_qk = [&](int item) {
-        const int b = item / H, h = item % H;
-        const int tok0 = cu[b];
-        mbar_arrive_expect_tx(bar_qk, 2 * kTile);
-        tma_load_2d(sQ, &tm_qkv, bar_qk, h * 64, tok0);
-        tma_load_2d(sK, &tm_qkv, bar_qk, D + h * 64, tok0);
-      };
-      auto load_v = [&](int item) {
-        const int b = item / H, h = item % H;
-        const int tok0 = cu[b];
-        mbar_arrive_expect_tx(bar_v, kTile);
-        tma_load_2d(sV, &tm_qkv, bar_v, 2 * D + h * 64, tok0);
-      };
-      int item = blockIdx.x;
-      if (item < num_items) {
-        load_qk(item);
-        load_v(item);
-      }
-      uint32_t ph = 0;
-      for (; item < num_items; item += gridDim.x, ph ^= 1) {
-        const int next = item + gridDim.x;
-        // ---- S = Q K^T ----
-        mbar_wait(bar_qk, ph);
-        tc_fence_after();
-        {
-          const uint64_t qd = umma_desc_kmajor_sw128(smem_u32(sQ));
-          const uint64_t kd = umma_desc_kmajor_sw128(smem_u32(sK));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16<1>(tmem_s, qd + uint64_t(2 * k), kd + uint64_t(2 * k), idesc_s, k != 0);
-          umma_commit<1>(bar_s);
-        }
-        mbar_wait(bar_s, ph);  // Q, K consumed -> prefetch the next item's Q, K
-        if (next < num_items) load_qk(next);
-        // ---- O = P V ----
-        mbar_wait(bar_p, ph);  // P in smem (and S fully read)
-        mbar_wait(bar_v, ph);
-        if (item != int(blockIdx.x)) mbar_wait(bar_drained, ph ^ 1);  // previous O read out of TMEM
-        tc_fence_after();
-        {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint64_t pd = umma_desc_kmajor_sw128(smem_u32(sP + (k >> 2) * kTile)) + uint64_t(2 * (k & 3));
-            const uint64_t vd = umma_desc_mnmajor_sw128(smem_u32(sV + k * 2048));  // 16 keys * 128 B per k-step
-            umma_bf16<1>(tmem_o, pd, vd, idesc_o, k != 0);
-          }
-          umma_commit<1>(bar_o);
-        }
-        mbar_wait(bar_o, ph);  // P, V consumed -> prefetch the next item's V
-        if (next < num_items) load_v(next);
+      UnitStream s0, s1;  // (two named streams, selected by value: indexing an array of them would put them in local memory)
+      s0.init(cu, H, num_items, blockIdx.x, 2 * gridDim.x);
+      s1.init(cu, H, num_items, blockIdx.x + gridDim.x, 2 * gridDim.x);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int turn = 0; s0.valid || s1.valid; ++turn) {
+        const bool g1 = (turn & 1) ? s1.valid : !s0.valid;
+        const int col = (g1 ? s1.h : s0.h) * 64;
+        const int qrow = g1 ? s1.tok0 + s1.qt * 128 : s0.tok0 + s0.qt * 128;
+        const int krow = g1 ? s1.tok0 + s1.kt * 128 : s0.tok0 + s0.kt * 128;
+        uint8_t* base = smem + stage * kStageBytes;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_qk[stage], 2 * kTile);
+        tma_load_2d(base, &tm_qkv, &full_qk[stage], col, qrow);
+        tma_load_2d(base + kTile, &tm_qkv, &full_qk[stage], D + col, krow);
+        mbar_arrive_expect_tx(&full_v[stage], kTile);
+        tma_load_2d(base + 2 * kTile, &tm_qkv, &full_v[stage], 2 * D + col, krow);
+        if (g1) s1.advance(); else s0.advance();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
-  } else {
-    // ============================ softmax + epilogue: one thread per query row ============================
-    const int row = warp * 32 + lane;
-    const uint32_t lane_base = uint32_t(warp * 32) << 16;
-    const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-    uint32_t ph = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ph ^= 1) {
-      const int b = item / H, h = item % H;
-      const int tok0 = cu[b];
-      const int len = cu[b + 1] - tok0;  // 1..128 (host guarantees max_len <= 128)
-      mbar_wait(bar_s, ph);
-      tc_fence_after();
-      // the whole S row (128 fp32) lives in registers: one batch of TMEM loads, one wait
-      const int nch = (len + 31) >> 5;  // 32-key chunks that hold valid keys (CTA-uniform)
-      uint32_t v[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_s + lane_base + c * 32, v[c]);  // stale columns are masked below
-      tmem_ld_wait();
-      float mx = -CUDART_INF_F;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c * 32 + 32 > len) {  // chunk reaches past the sentence: keys >= len -> -inf -> probability exactly 0
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c * 32 + j >= len) v[c][j] = __float_as_uint(-CUDART_INF_F);
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16_f32(128, 128);
+      constexpr uint32_t idesc_o = umma_idesc_bf16_f32(128, 64) | (1u << 16);  // B operand MN-major
+      UnitStream s0, s1;
+      s0.init(cu, H, num_items, blockIdx.x, 2 * gridDim.x);
+      s1.init(cu, H, num_items, blockIdx.x + gridDim.x, 2 * gridDim.x);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t n0 = 0, n1 = 0;  // units issued per group
+      // the unit whose P.V is still to be issued (one behind the S issue)
+      int pend_g = -1, pend_stage = 0, pend_ksteps = 0;
+      uint32_t pend_stage_phase = 0, pend_n = 0;
+      auto issue_pv = [&]() {
+        const int g = pend_g;
+        uint8_t* base = smem + pend_stage * kStageBytes;
+        mbar_wait(&p_ready[g], pend_n & 1);             // P in smem, S[g] read
+        mbar_wait(&full_v[pend_stage], pend_stage_phase);
+        if (pend_n > 0) mbar_wait(&o_free[g], (pend_n - 1) & 1);  // the group's previous O has been read out
+        tc_fence_after();
+        const uint32_t tmem_o = tmem_base + 256 + g * 64;
+        for (int k = 0; k < pend_ksteps; ++k) {
+          const uint64_t pd = umma_desc_kmajor_sw128(smem_u32(base + (k >> 2) * kTile)) + uint64_t(2 * (k & 3));
+          const uint64_t vd = umma_desc_mnmajor_sw128(smem_u32(base + 2 * kTile + k * 2048));  // 16 keys * 128 B
+          umma_bf16<1>(tmem_o, pd, vd, idesc_o, k != 0);
         }
-        if (c < nch) {
-          float m0 = __uint_as_float(v[c][0]), m1 = __uint_as_float(v[c][1]);
-#pragma unroll
-          for (int j = 2; j < 32; j += 2) {
-            m0 = fmaxf(m0, __uint_as_float(v[c][j]));
-            m1 = fmaxf(m1, __uint_as_float(v[c][j + 1]));
-          }
-          mx = fmaxf(mx, fmaxf(m0, m1));
+        umma_commit<1>(&o_full[g]);
+        umma_commit<1>(&empty[pend_stage]);
+        pend_g = -1;
+      };
+      for (int turn = 0; s0.valid || s1.valid; ++turn) {
+        const bool g1 = (turn & 1) ? s1.valid : !s0.valid;
+        const int g = g1 ? 1 : 0;
+        const uint32_t ng = g1 ? n1 : n0;
+        const int kv_valid = g1 ? min(128, s1.len - s1.kt * 128) : min(128, s0.len - s0.kt * 128);
+        uint8_t* base = smem + stage * kStageBytes;
+        // a P that is already waiting goes to the tensor core before this thread blocks on the next unit's loads
+        if (pend_g >= 0 && mbar_try_wait(&p_ready[pend_g], pend_n & 1)) issue_pv();
+        // ---- S = Q K^T for this unit ----
+        mbar_wait(&full_qk[stage], phase);
+        if (ng > 0) {
+          if (pend_g == g) issue_pv();                 // same group twice in a row: its P.V must go first
+          mbar_wait(&p_ready[g], (ng - 1) & 1);        // S[g] of the group's previous unit has been read
         }
+        tc_fence_after();
+        {
+          const uint64_t qd = umma_desc_kmajor_sw128(smem_u32(base));
+          const uint64_t kd = umma_desc_kmajor_sw128(smem_u32(base + kTile));
+          const uint32_t tmem_s = tmem_base + g * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16<1>(tmem_s, qd + uint64_t(2 * k), kd + uint64_t(2 * k), idesc_s, k != 0);
+          umma_commit<1>(&s_full[g]);
+        }
+        // ---- P.V of the previous unit (normally the other group's) ----
+        if (pend_g >= 0) issue_pv();
+        pend_g = g;
+        pend_stage = stage;
+        pend_stage_phase = phase;
+        pend_ksteps = (kv_valid + 15) >> 4;
+        pend_n = ng;
+        if (g1) { ++n1; s1.advance(); } else { ++n0; s0.advance(); }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      const float mxs = mx * sl2;
-      // p = exp2(s*c - max*c), row sum, bf16 P row -> swizzled K-major smem (zeros beyond the valid chunks)
+      if (pend_g >= 0) issue_pv();
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ============================ softmax + epilogue: one thread per query row ============================
+    const int g = (warp - 4) >> 2;
+    const int wq = warp & 3;  // TMEM lane quarter
+    const int row = wq * 32 + lane;
+    const uint32_t lane_base = uint32_t(wq * 32) << 16;
+    const uint32_t tmem_s = tmem_base + g * 128 + lane_base;
+    const uint32_t tmem_o = tmem_base + 256 + g * 64 + lane_base;
+    const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    UnitStream u;
+    u.init(cu, H, num_items, blockIdx.x + g * gridDim.x, 2 * gridDim.x);
+    // ring position of this group's next unit: both producers of the interleaving (turn order) are replayed here
+    UnitStream other;
+    other.init(cu, H, num_items, blockIdx.x + (g ^ 1) * gridDim.x, 2 * gridDim.x);
+    int turn = 0, ring = 0;  // `ring` = units issued so far by both groups = stage index modulo kStages
+    uint32_t n = 0;
+    float m_run = -CUDART_INF_F, l_run = 0.f;
+    float o_acc[64];
+    while (u.valid) {
+      // advance the interleaving until it is this group's turn
+      for (;;) {
+        const int tg = (turn & 1);
+        const int pick = (tg == g ? u.valid : other.valid) ? tg : (tg ^ 1);
+        ++turn;
+        if (pick == g) break;
+        other.advance();
+        ++ring;
+      }
+      const int stage = ring % kStages;
+      ++ring;
+      uint8_t* sP = smem + stage * kStageBytes;  // P overwrites the unit's Q | K tiles
+      const int kv_valid = min(128, u.len - u.kt * 128);
+      const int nch = (kv_valid + 31) >> 5;  // 32-key chunks holding valid keys
+      const bool single = (u.nt == 1);
+      if (u.kt == 0) { m_run = -CUDART_INF_F; l_run = 0.f; }
+
+      mbar_wait(&s_full[g], n & 1);
+      tc_fence_after();
+      // ---- pass 1: row maximum over the valid keys ----
+      float mx = -CUDART_INF_F;
+      for (int c = 0; c < nch; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_s + c * 32, v);
+        tmem_ld_wait();
+        const int lim = kv_valid - c * 32;  // keys >= lim of this chunk are beyond the sentence
+        float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          m0 = fmaxf(m0, j < lim ? __uint_as_float(v[j]) : -CUDART_INF_F);
+          m1 = fmaxf(m1, j + 1 < lim ? __uint_as_float(v[j + 1]) : -CUDART_INF_F);
+        }
+        mx = fmaxf(mx, fmaxf(m0, m1));
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = fast_exp2((m_run - m_new) * sl2);  // 0 on the first key tile (m_run = -inf)
+      const float mxs = m_new * sl2;
+      // ---- pass 2: p = exp2(s*c - m*c), row sum, bf16 P row -> swizzled K-major smem ----
       float sum0 = 0.f, sum1 = 0.f;
       uint8_t* prow = sP + row * 128;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < nch; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_s + c * 32, v);
+        tmem_ld_wait();
+        const int lim = kv_valid - c * 32;
         float p[32];
-        if (c < nch) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            p[j] = fast_exp2(fmaf(__uint_as_float(v[c][j]), sl2, -mxs));
-            p[j + 1] = fast_exp2(fmaf(__uint_as_float(v[c][j + 1]), sl2, -mxs));
-            sum0 += p[j];
-            sum1 += p[j + 1];
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) p[j] = 0.f;
+        for (int j = 0; j < 32; j += 2) {
+          const float a = j < lim ? __uint_as_float(v[j]) : -CUDART_INF_F;  // -inf -> probability exactly 0
+          const float bq = j + 1 < lim ? __uint_as_float(v[j + 1]) : -CUDART_INF_F;
+          p[j] = fast_exp2(fmaf(a, sl2, -mxs));
+          p[j + 1] = fast_exp2(fmaf(bq, sl2, -mxs));
+          sum0 += p[j];
+          sum1 += p[j + 1];
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -205,39 +313,66 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* _
                          pack_bf16x2(p[8 * q + 4], p[8 * q + 5]), pack_bf16x2(p[8 * q + 6], p[8 * q + 7]));
         }
       }
-      const float sum = sum0 + sum1;
+      // P.V consumes whole 16-key k-steps: with an odd number of valid 16-key groups inside the last 32-key chunk
+      // nothing more is needed (the chunk was written in full, masked keys as zeros)
+      l_run = l_run * alpha + (sum0 + sum1);
+      m_run = m_new;
       tc_fence_before();
       fence_proxy_async_smem();  // generic-proxy writes of P -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p);
-      // ---- epilogue: O / sum -> bf16 -> global ----
-      const float inv = 1.0f / sum;
-      mbar_wait(bar_o, ph);
+      if (lane == 0) mbar_arrive(&p_ready[g]);
+      // ---- O tile: accumulate / write out ----
+      mbar_wait(&o_full[g], n & 1);
       tc_fence_after();
       uint32_t o[2][32];
-      tmem_ld_32x32(tmem_o + lane_base, o[0]);
-      tmem_ld_32x32(tmem_o + lane_base + 32, o[1]);
+      tmem_ld_32x32(tmem_o, o[0]);
+      tmem_ld_32x32(tmem_o + 32, o[1]);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_drained);
-      if (row < len) {
-        uint4* dst = reinterpret_cast<uint4*>(out + (long long)(tok0 + row) * D + h * 64);
+      if (lane == 0) mbar_arrive(&o_free[g]);
+      const bool last = (u.kt == u.nt - 1);
+      const int qrow = u.qt * 128 + row;
+      if (single) {
+        if (qrow < u.len) {
+          const float inv = 1.0f / l_run;
+          uint4* dst = reinterpret_cast<uint4*>(out + (long long)(u.tok0 + qrow) * D + u.h * 64);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const uint32_t* s = &o[q >> 2][(q & 3) * 8];
-          dst[q] = make_uint4(pack_bf16x2(__uint_as_float(s[0]) * inv, __uint_as_float(s[1]) * inv),
-                              pack_bf16x2(__uint_as_float(s[2]) * inv, __uint_as_float(s[3]) * inv),
-                              pack_bf16x2(__uint_as_float(s[4]) * inv, __uint_as_float(s[5]) * inv),
-                              pack_bf16x2(__uint_as_float(s[6]) * inv, __uint_as_float(s[7]) * inv));
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t* s = &o[q >> 2][(q & 3) * 8];
+            dst[q] = make_uint4(pack_bf16x2(__uint_as_float(s[0]) * inv, __uint_as_float(s[1]) * inv),
+                                pack_bf16x2(__uint_as_float(s[2]) * inv, __uint_as_float(s[3]) * inv),
+                                pack_bf16x2(__uint_as_float(s[4]) * inv, __uint_as_float(s[5]) * inv),
+                                pack_bf16x2(__uint_as_float(s[6]) * inv, __uint_as_float(s[7]) * inv));
+          }
+        }
+      } else {
+        if (u.kt == 0) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) o_acc[j] = __uint_as_float(o[j >> 5][j & 31]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) o_acc[j] = fmaf(o_acc[j], alpha, __uint_as_float(o[j >> 5][j & 31]));
+        }
+        if (last && qrow < u.len) {
+          const float inv = 1.0f / l_run;
+          uint4* dst = reinterpret_cast<uint4*>(out + (long long)(u.tok0 + qrow) * D + u.h * 64);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            dst[q] = make_uint4(pack_bf16x2(o_acc[8 * q] * inv, o_acc[8 * q + 1] * inv),
+                                pack_bf16x2(o_acc[8 * q + 2] * inv, o_acc[8 * q + 3] * inv),
+                                pack_bf16x2(o_acc[8 * q + 4] * inv, o_acc[8 * q + 5] * inv),
+                                pack_bf16x2(o_acc[8 * q + 6] * inv, o_acc[8 * q + 7] * inv));
         }
       }
+      ++n;
+      u.advance();
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<1>(tmem_base, 256);
+  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 
 }  // namespace
@@ -253,7 +388,7 @@ int attention_packed_tc(const __nv_bfloat16* qkv, const int32_t* cu_seqlens, int
     SB_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   }
   long long items = (long long)B * H;
-  long long grid = 2ll * (num_sms > 0 ? num_sms : 148);
+  long long grid = (num_sms > 0 ? num_sms : 148);
   if (grid > items) grid = items;
   attention_tc_kernel<<<(unsigned)grid, kThreads, kSmemBytes, stream>>>(tm, cu_seqlens, B, H, out);
   SB_CUDA_CHECK(cudaGetLastError());

@@ -21,7 +21,8 @@ namespace sb {
 __global__ void __launch_bounds__(256)
 embed_kernel(const int64_t* __restrict__ ids, long long ids_stride, const int32_t* __restrict__ cu, int S,
              const __nv_bfloat16* __restrict__ embed, long long vocab, const float* __restrict__ pos_table, int D,
-             float scale, float* __restrict__ x, int* __restrict__ err_flag, int pos_offset) {
+             float scale, float* __restrict__ x, int* __restrict__ err_flag, int pos_offset,
+             __nv_bfloat16* __restrict__ h_out, float* __restrict__ stats_out) {
   const int b = blockIdx.x;
   const int pos = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -36,6 +37,9 @@ embed_kernel(const int64_t* __restrict__ ids, long long ids_stride, const int32_
   const uint4* erow = reinterpret_cast<const uint4*>(embed + id * (long long)D);
   const float4* prow = reinterpret_cast<const float4*>(pos_table + (long long)(pos + pos_offset) * D);
   float4* xrow = reinterpret_cast<float4*>(x + (long long)(start + pos) * D);
+  // LnFold producer side (optional): bf16 copy of the row and (mean, M2) of each 256-column chunk -- chunk k is covered by
+  // iteration k of the loop below (32 lanes x 8 columns), so one warp reduction per iteration gives its statistics
+  uint4* hrow = h_out ? reinterpret_cast<uint4*>(h_out + (long long)(start + pos) * D) : nullptr;
   for (int c = lane; c < D / 8; c += 32) {
     const uint4 e = __ldg(erow + c);
     const float4 p0 = __ldg(prow + 2 * c), p1 = __ldg(prow + 2 * c + 1);
@@ -54,21 +58,74 @@ embed_kernel(const int64_t* __restrict__ ids, long long ids_stride, const int32_
     o1.w = fmaf(__high2float(e3), scale, p1.w);
     xrow[2 * c] = o0;
     xrow[2 * c + 1] = o1;
+    if (hrow != nullptr) {
+      hrow[c] = make_uint4(pack_bf16x2(o0.x, o0.y), pack_bf16x2(o0.z, o0.w), pack_bf16x2(o1.x, o1.y), pack_bf16x2(o1.z, o1.w));
+      const float mean = warp_sum((o0.x + o0.y) + (o0.z + o0.w) + (o1.x + o1.y) + (o1.z + o1.w)) * (1.0f / 256.0f);
+      float q = 0.f;
+      q = fmaf(o0.x - mean, o0.x - mean, q); q = fmaf(o0.y - mean, o0.y - mean, q);
+      q = fmaf(o0.z - mean, o0.z - mean, q); q = fmaf(o0.w - mean, o0.w - mean, q);
+      q = fmaf(o1.x - mean, o1.x - mean, q); q = fmaf(o1.y - mean, o1.y - mean, q);
+      q = fmaf(o1.z - mean, o1.z - mean, q); q = fmaf(o1.w - mean, o1.w - mean, q);
+      q = warp_sum(q);
+      if (lane == 0)
+        reinterpret_cast<float2*>(stats_out)[(long long)(start + pos) * (D / 256) + (c >> 5)] = make_float2(mean, q);
+    }
   }
 }
 
 int embed_tokens(const int64_t* ids, long long ids_stride, const int32_t* cu_seqlens, int B, int S,
                  const __nv_bfloat16* embed, long long vocab, const float* pos_table, int pos_rows, int D, float scale,
-                 float* x, int* err_flag, cudaStream_t stream, int pos_offset) {
+                 float* x, int* err_flag, cudaStream_t stream, int pos_offset, __nv_bfloat16* h_out, float* stats_out) {
   if (B <= 0 || S <= 0) return 0;
   if (D % 8 != 0) { set_last_error("embed_tokens: D must be a multiple of 8"); return -1; }
+  if ((h_out != nullptr) != (stats_out != nullptr) || (h_out != nullptr && D % 256 != 0)) {
+    set_last_error("embed_tokens: h_out and stats_out go together and need D %% 256 == 0");
+    return -1;
+  }
   if (S + pos_offset > pos_rows || pos_offset < 0) {
     set_last_error("embed_tokens: positions [%d,%d) exceed the position table (%d rows)", pos_offset, S + pos_offset, pos_rows);
     return -1;
   }
   dim3 grid((unsigned)B, (unsigned)((S + 7) / 8), 1);
   embed_kernel<<<grid, 256, 0, stream>>>(ids, ids_stride, cu_seqlens, S, embed, vocab, pos_table, D, scale, x,
-                                         err_flag, pos_offset);
+                                         err_flag, pos_offset, h_out, stats_out);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// LnFold weight preparation (once, at create): one warp per output row n of W [N, K]
+//   Wf[n,k] = bf16(W[n,k] * gamma[k]);  colsum[n] = sum_k Wf[n,k];  bias_f[n] = bias[n] + sum_k W[n,k] * beta[k]
+__global__ void __launch_bounds__(256)
+fold_layernorm_kernel(const __nv_bfloat16* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, int N, int K, __nv_bfloat16* __restrict__ Wf,
+                      float* __restrict__ colsum, float* __restrict__ bias_f) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const __nv_bfloat16* w = W + (long long)n * K;
+  __nv_bfloat16* wf = Wf + (long long)n * K;
+  double cs = 0.0, bs = 0.0;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = __bfloat162float(w[k]);
+    const __nv_bfloat16 r = __float2bfloat16_rn(wv * gamma[k]);
+    wf[k] = r;
+    cs += (double)__bfloat162float(r);
+    bs += (double)wv * (double)beta[k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cs += __shfl_xor_sync(0xffffffffu, cs, o);
+    bs += __shfl_xor_sync(0xffffffffu, bs, o);
+  }
+  if (lane == 0) {
+    colsum[n] = (float)cs;
+    bias_f[n] = (float)((double)bias[n] + bs);
+  }
+}
+
+int fold_layernorm_weights(const __nv_bfloat16* W, const float* bias, const float* gamma, const float* beta, int N, int K,
+                           __nv_bfloat16* Wf, float* colsum, float* bias_f, cudaStream_t stream) {
+  fold_layernorm_kernel<<<(unsigned)((N + 7) / 8), 256, 0, stream>>>(W, bias, gamma, beta, N, K, Wf, colsum, bias_f);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -8,9 +8,16 @@
 //   tokens are PACKED: row cu_seqlens[b] + t holds token t of sentence b, so padded
 //   positions never exist on the device (the reference computes them and masks them).
 //   x   fp32 [T, D]   residual stream (fp32 so 48 residual adds do not accumulate bf16 rounding)
-//   h   bf16 [T, D]   LayerNorm output / attention output (GEMM A operands)
-//   qkv bf16 [T, 3D]  fused q|k|v projections
+//   h   bf16 [T, D]   GEMM A operands: bf16 copy of x (LayerNorm folded into the GEMMs) or LayerNorm output; attention output
+//   qkv bf16 [T, 3D]  fused q|k|v projections (its first [T, D] doubles as the bf16 copy of x behind the out-projection)
 //   f   bf16 [T, F]   FFN inner activations
+//
+// Default schedule (cfg.ln_fold = 1), 5 launches per layer, no LayerNorm kernel:
+//   embed -> x, h = bf16(x), row stats
+//   24 x [ QKV GEMM (folds LN1: stats + gamma/beta prepared into W', c, b') -> attention (tcgen05) ->
+//          out-proj GEMM (+residual; emits x, bf16(x), stats) -> FFN1 GEMM (folds LN2, +ReLU) ->
+//          FFN2 GEMM (+residual; emits x, bf16(x), stats) ] -> final LN + pool
+// cfg.ln_fold = 0 keeps the classic schedule (separate LayerNorm kernels, residual adds by TMA reduce-add).
 
 #include "../../include/sonar_b200.h"
 #include <stdlib.h>
@@ -39,9 +46,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 struct Workspace {
   int32_t* cu;
-  int32_t* err_flag;
-  int32_t* ln_counters;  // one arrival counter per 128-row block (LayerNorm fused behind the residual GEMMs)
-  size_t ln_counter_bytes;
+  float* ln_stats;  // [T, D/256, 2] per-row LayerNorm partials (LnFold)
   float* x;
   __nv_bfloat16* h;
   __nv_bfloat16* qkv;
@@ -53,8 +58,20 @@ struct Workspace {
 
 using namespace sb;
 
+struct FoldedLayer {  // LnFold weights of one layer (device memory owned by the handle)
+  __nv_bfloat16* wqkv = nullptr;
+  __nv_bfloat16* w1 = nullptr;
+  float* cqkv = nullptr;
+  float* bqkv = nullptr;
+  float* c1 = nullptr;
+  float* b1 = nullptr;
+};
+
 struct SbEncoder {
   SbEncoderConfig cfg;
+  std::vector<FoldedLayer> folded;
+  void* fold_pool = nullptr;     // one allocation behind all FoldedLayer pointers
+  int32_t* err_flag = nullptr;   // device: sticky "token id out of range" flag, cleared by sb_encoder_check_inputs
   const void* embed;
   const float* pos_table;
   const float* final_ln_g;
@@ -78,13 +95,10 @@ static Workspace carve(const SbEncoder* e, int32_t max_batch, int64_t max_tokens
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   size_t off = 0;
   Workspace w;
-  w.err_flag = reinterpret_cast<int32_t*>(p + off);  // fixed offset 0: see sb_encoder_check_inputs
-  off = align_up(off + 256, 1024);
   w.cu = reinterpret_cast<int32_t*>(p + off);
   off = align_up(off + sizeof(int32_t) * ((size_t)max_batch + 1), 1024);
-  w.ln_counters = reinterpret_cast<int32_t*>(p + off);
-  w.ln_counter_bytes = sizeof(int32_t) * (T / 128 + 8);
-  off = align_up(off + w.ln_counter_bytes, 1024);
+  w.ln_stats = reinterpret_cast<float*>(p + off);
+  off = align_up(off + T * (D / 256) * 2 * sizeof(float), 1024);
   w.x = reinterpret_cast<float*>(p + off);
   off = align_up(off + T * D * 4, 1024);
   w.h = reinterpret_cast<__nv_bfloat16*>(p + off);
@@ -100,7 +114,7 @@ static Workspace carve(const SbEncoder* e, int32_t max_batch, int64_t max_tokens
 extern "C" {
 
 const char* sb_last_error(void) { return g_err; }
-int sb_version(void) { return 100; }
+int sb_version(void) { return 101; }
 
 int sb_encoder_create(const SbEncoderConfig* cfg, const SbEncoderWeights* w, SbEncoder** out) {
   if (!cfg || !w || !out) { set_last_error("sb_encoder_create: null argument"); return SB_ERR_INVALID; }
@@ -115,6 +129,7 @@ int sb_encoder_create(const SbEncoderConfig* cfg, const SbEncoderWeights* w, SbE
     return SB_ERR_INVALID;
   }
   if (F <= 0 || F % 256 != 0) { set_last_error("sb_encoder_create: ffn_inner_dim must be a multiple of 256"); return SB_ERR_INVALID; }
+  if (cfg->ln_fold != 0 && cfg->ln_fold != 1) { set_last_error("sb_encoder_create: ln_fold must be 0 or 1"); return SB_ERR_INVALID; }
   if (cfg->num_layers < 0 || cfg->pos_rows <= 0 || cfg->vocab_size <= 0) {
     set_last_error("sb_encoder_create: bad num_layers / pos_rows / vocab_size");
     return SB_ERR_INVALID;
@@ -165,6 +180,48 @@ int sb_encoder_create(const SbEncoderConfig* cfg, const SbEncoderWeights* w, SbE
     delete e;
     return SB_ERR_CUDA;
   }
+  if (cudaMalloc(reinterpret_cast<void**>(&e->err_flag), 256) != cudaSuccess ||
+      cudaMemset(e->err_flag, 0, 256) != cudaSuccess) {
+    set_last_error("sb_encoder_create: cudaMalloc of the input-check flag failed");
+    sb_encoder_destroy(e);
+    return SB_ERR_CUDA;
+  }
+  if (cfg->ln_fold && cfg->num_layers > 0) {
+    // LayerNorm folding (LnFold): W' = W diag(gamma), c = row sums of W', b' = b + W beta for the two GEMMs that consume a
+    // LayerNorm in every layer; prepared once here (the caller's weights are not modified)
+    const size_t D_ = D, F_ = F;
+    const size_t per_layer = align_up(3 * D_ * D_ * 2, 256) + align_up(F_ * D_ * 2, 256) + 2 * align_up(3 * D_ * 4, 256) +
+                             2 * align_up(F_ * 4, 256);
+    if (cudaMalloc(&e->fold_pool, per_layer * cfg->num_layers) != cudaSuccess) {
+      set_last_error("sb_encoder_create: cudaMalloc of %zu bytes for the LayerNorm-folded weights failed",
+                     per_layer * cfg->num_layers);
+      sb_encoder_destroy(e);
+      return SB_ERR_CUDA;
+    }
+    e->folded.resize(cfg->num_layers);
+    uint8_t* p = reinterpret_cast<uint8_t*>(e->fold_pool);
+    for (int i = 0; i < cfg->num_layers; ++i) {
+      FoldedLayer& f = e->folded[i];
+      const SbLayerWeights& l = e->layers[i];
+      f.wqkv = reinterpret_cast<__nv_bfloat16*>(p); p += align_up(3 * D_ * D_ * 2, 256);
+      f.w1 = reinterpret_cast<__nv_bfloat16*>(p); p += align_up(F_ * D_ * 2, 256);
+      f.cqkv = reinterpret_cast<float*>(p); p += align_up(3 * D_ * 4, 256);
+      f.bqkv = reinterpret_cast<float*>(p); p += align_up(3 * D_ * 4, 256);
+      f.c1 = reinterpret_cast<float*>(p); p += align_up(F_ * 4, 256);
+      f.b1 = reinterpret_cast<float*>(p); p += align_up(F_ * 4, 256);
+      int rc = fold_layernorm_weights(reinterpret_cast<const __nv_bfloat16*>(l.wqkv), l.bqkv, l.ln1_g, l.ln1_b, 3 * D, D,
+                                      f.wqkv, f.cqkv, f.bqkv, nullptr);
+      if (!rc)
+        rc = fold_layernorm_weights(reinterpret_cast<const __nv_bfloat16*>(l.w1), l.b1, l.ln2_g, l.ln2_b, F, D, f.w1, f.c1,
+                                    f.b1, nullptr);
+      if (rc) { sb_encoder_destroy(e); return rc; }
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+      set_last_error("sb_encoder_create: folding the LayerNorm weights failed: %s", cudaGetErrorString(cudaGetLastError()));
+      sb_encoder_destroy(e);
+      return SB_ERR_CUDA;
+    }
+  }
   for (int i = 0; i < SbEncoder::kSlots; ++i) {
     if (cudaEventCreateWithFlags(&e->ev[i], cudaEventDisableTiming) != cudaSuccess) {
       set_last_error("sb_encoder_create: cudaEventCreate failed");
@@ -182,6 +239,8 @@ void sb_encoder_destroy(SbEncoder* e) {
   for (int i = 0; i < SbEncoder::kSlots; ++i)
     if (e->ev_ok[i]) cudaEventDestroy(e->ev[i]);
   if (e->pinned) cudaFreeHost(e->pinned);
+  if (e->fold_pool) cudaFree(e->fold_pool);
+  if (e->err_flag) cudaFree(e->err_flag);
   delete e;
 }
 
@@ -230,7 +289,6 @@ int sb_encoder_forward(SbEncoder* e, const int64_t* ids, int64_t ids_row_stride,
                    workspace_bytes, (size_t)(base - reinterpret_cast<uintptr_t>(workspace)) + w.bytes, B, T);
     return SB_ERR_INVALID;
   }
-  SB_CUDA_CHECK(cudaMemsetAsync(w.err_flag, 0, sizeof(int32_t), stream));
   SB_CUDA_CHECK(cudaMemcpyAsync(w.cu, cu_h, sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, stream));
   SB_CUDA_CHECK(cudaEventRecord(e->ev[slot], stream));
   if (T == 0) {
@@ -238,67 +296,77 @@ int sb_encoder_forward(SbEncoder* e, const int64_t* ids, int64_t ids_row_stride,
     return SB_OK;
   }
 
+  const bool fold = e->cfg.ln_fold != 0 && e->cfg.num_layers > 0;
+  __nv_bfloat16* hn = w.qkv;  // [T, D] view of the (dead after attention) qkv buffer: bf16(x) behind the out-projection
   int rc;
   if ((rc = embed_tokens(ids, ids_row_stride, w.cu, B, S, reinterpret_cast<const __nv_bfloat16*>(e->embed),
-                         e->cfg.vocab_size, e->pos_table, e->cfg.pos_rows, D, e->cfg.embed_scale, w.x, w.err_flag,
-                         stream)))
+                         e->cfg.vocab_size, e->pos_table, e->cfg.pos_rows, D, e->cfg.embed_scale, w.x, e->err_flag,
+                         stream, 0, fold ? w.h : nullptr, fold ? w.ln_stats : nullptr)))
     return rc;
 
   GemmArgs g;
   g.cta_group = (e->cfg.cta_group == 1) ? 1 : 2;
   g.num_sms = e->num_sms;
   g.M = (int)T;
-  // Experimental (off by default): LayerNorm riding behind the residual GEMMs -- their two idle warps normalise each
-  // 128-row block out of L2 once all of its n-tiles have been reduced into x (LnFuse, gemm_tcgen05.cu).  Bit-identical
-  // to the separate kernels (tests/test_gpu_encoder.py), but measured on B200 it does not pay: behind FFN2 it is a wash
-  // (9 340 vs 9 293 sent/s, same box), behind the out-projection it loses 6 % -- two warps keep only 32 KB in flight
-  // against ~5 us of loaded memory latency, so a 1 ms GEMM cannot hide its 14 MB of LayerNorm traffic per SM.
-  // SONAR_B200_FUSE_LN=1 fuses behind FFN2, =2 behind both GEMMs.
-  const char* fuse_env = getenv("SONAR_B200_FUSE_LN");
-  const int fuse_mode = fuse_env ? (fuse_env[0] - '0') : 0;  // 0 = separate kernels, 1 = behind FFN2, 2 = behind both GEMMs
-  const bool fuse_ln = fuse_mode >= 1 && fuse_mode <= 2 && T > 64 && gemm_ln_fusable((int)T, D, g.cta_group, e->num_sms);
-  const bool fuse_ln2 = fuse_ln && fuse_mode == 2;
-  if (fuse_ln) SB_CUDA_CHECK(cudaMemsetAsync(w.ln_counters, 0, w.ln_counter_bytes, stream));
+  LnFold consume;  // what a LayerNorm-consuming GEMM needs
+  consume.stats_in = w.ln_stats;
+  consume.chunks = D / 256;
+  consume.eps = e->cfg.ln_eps;
   for (int li = 0; li < e->cfg.num_layers; ++li) {
     const SbLayerWeights& L = e->layers[li];
     // --- self-attention block: x += Wo . SDPA(LN1(x)) + bo ---
-    if (li == 0 || !fuse_ln)
+    if (!fold)
       if ((rc = layernorm_bf16(w.x, L.ln1_g, L.ln1_b, e->cfg.ln_eps, w.h, T, D, stream))) return rc;
-    g.A = w.h; g.lda = D; g.W = reinterpret_cast<const __nv_bfloat16*>(L.wqkv); g.ldw = D;
-    g.C = w.qkv; g.ldc = 3 * D; g.out_fp32 = 0; g.bias = L.bqkv; g.residual = nullptr; g.ldr = 0;
+    g.A = w.h; g.lda = D; g.ldw = D;
+    g.C = w.qkv; g.ldc = 3 * D; g.out_fp32 = 0; g.residual = nullptr; g.ldr = 0;
     g.N = 3 * D; g.K = D; g.epi = EPI_BIAS;
-    if ((rc = gemm_bf16(g, stream))) return rc;
+    if (fold) {
+      const FoldedLayer& f = e->folded[li];
+      g.W = f.wqkv; g.bias = f.bqkv; g.lf = consume; g.lf.colsum = f.cqkv;
+    } else {
+      g.W = reinterpret_cast<const __nv_bfloat16*>(L.wqkv); g.bias = L.bqkv;
+    }
+    rc = gemm_bf16(g, stream);
+    g.lf = LnFold();
+    if (rc) return rc;
     if ((rc = attention_packed(w.qkv, w.cu, B, max_len, H, T, 0, e->num_sms, w.h, stream))) return rc;
     g.A = w.h; g.lda = D; g.W = reinterpret_cast<const __nv_bfloat16*>(L.wo); g.ldw = D;
     g.C = w.x; g.ldc = D; g.out_fp32 = 1; g.bias = L.bo; g.residual = w.x; g.ldr = D;
     g.N = D; g.K = D; g.epi = EPI_BIAS_RESIDUAL;
-    if (fuse_ln2) {  // h (the attention output this GEMM reads) is overwritten block by block with LN2(x): a block is
-      g.ln.gamma = L.ln2_g; g.ln.beta = L.ln2_b; g.ln.eps = e->cfg.ln_eps;  // normalised only after all its tiles ran
-      g.ln.out = w.h; g.ln.ldo = D; g.ln.counters = w.ln_counters;
+    if (fold) {  // emits x, hn = bf16(x) and the statistics LN2 needs
+      g.epi = EPI_BIAS_RESIDUAL_STATS;
+      g.lf.h_out = hn; g.lf.ldh = D; g.lf.stats_out = w.ln_stats;
     }
     rc = gemm_bf16(g, stream);
-    g.ln = LnFuse();
+    g.lf = LnFold();
     if (rc) return rc;
     // --- feed-forward block: x += W2 . relu(W1 . LN2(x) + b1) + b2 ---
-    if (!fuse_ln2)
+    if (!fold)
       if ((rc = layernorm_bf16(w.x, L.ln2_g, L.ln2_b, e->cfg.ln_eps, w.h, T, D, stream))) return rc;
-    g.A = w.h; g.lda = D; g.W = reinterpret_cast<const __nv_bfloat16*>(L.w1); g.ldw = D;
-    g.C = w.f; g.ldc = F; g.out_fp32 = 0; g.bias = L.b1; g.residual = nullptr; g.ldr = 0;
+    g.A = fold ? hn : w.h; g.lda = D; g.ldw = D;
+    g.C = w.f; g.ldc = F; g.out_fp32 = 0; g.residual = nullptr; g.ldr = 0;
     g.N = F; g.K = D; g.epi = EPI_BIAS_RELU;
+    if (fold) {
+      const FoldedLayer& f = e->folded[li];
+      g.W = f.w1; g.bias = f.b1; g.lf = consume; g.lf.colsum = f.c1;
+    } else {
+      g.W = reinterpret_cast<const __nv_bfloat16*>(L.w1); g.bias = L.b1;
+    }
     const bool prof = e->prof_start && li == e->cfg.num_layers / 2;
     if (prof) SB_CUDA_CHECK(cudaEventRecord(e->prof_start, stream));
-    if ((rc = gemm_bf16(g, stream))) return rc;
+    rc = gemm_bf16(g, stream);
+    g.lf = LnFold();
+    if (rc) return rc;
     if (prof) SB_CUDA_CHECK(cudaEventRecord(e->prof_stop, stream));
     g.A = w.f; g.lda = F; g.W = reinterpret_cast<const __nv_bfloat16*>(L.w2); g.ldw = F;
     g.C = w.x; g.ldc = D; g.out_fp32 = 1; g.bias = L.b2; g.residual = w.x; g.ldr = D;
     g.N = D; g.K = F; g.epi = EPI_BIAS_RESIDUAL;
-    if (fuse_ln && li + 1 < e->cfg.num_layers) {  // the next layer's LN1
-      const SbLayerWeights& Ln = e->layers[li + 1];
-      g.ln.gamma = Ln.ln1_g; g.ln.beta = Ln.ln1_b; g.ln.eps = e->cfg.ln_eps;
-      g.ln.out = w.h; g.ln.ldo = D; g.ln.counters = w.ln_counters;
+    if (fold) {  // emits x, h = bf16(x) and the statistics the next layer's LN1 needs
+      g.epi = EPI_BIAS_RESIDUAL_STATS;
+      g.lf.h_out = w.h; g.lf.ldh = D; g.lf.stats_out = w.ln_stats;
     }
     rc = gemm_bf16(g, stream);
-    g.ln = LnFuse();
+    g.lf = LnFold();
     if (rc) return rc;
   }
   return ln_pool(w.x, w.cu, B, D, e->final_ln_g, e->final_ln_b, e->cfg.ln_eps, 1, e->cfg.pooling, out, encoded, S,
@@ -332,15 +400,15 @@ int sb_encoder_profile_ffn1(SbEncoder* e, void* start_event, void* stop_event) {
 }
 
 int sb_encoder_check_inputs(SbEncoder* e, void* workspace, void* stream_v) {
-  if (!e || !workspace) { set_last_error("sb_encoder_check_inputs: null argument"); return SB_ERR_INVALID; }
+  (void)workspace;  // (kept in the signature; the flag lives in the handle since v101)
+  if (!e) { set_last_error("sb_encoder_check_inputs: null argument"); return SB_ERR_INVALID; }
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023);
-  Workspace w = carve(e, 1, 1, reinterpret_cast<void*>(base));
   int32_t flag = 0;
-  SB_CUDA_CHECK(cudaMemcpyAsync(&flag, w.err_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  SB_CUDA_CHECK(cudaMemcpyAsync(&flag, e->err_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  SB_CUDA_CHECK(cudaMemsetAsync(e->err_flag, 0, sizeof(int32_t), stream));  // sticky until read: covers every forward since
   SB_CUDA_CHECK(cudaStreamSynchronize(stream));
   if (flag != 0) {
-    set_last_error("token id outside [0, vocab_size) in the last sb_encoder_forward batch");
+    set_last_error("token id outside [0, vocab_size) in a batch passed to sb_encoder_forward since the last check");
     return SB_ERR_INPUT;
   }
   return SB_OK;
@@ -360,6 +428,51 @@ int sb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C
   g.M = M; g.N = N; g.K = K; g.epi = epi;
   g.cta_group = cta_group == 1 ? 1 : 2;
   g.allow_skinny = (cta_group == 0);  // 0 = automatic: M <= 64 may take the weight-streaming path
+  int dev = 0, sms = 0;
+  SB_CUDA_CHECK(cudaGetDevice(&dev));
+  SB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  g.num_sms = sms;
+  return gemm_bf16(g, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sb_fold_layernorm(const void* W, const float* bias, const float* gamma, const float* beta, int32_t N, int32_t K,
+                      void* Wf, float* colsum, float* bias_f, void* stream) {
+  if (!W || !bias || !gamma || !beta || !Wf || !colsum || !bias_f || N <= 0 || K <= 0) {
+    set_last_error("sb_fold_layernorm: bad argument");
+    return SB_ERR_INVALID;
+  }
+  return fold_layernorm_weights(reinterpret_cast<const __nv_bfloat16*>(W), bias, gamma, beta, N, K,
+                                reinterpret_cast<__nv_bfloat16*>(Wf), colsum, bias_f, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sb_gemm_ln_consumer(const void* A, int64_t lda, const void* Wf, int64_t ldw, void* C, int64_t ldc, const float* bias_f,
+                        const float* colsum, const float* stats, float eps, int32_t M, int32_t N, int32_t K, int32_t relu,
+                        void* stream) {
+  if (!A || !Wf || !C || !bias_f || !colsum || !stats) { set_last_error("sb_gemm_ln_consumer: null pointer"); return SB_ERR_INVALID; }
+  GemmArgs g;
+  g.A = reinterpret_cast<const __nv_bfloat16*>(A); g.lda = lda;
+  g.W = reinterpret_cast<const __nv_bfloat16*>(Wf); g.ldw = ldw;
+  g.C = C; g.ldc = ldc; g.out_fp32 = 0; g.bias = bias_f; g.residual = nullptr; g.ldr = 0;
+  g.M = M; g.N = N; g.K = K; g.epi = relu ? EPI_BIAS_RELU : EPI_BIAS;
+  g.cta_group = 2;
+  g.lf.stats_in = stats; g.lf.colsum = colsum; g.lf.chunks = K / 256; g.lf.eps = eps;
+  int dev = 0, sms = 0;
+  SB_CUDA_CHECK(cudaGetDevice(&dev));
+  SB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  g.num_sms = sms;
+  return gemm_bf16(g, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sb_gemm_residual_stats(const void* A, int64_t lda, const void* W, int64_t ldw, float* x, int64_t ldx, const float* bias,
+                           void* h_out, int64_t ldh, float* stats_out, int32_t M, int32_t N, int32_t K, void* stream) {
+  if (!A || !W || !x || !bias || !h_out || !stats_out) { set_last_error("sb_gemm_residual_stats: null pointer"); return SB_ERR_INVALID; }
+  GemmArgs g;
+  g.A = reinterpret_cast<const __nv_bfloat16*>(A); g.lda = lda;
+  g.W = reinterpret_cast<const __nv_bfloat16*>(W); g.ldw = ldw;
+  g.C = x; g.ldc = ldx; g.out_fp32 = 1; g.bias = bias; g.residual = x; g.ldr = ldx;
+  g.M = M; g.N = N; g.K = K; g.epi = EPI_BIAS_RESIDUAL_STATS;
+  g.cta_group = 2;
+  g.lf.h_out = reinterpret_cast<__nv_bfloat16*>(h_out); g.lf.ldh = ldh; g.lf.stats_out = stats_out;
   int dev = 0, sms = 0;
   SB_CUDA_CHECK(cudaGetDevice(&dev));
   SB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

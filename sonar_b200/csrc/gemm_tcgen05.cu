@@ -12,8 +12,9 @@
 //   buffered (2 x 256 = all 512 columns) so the epilogue of tile i overlaps the
 //   mainloop of tile i+1.  cta_group::1 variant: 128 x 256 x 64 per CTA.
 // Warp roles (256 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM alloc/dealloc,
-//   w3 idle, w4-7 epilogue (TMEM -> regs -> bias/ReLU/residual -> swizzled smem -> TMA store).  With the optional
-//   fused LayerNorm (LnFuse, accumulate epilogue only) warps 2 and 3 normalise completed 128-row blocks out of L2.
+//   w3 idle, w4-7 epilogue (TMEM -> regs -> bias/ReLU/residual -> swizzled smem -> TMA store).
+// LayerNorm folding (LnFold, sonar_b200_internal.h): a consumer GEMM scales its accumulator rows by the LayerNorm
+// statistics of its input; the residual-stream GEMMs emit those statistics and the bf16 copy of the stream.
 // Operand smem layout: K-major, 128-byte rows, SWIZZLE_128B (TMA writes it, UMMA reads it).
 
 #include "common.cuh"
@@ -106,8 +107,7 @@ __global__ void __launch_bounds__(256, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                          const __grid_constant__ CUtensorMap tm_c, const float* __restrict__ bias,
                          const OutT* residual, long long ldr, int M, int N, int K, float* __restrict__ cand_val,
-                         int* __restrict__ cand_idx, float* __restrict__ lse_part, int n_chunks, const LnFuse ln,
-                         const float* ln_x, long long ln_ldx) {
+                         int* __restrict__ cand_idx, float* __restrict__ lse_part, int n_chunks, const LnFold lf) {
   constexpr bool kSweep = (kEpi == EPI_TOPK);
   using Cfg = GemmCfg<kCtaGroup>;
   extern __shared__ uint8_t smem_raw[];
@@ -120,7 +120,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  [[maybe_unused]] const bool ln_on = (kEpi == EPI_BIAS_ACCUM) && ln.out != nullptr;
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -234,14 +233,45 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     [[maybe_unused]] float tv[KC];
     [[maybe_unused]] int ti[KC];
     [[maybe_unused]] float run_max = -CUDART_INF_F, run_sum = 0.f;  // online log-sum-exp of the row (optional)
-    [[maybe_unused]] int ln_pending_blk = -1;  // store thread: 128-row block whose reduce-adds are still in flight
     for (uint32_t iter = 0; sched.next(m_blk, n_blk, chunk, first_in_item, last_in_item); ++iter) {
       const int m0 = m_blk * tile_m + int(cta_rank) * Cfg::BLOCK_M;
       const int n0 = n_blk * Cfg::BLOCK_N;
       const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
+      const int grow = m0 + row_in_tile;
+      // ---- LayerNorm folding, consumer side: (mean, rstd) of this thread's input row from its 256-column partials ----
+      [[maybe_unused]] float ln_mean = 0.f, ln_rstd = 1.f;
+      [[maybe_unused]] bool fold_in = false;
+      if constexpr (kEpi == EPI_BIAS || kEpi == EPI_BIAS_RELU) {
+        fold_in = lf.stats_in != nullptr;
+        if (fold_in && grow < M) {
+          const float2* sp = reinterpret_cast<const float2*>(lf.stats_in) + (long long)grow * lf.chunks;
+          float2 part[4];
+          float msum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < lf.chunks) { part[i] = sp[i]; msum += part[i].x; }
+          ln_mean = msum / float(lf.chunks);
+          float m2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < lf.chunks) { const float dm = part[i].x - ln_mean; m2 += part[i].y + 256.f * dm * dm; }
+          ln_rstd = 1.0f / sqrtf(m2 / float(256 * lf.chunks) + lf.eps);
+        }
+      }
+      // ---- producer side: the first 32 residual columns of this thread's row are fetched while the MMAs still run ----
+      [[maybe_unused]] float4 rnext[8];
+      [[maybe_unused]] float st_n = 0.f, st_mean = 0.f, st_m2 = 0.f;
+      if constexpr (kEpi == EPI_BIAS_RESIDUAL_STATS) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) rnext[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (grow < M) {
+          const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(residual) + (long long)grow * ldr + n0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) rnext[q] = rp[q];
+        }
+      }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const int grow = m0 + row_in_tile;
       if constexpr (kEpi == EPI_TOPK) {
         // ---- running per-row top-KC over the whole sweep of n tiles (no C matrix is ever written) ----
         if (first_in_item) {
@@ -323,13 +353,63 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           tmem_ld_wait();
           const int gcol = n0 + col_in_tile;
           float f[32];
+          if (fold_in) {  // rstd * (x.W'^T - mean * c) + b'   (LnFold)
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + gcol + j));
-            f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
-            f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-            f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + gcol + j));
+              const float4 c4 = __ldg(reinterpret_cast<const float4*>(lf.colsum + gcol + j));
+              f[j + 0] = fmaf(ln_rstd, fmaf(-ln_mean, c4.x, __uint_as_float(v[j + 0])), b4.x);
+              f[j + 1] = fmaf(ln_rstd, fmaf(-ln_mean, c4.y, __uint_as_float(v[j + 1])), b4.y);
+              f[j + 2] = fmaf(ln_rstd, fmaf(-ln_mean, c4.z, __uint_as_float(v[j + 2])), b4.z);
+              f[j + 3] = fmaf(ln_rstd, fmaf(-ln_mean, c4.w, __uint_as_float(v[j + 3])), b4.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + gcol + j));
+              f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
+              f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+              f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+              f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            }
+          }
+          if constexpr (kEpi == EPI_BIAS_RESIDUAL_STATS) {
+            // x_new = x + (acc + bias): the residual chunk was fetched one chunk ahead; fetch the next one now
+            float4 rcur[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) rcur[q] = rnext[q];
+            if (c + 1 < NUM_CHUNKS && grow < M) {
+              const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(residual) +
+                                                                 (long long)grow * ldr + gcol + CHUNK_COLS);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) rnext[q] = rp[q];
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              f[4 * q + 0] += rcur[q].x; f[4 * q + 1] += rcur[q].y; f[4 * q + 2] += rcur[q].z; f[4 * q + 3] += rcur[q].w;
+            }
+            // running (mean, M2) of the row over this tile's columns: two-pass inside the chunk, Chan merge across chunks
+            float cs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cs += f[j];
+            const float cm = cs * (1.0f / 32.0f);
+            float cq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const float dv = f[j] - cm; cq = fmaf(dv, dv, cq); }
+            const float n_new = st_n + 32.f;
+            const float dlt = cm - st_mean;
+            st_mean = fmaf(dlt, 32.f / n_new, st_mean);
+            st_m2 += cq + dlt * dlt * (st_n * 32.f / n_new);
+            st_n = n_new;
+            if (grow < M) {  // bf16 copy of the new residual stream: the A operand of the next (LayerNorm-folded) GEMM
+              uint4* hp = reinterpret_cast<uint4*>(lf.h_out + (long long)grow * lf.ldh + gcol);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                hp[q] = make_uint4(pack_bf16x2(f[8 * q], f[8 * q + 1]), pack_bf16x2(f[8 * q + 2], f[8 * q + 3]),
+                                   pack_bf16x2(f[8 * q + 4], f[8 * q + 5]), pack_bf16x2(f[8 * q + 6], f[8 * q + 7]));
+              if (c == NUM_CHUNKS - 1)
+                reinterpret_cast<float2*>(lf.stats_out)[(long long)grow * num_n_tiles + n_blk] = make_float2(st_mean, st_m2);
+            }
           }
           if constexpr (kEpi == EPI_BIAS_RELU) {
 #pragma unroll
@@ -398,76 +478,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           else
             tma_store_2d(&tm_c, smem_cd + cd_stage * Cfg::CD_STAGE_BYTES, n0 + c * CHUNK_COLS, m0);
           tma_store_commit();
-          if constexpr (kEpi == EPI_BIAS_ACCUM) {
-            if (ln_on) {
-              // publish the PREVIOUS tile's rows: with at most the 4 groups of this tile pending, all of its
-              // reduce-adds have completed; release them to the GPU and count the n-tile in
-              if (c == 3 && ln_pending_blk >= 0) {
-                tma_store_wait_all<4>();
-                __threadfence();
-                atomicAdd(&ln.counters[ln_pending_blk], 1);
-                ln_pending_blk = -1;
-              }
-              if (c == NUM_CHUNKS - 1) ln_pending_blk = m0 >> 7;
-            }
-          }
         }
         cd_stage ^= 1;
       }
     }
-    if (ew == 0 && lane == 0) {
-      tma_store_wait_all<0>();
-      if constexpr (kEpi == EPI_BIAS_ACCUM) {
-        if (ln_on) {
-          if (ln_pending_blk >= 0) {
-            __threadfence();
-            atomicAdd(&ln.counters[ln_pending_blk], 1);
-          }
-        }
-      }
-    }
-  } else if (kEpi == EPI_BIAS_ACCUM && ln_on) {
-    // ===================== fused LayerNorm (warps 2 and 3, otherwise idle) =====================
-    // Every warp role walks an identical copy of the tile schedule.  The CTA whose tile has n_blk == m_blk % num_n_tiles
-    // owns that 128-row block (ownership rotates over the n index so the blocks spread evenly over the CTAs); warp 2
-    // normalises its rows 0..63, warp 3 rows 64..127, once the block's arrival counter says every n-tile's
-    // reduce-add has completed.  Nothing ever waits on these warps, so the wait cannot deadlock.
-    const int nvec = N / 128;
-    while (sched.next(m_blk, n_blk, chunk, first_in_item, last_in_item)) {
-      const int m0 = m_blk * tile_m + int(cta_rank) * Cfg::BLOCK_M;
-      if (n_blk != m_blk % num_n_tiles || m0 >= M) continue;
-      const int blk = m0 >> 7;
-      const int r0 = m0 + (warp_idx - 2) * 64;
-      const long long t0 = clock64();
-      for (;;) {  // acquire pairs with the store threads' fence + add
-        int cnt;
-        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(cnt) : "l"(ln.counters + blk) : "memory");
-        if (cnt >= num_n_tiles) break;
-        __nanosleep(128);
-        if (clock64() - t0 > SB_MBAR_TIMEOUT_CYCLES) { printf("sonar_b200: fused-LN counter timeout\n"); __trap(); }
-      }
-#pragma unroll 1
-      for (int r = 0; r < 64; r += 4) {
-        float4 v[4][kMaxVec];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (r0 + r + q < M) load_row<true>(ln_x + (long long)(r0 + r + q) * ln_ldx, nvec, lane, v[q]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int row = r0 + r + q;
-          if (row < M) {
-            normalize_row(v[q], nvec, lane, N, ln.gamma, ln.beta, ln.eps);
-            uint2* yrow = reinterpret_cast<uint2*>(ln.out + (long long)row * ln.ldo);
-#pragma unroll
-            for (int i = 0; i < kMaxVec; ++i)
-              if (i < nvec) yrow[i * 32 + lane] = make_uint2(pack_bf16x2(v[q][i].x, v[q][i].y), pack_bf16x2(v[q][i].z, v[q][i].w));
-          }
-        }
-      }
-      // the second of the block's two halves to finish re-arms the counter for the next launch
-      __syncwarp();
-      if (lane == 0 && atomicAdd(&ln.counters[blk], 16) >= num_n_tiles + 16) ln.counters[blk] = 0;
-    }
+    if (ew == 0 && lane == 0) tma_store_wait_all<0>();
   }
 
   // ===================== teardown =====================
@@ -529,7 +544,7 @@ template <int kCtaGroup, int kEpi, typename OutT>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const float* bias,
                        const void* residual, long long ldr, int M, int N, int K, int num_sms, cudaStream_t stream,
                        float* cand_val = nullptr, int* cand_idx = nullptr, float* lse_part = nullptr,
-                       int n_chunks = 1, const LnFuse& ln = LnFuse(), const float* ln_x = nullptr, long long ln_ldx = 0) {
+                       int n_chunks = 1, const LnFold& lf = LnFold()) {
   using Cfg = GemmCfg<kCtaGroup>;
   auto kern = gemm_bf16_tcgen05_kernel<kCtaGroup, kEpi, OutT>;
   static bool attr_set[64] = {};
@@ -556,16 +571,8 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, bias, reinterpret_cast<const OutT*>(residual), ldr, M, N, K,
-                                   cand_val, cand_idx, lse_part, n_chunks, ln, ln_x, ln_ldx));
+                                   cand_val, cand_idx, lse_part, n_chunks, lf));
   return 0;
-}
-
-bool gemm_ln_fusable(int M, int N, int cta_group, int num_sms) {
-  const int cg = (cta_group == 1) ? 1 : 2;
-  if (M <= 64 || N % 256 != 0 || N > 128 * kMaxVec) return false;
-  (void)cg;
-  (void)num_sms;
-  return true;
 }
 
 // Number of n-chunks the top-k sweep is split into so that (m-blocks x chunks) fills the clusters.
@@ -613,7 +620,8 @@ int gemm_bf16_topk(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W
 
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   if (g.M <= 0) return 0;
-  if (g.allow_skinny && gemm_skinny_eligible(g)) return gemm_skinny(g, stream);
+  if (g.allow_skinny && gemm_skinny_eligible(g) && !g.lf.stats_in && g.epi != EPI_BIAS_RESIDUAL_STATS)
+    return gemm_skinny(g, stream);
   if (g.N % 256 != 0 || g.K % 64 != 0 || g.K <= 0 || g.N <= 0) {
     set_last_error("gemm_bf16: need N %% 256 == 0 and K %% 64 == 0 (got M=%d N=%d K=%d)", g.M, g.N, g.K);
     return -1;
@@ -641,16 +649,28 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     return -1;
   }
 
-  if (g.ln.out != nullptr) {
-    if (epi != EPI_BIAS_ACCUM || !gemm_ln_fusable(g.M, g.N, cg, sms) || !g.ln.counters || !g.ln.gamma || !g.ln.beta) {
-      set_last_error("gemm_bf16: fused LayerNorm needs the in-place fp32 accumulate epilogue over full rows (M=%d N=%d)", g.M, g.N);
+  // ---- LayerNorm folding (LnFold) ----
+  if (g.lf.stats_in != nullptr) {  // consumer
+    if ((epi != EPI_BIAS && epi != EPI_BIAS_RELU) || !g.lf.colsum || g.lf.chunks < 1 || g.lf.chunks > 4 ||
+        g.K != 256 * g.lf.chunks) {
+      set_last_error("gemm_bf16: folded LayerNorm input needs a bias / bias+ReLU epilogue and K = 256 * chunks <= 1024 "
+                     "(K=%d chunks=%d)", g.K, g.lf.chunks);
       return -1;
     }
+  }
+  if (epi == EPI_BIAS_RESIDUAL_STATS) {  // producer
+    if (!g.out_fp32 || !g.residual || !g.lf.h_out || !g.lf.stats_out || g.lf.ldh < g.N) {
+      set_last_error("gemm_bf16: the residual+statistics epilogue needs fp32 C, a residual, h_out and stats_out");
+      return -1;
+    }
+  } else if (g.lf.h_out != nullptr || g.lf.stats_out != nullptr) {
+    set_last_error("gemm_bf16: h_out / stats_out are outputs of EPI_BIAS_RESIDUAL_STATS only");
+    return -1;
   }
 
 #define SB_DISPATCH(CG, EPI, T)                                                                                   \
   return launch_inst<CG, EPI, T>(ta, tb, tc, g.bias, g.residual, g.ldr, g.M, g.N, g.K, sms, stream, nullptr, nullptr, \
-                                 nullptr, 1, g.ln, reinterpret_cast<const float*>(g.C), g.ldc)
+                                 nullptr, 1, g.lf)
 #define SB_DISPATCH_EPI(CG, T)                                              \
   switch (epi) {                                                            \
     case EPI_BIAS: SB_DISPATCH(CG, EPI_BIAS, T);                            \
@@ -658,6 +678,7 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     case EPI_BIAS_SILU: SB_DISPATCH(CG, EPI_BIAS_SILU, T);                  \
     case EPI_BIAS_RESIDUAL: SB_DISPATCH(CG, EPI_BIAS_RESIDUAL, T);          \
     case EPI_BIAS_ACCUM: SB_DISPATCH(CG, EPI_BIAS_ACCUM, float);            \
+    case EPI_BIAS_RESIDUAL_STATS: SB_DISPATCH(CG, EPI_BIAS_RESIDUAL_STATS, float); \
     default: set_last_error("gemm_bf16: bad epilogue %d", epi); return -1;  \
   }
   if (cg == 2) {

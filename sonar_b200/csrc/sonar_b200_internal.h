@@ -14,7 +14,9 @@ namespace sb {
 // Bit-identical to EPI_BIAS_RESIDUAL: both compute fl32(x + fl32(acc + bias)).
 // EPI_TOPK (internal): no C at all -- the epilogue keeps a running per-row top-k of the product (xsim mining).
 // EPI_BIAS_SILU: x*sigmoid(x) (the Conformer's swish FFN activation)
-enum EpiMode { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_RESIDUAL = 2, EPI_BIAS_ACCUM = 3, EPI_TOPK = 4, EPI_BIAS_SILU = 5 };
+// EPI_BIAS_RESIDUAL_STATS (internal): fp32 C = residual + A.W^T + bias, plus the bf16 copy and row statistics of LnFold
+enum EpiMode { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_RESIDUAL = 2, EPI_BIAS_ACCUM = 3, EPI_TOPK = 4, EPI_BIAS_SILU = 5,
+               EPI_BIAS_RESIDUAL_STATS = 6 };
 constexpr int kTopkCandidates = 16;  // bf16-similarity candidates per row handed to the exact fp64 re-rank
 enum PoolMode { POOL_MAX = 1, POOL_MEAN = 2, POOL_LAST = 3 };  // = reference `Pooling` enum values (model.py:23-27)
 
@@ -30,17 +32,22 @@ inline bool first_use_on_device(bool (&flags)[64]) {
   return true;
 }
 
-// Optional LayerNorm fused behind an in-place fp32 accumulate GEMM (x += A.W^T + b over FULL rows, N == D): the idle
-// warps of the GEMM CTAs normalise each 128-row block as soon as its last n-tile has been reduced into x -- while those
-// rows are still in L2 -- and write the bf16 rows the next GEMM consumes.  `counters` is one int per 128-row block,
-// zero on entry, left zero on exit.  Same arithmetic as layernorm_bf16 (bitwise identical result).
-struct LnFuse {
-  const float* gamma = nullptr;
-  const float* beta = nullptr;
+// LayerNorm FOLDED into the GEMMs on either side of it (the text encoder's default schedule; no LayerNorm kernel runs).
+//   LN(x) . W^T + b  =  rstd * (x . W'^T  -  mean * c)  +  b'      with  W' = W diag(gamma),  c[n] = sum_k W'[n,k],
+//                                                                        b' = b + W beta          (prepared once at create)
+// so the GEMM that CONSUMES a LayerNorm runs on the un-normalised bf16 copy of the residual stream and applies the
+// per-row (mean, rstd) in its epilogue (`stats_in`, `colsum`), and the GEMM that PRODUCES the residual stream
+// (EPI_BIAS_RESIDUAL_STATS) emits, next to x, that bf16 copy (`h_out`) and per-row partial statistics (`stats_out`):
+// one (mean, M2) pair per 256-column tile of the row, merged by the consumer with Chan's formula (no E[x^2]-mean^2
+// cancellation).  Saves the LayerNorm kernel's read of x and one of the two passes over h per LayerNorm.
+struct LnFold {
+  const float* stats_in = nullptr;  // [M, chunks, 2] (mean, M2) of each 256-column chunk of the consumer's input rows
+  const float* colsum = nullptr;    // [N] c[n]
+  int chunks = 0;                   // K / 256 of the LayerNorm the consumer folds
   float eps = 0.f;
-  __nv_bfloat16* out = nullptr;  // [M, D] bf16, leading dimension ldo; nullptr = no fusion
-  long long ldo = 0;
-  int* counters = nullptr;
+  __nv_bfloat16* h_out = nullptr;   // producer: [M, N] bf16 copy of the new residual stream, leading dimension ldh
+  long long ldh = 0;
+  float* stats_out = nullptr;       // producer: [M, N / 256, 2]
 };
 
 struct GemmArgs {
@@ -58,7 +65,7 @@ struct GemmArgs {
   int epi;        // EpiMode
   int cta_group;  // 1 or 2
   int num_sms;    // 0 -> 148
-  LnFuse ln;      // only with the in-place fp32 accumulate epilogue
+  LnFold lf;      // LayerNorm folding (see above); default = off
   // Opt-in to the weight-streaming path for M <= 64 (gemm_skinny.cu).  It sums K in a different order than the tcgen05
   // tiles, so a caller that promises results independent of the batch size across the M = 64 boundary (the text
   // encoder: bitwise batch-composition invariance) leaves it off; the decoder step and the speech pooler turn it on.
@@ -66,8 +73,6 @@ struct GemmArgs {
 };
 
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
-// true if gemm_bf16 can run `ln` fused for this shape (otherwise the caller launches layernorm_bf16 itself)
-bool gemm_ln_fusable(int M, int N, int cta_group, int num_sms);
 
 // M <= 64 rows: weight-streaming mma.sync path (gemm_skinny.cu); gemm_bf16 dispatches to it when eligible
 bool gemm_skinny_eligible(const GemmArgs& g);
@@ -84,7 +89,12 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long ro
 // x[cu[b]+t, :] = E[ids[b,t], :] * scale + pos[t, :]   (fp32 out)
 int embed_tokens(const int64_t* ids, long long ids_stride, const int32_t* cu_seqlens, int B, int S,
                  const __nv_bfloat16* embed, long long vocab, const float* pos_table, int pos_rows, int D, float scale,
-                 float* x, int* err_flag, cudaStream_t stream, int pos_offset = 0);
+                 float* x, int* err_flag, cudaStream_t stream, int pos_offset = 0, __nv_bfloat16* h_out = nullptr,
+                 float* stats_out = nullptr);  // h_out / stats_out: LnFold producer outputs (bf16 copy + row statistics)
+
+// LnFold weight preparation: Wf = bf16(W diag(gamma)), colsum[n] = sum_k Wf[n,k], bias_f = bias + W beta
+int fold_layernorm_weights(const __nv_bfloat16* W, const float* bias, const float* gamma, const float* beta, int N, int K,
+                           __nv_bfloat16* Wf, float* colsum, float* bias_f, cudaStream_t stream);
 
 // y = LN(x) * gamma + beta, fp32 in, bf16 out, one warp per row
 int layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, __nv_bfloat16* y, long long T,
@@ -95,7 +105,7 @@ int layernorm_dual(const float* x, const float* gamma, const float* beta, float 
                    long long T, int D, cudaStream_t stream);
 
 // softmax(q k^T / sqrt(64)) v over packed sequences; qkv [T, 3*D] bf16 (q | k | v), out [T, D] bf16
-// impl: 0 = auto (tcgen05 kernel when max_len <= 128, mma.sync flash kernel otherwise), 1 = mma.sync, 2 = tcgen05
+// impl: 0 = auto (= 2), 1 = mma.sync flash kernel (tests / A-B only), 2 = tcgen05 (any length)
 int attention_packed(const __nv_bfloat16* qkv, const int32_t* cu_seqlens, int B, int max_len, int H,
                      long long total_tokens, int impl, int num_sms, __nv_bfloat16* out, cudaStream_t stream);
 int attention_packed_tc(const __nv_bfloat16* qkv, const int32_t* cu_seqlens, int B, int H, long long total_tokens,

@@ -164,7 +164,21 @@ class TextToEmbeddingModelPipeline(torch.nn.Module):
                 yield to_sequence_batch(ids, lens, ragged, self.device if on_cuda else CPU)
 
         out_device = torch.device(target_device) if target_device is not None else self.device
-        pipeline: Iterable = (self.model(b).sentence_embeddings.to(out_device) for b in prefetch(batches(), 2))
+
+        def run_model() -> Iterable[Tensor]:
+            # One batch of lag between launching a batch and collecting its embeddings: batch k+1 is already queued on the
+            # GPU when the host blocks on the device->host copy of batch k, so the GPU never idles between batches (the
+            # reference's `.map(self.model)` + `.to(target_device)` per batch leaves that gap).
+            pending = None
+            for b in prefetch(batches(), 2):
+                cur = _PendingEmbeddings(self.model(b).sentence_embeddings, out_device)
+                if pending is not None:
+                    yield pending.get()
+                pending = cur
+            if pending is not None:
+                yield pending.get()
+
+        pipeline: Iterable = run_model()
         if progress_bar:
             pipeline = add_progress_bar(pipeline, inputs=input,
                                         batch_size=batch_size if batch_max_tokens is None else None)
@@ -190,6 +204,26 @@ class TextToEmbeddingModelPipeline(torch.nn.Module):
             reversed_index = torch.argsort(sorting_index)
             sentence_embeddings = sentence_embeddings[reversed_index.to(sentence_embeddings.device)]
         return sentence_embeddings
+
+
+class _PendingEmbeddings:
+    """Embeddings of one batch on their way to `device`: a device->host copy goes through pinned memory without blocking the
+    launching thread; `get()` waits for it."""
+
+    def __init__(self, emb: Tensor, device: torch.device) -> None:
+        self._event = None
+        if emb.is_cuda and device.type == "cpu":
+            self._out = torch.empty(emb.shape, dtype=emb.dtype, pin_memory=True)
+            self._out.copy_(emb, non_blocking=True)
+            self._event = torch.cuda.Event()
+            self._event.record(torch.cuda.current_stream(emb.device))
+        else:
+            self._out = emb.to(device, non_blocking=True)
+
+    def get(self) -> Tensor:
+        if self._event is not None:
+            self._event.synchronize()
+        return self._out
 
 
 def _load_decoder_card(name: str, device: Device) -> B200TextDecoderModel:

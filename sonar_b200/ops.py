@@ -75,6 +75,48 @@ def cu_seqlens_of(seq_lens) -> Tensor:
 ATTENTION_IMPLS = {"auto": 0, "mma_sync": 1, "tcgen05": 2}
 
 
+def fold_layernorm(w: Tensor, bias: Tensor, gamma: Tensor, beta: Tensor):
+    """LayerNorm folding, weight side: -> (Wf bf16 [N,K], colsum fp32 [N], bias_f fp32 [N])."""
+    _need_cuda(w, bias, gamma, beta)
+    assert w.dtype == torch.bfloat16 and w.is_contiguous()
+    n, k = w.shape
+    wf = torch.empty_like(w)
+    colsum = torch.empty((n,), dtype=torch.float32, device=w.device)
+    bias_f = torch.empty((n,), dtype=torch.float32, device=w.device)
+    rc = _lib.load().sb_fold_layernorm(w.data_ptr(), bias.data_ptr(), gamma.data_ptr(), beta.data_ptr(), n, k, wf.data_ptr(),
+                                       colsum.data_ptr(), bias_f.data_ptr(), _stream())
+    _lib.check(rc, "sb_fold_layernorm")
+    return wf, colsum, bias_f
+
+
+def gemm_residual_stats(a: Tensor, w: Tensor, bias: Tensor, x: Tensor):
+    """x += a . w^T + bias in place (fp32); -> (h = bf16(x) [M,N], stats fp32 [M, N/256, 2])."""
+    _need_cuda(a, w, bias, x)
+    m, k = a.shape
+    n = w.shape[0]
+    assert x.shape == (m, n) and x.dtype == torch.float32 and x.is_contiguous() and n % 256 == 0
+    h = torch.empty((m, n), dtype=torch.bfloat16, device=a.device)
+    stats = torch.empty((m, n // 256, 2), dtype=torch.float32, device=a.device)
+    rc = _lib.load().sb_gemm_residual_stats(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), x.data_ptr(), n,
+                                            bias.data_ptr(), h.data_ptr(), n, stats.data_ptr(), m, n, k, _stream())
+    _lib.check(rc, "sb_gemm_residual_stats")
+    return h, stats
+
+
+def gemm_ln_consumer(a: Tensor, wf: Tensor, bias_f: Tensor, colsum: Tensor, stats: Tensor, eps: float = 1e-5,
+                     relu: bool = False) -> Tensor:
+    """bf16 [M,N] = [relu](rstd * (a . wf^T - mean * colsum) + bias_f), (mean, rstd) merged from stats [M, K/256, 2]."""
+    _need_cuda(a, wf, bias_f, colsum, stats)
+    m, k = a.shape
+    n = wf.shape[0]
+    out = torch.empty((m, n), dtype=torch.bfloat16, device=a.device)
+    rc = _lib.load().sb_gemm_ln_consumer(a.data_ptr(), a.stride(0), wf.data_ptr(), wf.stride(0), out.data_ptr(), n,
+                                         bias_f.data_ptr(), colsum.data_ptr(), stats.data_ptr(), eps, m, n, k,
+                                         1 if relu else 0, _stream())
+    _lib.check(rc, "sb_gemm_ln_consumer")
+    return out
+
+
 def attention(qkv: Tensor, cu_seqlens: Tensor, max_len: int, num_heads: int, impl: str = "auto") -> Tensor:
     """Packed bidirectional MHA: qkv bf16 [T, 3*64*H] -> bf16 [T, 64*H]."""
     _need_cuda(qkv, cu_seqlens)

@@ -22,6 +22,7 @@ from enum import Enum
 from pathlib import Path
 from typing import Dict, List, Optional, Union
 
+import numpy as np
 import torch
 from torch import Tensor
 
@@ -138,8 +139,11 @@ class B200TextEncoderModel(torch.nn.Module):
     """SONAR text encoder (24-layer pre-LN Transformer + final LN + pooling) on sm_100a kernels."""
 
     def __init__(self, config: SonarTextEncoderConfig, state_dict: Dict[str, Tensor],
-                 device: Union[str, torch.device] = "cuda", *, cta_group: int = 2) -> None:
+                 device: Union[str, torch.device] = "cuda", *, cta_group: int = 2, ln_fold: bool = True) -> None:
+        """``ln_fold`` (default on): the engine folds every encoder-layer LayerNorm into the GEMMs around it (see
+        ``SbEncoderConfig.ln_fold`` in ``include/sonar_b200.h``); ``False`` runs the separate LayerNorm kernels."""
         super().__init__()
+        self.ln_fold = bool(ln_fold)
         _check_supported(config)
         self.config = config
         self.model_dim = config.model_dim
@@ -191,7 +195,8 @@ class B200TextEncoderModel(torch.nn.Module):
         cfg_c = _lib.SbEncoderConfig(
             model_dim=d, num_layers=L, num_heads=config.num_encoder_attn_heads, ffn_inner_dim=config.ffn_inner_dim,
             vocab_size=config.vocab_info.size, pos_rows=max_len, pooling=self.pooling.value, ln_eps=1e-5,
-            embed_scale=1.0 if config.no_scale_embedding else math.sqrt(d), cta_group=cta_group, num_sms=0)
+            embed_scale=1.0 if config.no_scale_embedding else math.sqrt(d), cta_group=cta_group, num_sms=0,
+            ln_fold=1 if ln_fold else 0)
         layers_c = (_lib.SbLayerWeights * max(L, 1))()
         for i, bufs in enumerate(self._layer_bufs):
             for k, v in bufs.items():
@@ -252,9 +257,9 @@ class B200TextEncoderModel(torch.nn.Module):
         n, s = seqs.shape
         pm = batch.padding_mask
         if pm is not None:
-            lens_host = pm.seq_lens_host
-            lens_c = (C.c_int32 * n)(*lens_host)
-            tokens = int(sum(lens_host))
+            lens_np = np.ascontiguousarray(pm.seq_lens_host, dtype=np.int32)  # one vectorised conversion, no per-item Python
+            lens_c = lens_np.ctypes.data_as(C.POINTER(C.c_int32))
+            tokens = int(lens_np.sum(dtype=np.int64))
         else:
             lens_c = None
             tokens = n * s

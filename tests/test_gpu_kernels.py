@@ -140,8 +140,11 @@ def test_layernorm(ops, cuda_device, t, d):
 
 
 ATTN_CASES = [([128] * 4, "tcgen05"), ([128] * 4, "mma_sync"), ([1, 2, 17, 64, 65, 128], "tcgen05"),
-              ([1, 2, 17, 64, 65, 128], "mma_sync"), ([200, 129, 514], "auto"), ([33], "auto"),
-              ([128] * 700 + [5, 77, 128, 31] * 20, "tcgen05")]  # > 2 x 148 CTAs worth of items: persistent loop
+              ([1, 2, 17, 64, 65, 128], "mma_sync"), ([200, 129, 514], "auto"), ([200, 129, 514], "mma_sync"), ([33], "auto"),
+              ([128] * 700 + [5, 77, 128, 31] * 20, "tcgen05"),  # > 2 x 148 CTAs worth of items: persistent loop
+              # multi-tile sentences (online softmax across 128-key tiles) mixed with short ones, uneven item costs per CTA
+              ([514, 1, 256, 257, 128, 129, 383, 16, 512, 300] * 4, "tcgen05"),
+              ([130] * 40 + [7] * 5, "tcgen05")]
 
 
 @pytest.mark.parametrize("lens,impl", ATTN_CASES)
@@ -169,16 +172,17 @@ def test_attention_vs_sdpa(ops, cuda_device, lens, impl):
         start += n
 
 
-def test_attention_impls_agree_and_tc_rejects_long(ops, cuda_device):
+def test_attention_impls_agree(ops, cuda_device):
     h, d = 16, 1024
-    lens = [128, 90, 3]
+    lens = [128, 90, 3, 300, 514]
     qkv = _rand((sum(lens), 3 * d), 1.0, 21, cuda_device, torch.bfloat16)
     cu = ops.cu_seqlens_of(lens).to(cuda_device)
-    a = ops.attention(qkv, cu, 128, h, impl="tcgen05").float()
-    b = ops.attention(qkv, cu, 128, h, impl="mma_sync").float()
+    a = ops.attention(qkv, cu, 514, h, impl="tcgen05").float()
+    b = ops.attention(qkv, cu, 514, h, impl="mma_sync").float()
     torch.testing.assert_close(a, b, rtol=2e-2, atol=2e-2)
-    with pytest.raises(ValueError):
-        ops.attention(qkv, cu, 200, h, impl="tcgen05")
+    # each sentence's rows depend on that sentence only: bitwise equal when it is attended on its own
+    solo = ops.attention(qkv[128:218].contiguous(), ops.cu_seqlens_of([90]).to(cuda_device), 90, h, impl="tcgen05").float()
+    assert torch.equal(solo, a[128:218])
 
 
 def test_embed(ops, cuda_device):
@@ -251,3 +255,57 @@ def test_ln_pool_matches_torch(ops, cuda_device):
         torch.testing.assert_close(enc[i, :n], y[start : start + n], rtol=1e-5, atol=1e-5)
         assert float(enc[i, n:].abs().max()) == 0.0 if n < 128 else True
         start += n
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm folded into the GEMMs (LnFold): residual GEMM that emits statistics, consumer GEMM that applies them
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,k", [(1000, 1024), (4096, 8192), (300, 256), (77, 1024)])
+def test_gemm_residual_stats(ops, cuda_device, m, k):
+    """x += a.W^T + b (fp32, in place) with the bf16 copy and the per-256-column (mean, M2) partials of the NEW rows.
+    The rows get a large common offset (mean >> std) so a sum-of-squares style variance would visibly cancel."""
+    n = 1024
+    a = _rand((m, k), 1.0, 31, cuda_device, torch.bfloat16)
+    w = _rand((n, k), 1.0 / math.sqrt(k), 32, cuda_device, torch.bfloat16)
+    bias = _rand((n,), 0.5, 33, cuda_device)
+    x0 = _rand((m, n), 1.0, 34, cuda_device) + 40.0
+    x = x0.clone()
+    h, stats = ops.gemm_residual_stats(a, w, bias, x)
+    torch.cuda.synchronize()
+    ref = x0.double() + a.double() @ w.double().T + bias.double()
+    torch.testing.assert_close(x.double(), ref, rtol=1e-5, atol=2e-3)  # fp32 accumulate over K products + fp32 add
+    assert torch.equal(h, x.to(torch.bfloat16))                       # the bf16 copy is the rounding of what was stored
+    xc = x.double().view(m, n // 256, 256)
+    torch.testing.assert_close(stats[..., 0].double(), xc.mean(-1), rtol=1e-6, atol=1e-5)
+    m2 = ((xc - xc.mean(-1, keepdim=True)) ** 2).sum(-1)
+    torch.testing.assert_close(stats[..., 1].double(), m2, rtol=2e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("m,n,k", [(1000, 3072, 1024), (2048, 8192, 1024), (130, 512, 512)])
+def test_gemm_ln_consumer_equals_layernorm_then_linear(ops, cuda_device, relu, m, n, k):
+    """rstd * (bf16(x).Wf^T - mean * colsum) + bias_f  ==  LN(x; gamma, beta).W^T + b  (fp32 reference), with gamma/beta far
+    from (1, 0) and rows whose mean is comparable to their spread."""
+    x = _rand((m, k), 2.0, 41, cuda_device) + _rand((m, 1), 1.5, 42, cuda_device)
+    gamma = 1.0 + _rand((k,), 0.5, 43, cuda_device)
+    beta = _rand((k,), 0.5, 44, cuda_device)
+    w = _rand((n, k), 1.0 / math.sqrt(k), 45, cuda_device, torch.bfloat16)
+    bias = _rand((n,), 0.5, 46, cuda_device)
+    wf, colsum, bias_f = ops.fold_layernorm(w, bias, gamma, beta)
+    torch.testing.assert_close(wf.float(), (w.float() * gamma).to(torch.bfloat16).float(), rtol=0, atol=0)
+    torch.testing.assert_close(colsum, wf.float().sum(1), rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(bias_f, bias + w.float() @ beta, rtol=1e-5, atol=1e-4)
+    # statistics as a producer would emit them: (mean, M2) per 256-column chunk
+    xc = x.double().view(m, k // 256, 256)
+    stats = torch.stack([xc.mean(-1), ((xc - xc.mean(-1, keepdim=True)) ** 2).sum(-1)], -1).float().contiguous()
+    out = ops.gemm_ln_consumer(x.to(torch.bfloat16), wf, bias_f, colsum, stats, 1e-5, relu=relu)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (k,), gamma, beta, 1e-5) @ w.float().T + bias
+    if relu:
+        ref = torch.relu(ref)
+    # bf16 rounding of x (instead of LN(x)) and of W*gamma: same 2^-9 relative operand error as the unfused path, summed over
+    # K products of magnitude ~ |LN(x)| |W| -> a few 1e-2 absolute on outputs of magnitude ~1.5
+    err = (out.float() - ref).abs()
+    tol = ref.abs() * (1.5 * 2 ** -8) + 4e-2
+    assert bool((err <= tol).all()), f"max err {err.max().item()}"
+    assert float(err.mean()) < 6e-3
