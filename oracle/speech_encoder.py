@@ -12,9 +12,12 @@ the encoder output, then a bias-free 1024->1024 projection (``sonar_speech/facto
 
 The Conformer internals live in fairseq2's w2v-BERT ``600m`` config, which is not on disk: the block is
 restated from the identical-by-parameter-name HuggingFace ``SeamlessM4TConformerEncoderLayer`` and PINNED against it
-through ``tests/golden/conformer_layer_small.pt`` (``tests/golden/make_conformer_golden.py``).  The pooler and the
-frontend have no independent implementation offline: parity unpinned (the reference's golden
-``tests/integration_tests/data/speech_embedding.pt`` needs the downloaded checkpoint).
+through ``tests/golden/conformer_layer_small.pt`` (``tests/golden/make_conformer_golden.py``).  The pooler's POST-LN
+decoder-layer stack is PINNED against HuggingFace ``BartDecoderLayer`` (``tests/golden/pooler_layers_small.pt``,
+``make_pooler_golden.py``); the fbank features are pinned against torchaudio on the reference's own audio clips
+(``tests/test_reference_audio.py``).  What stays unpinned offline: the w2v-BERT ``600m`` hyper-parameters, the
+frame-stacking frontend and the pooler's one-token input (the reference's golden ``speech_embedding.pt`` needs the downloaded
+checkpoint; ``tests/test_reference_audio.py`` runs it when ``SONAR_B200_CHECKPOINT_DIR`` is set).
 """
 
 from __future__ import annotations
@@ -159,16 +162,22 @@ class OracleSpeechEncoder:
         x = x + 0.5 * ffn(lnorm(x, "ffn2_layer_norm"), "ffn2")
         return lnorm(x, "layer_norm")
 
-    # ------------------------------------------------------------------ attention pooler (POST-LN decoder layers)
-    def pooler(self, enc: Tensor, key_ok: Tensor) -> Tensor:
+    def pooler_query(self, batch: int) -> Tensor:
+        """The pooler's single decoder input: TransformerEmbeddingFrontend(embed, SinusoidalPositionEncoder) of the BOS
+        token = E[bos]*sqrt(d) + pos[0], pos[0] = [sin(0)... | cos(0)...] = [0.. | 1..]  [fs2]  (``encoder_pooler.py:70-76``)."""
+        cfg, sd = self.cfg, self.sd
+        d = cfg.model_dim
+        pos0 = torch.cat([torch.zeros(d // 2), torch.ones(d // 2)])
+        return (sd["encoder_pooler.decoder_frontend.embed.weight"][cfg.bos_idx] * math.sqrt(d) + pos0)[None, None].expand(batch, 1, d)
+
+    def pooler_layers(self, x: Tensor, enc: Tensor, key_ok: Tensor) -> Tensor:
+        """The POST-LN decoder-layer stack of the pooler (``sonar_speech/factory.py:110-137``): self-attention, encoder-decoder
+        attention with a key-padding mask, ReLU FFN, each followed by residual + LayerNorm.  PINNED against HuggingFace
+        ``BartDecoderLayer`` (post-LN, same sub-layer order) through ``tests/golden/pooler_layers_small.pt``."""
         cfg, sd = self.cfg, self.sd
         d, H = cfg.model_dim, cfg.pooler_heads
         hd = d // H
-        b, s, _ = enc.shape
-        # TransformerEmbeddingFrontend(embed, SinusoidalPositionEncoder(d, max_seq_len)): E[bos]*sqrt(d) + pos[0],
-        # pos[0] = [sin(0)... | cos(0)...] = [0.. | 1..]  [fs2]
-        pos0 = torch.cat([torch.zeros(d // 2), torch.ones(d // 2)])
-        x = (sd["encoder_pooler.decoder_frontend.embed.weight"][cfg.bos_idx] * math.sqrt(d) + pos0)[None, None].expand(b, 1, d)
+        b = enc.shape[0]
 
         def mha(pfx, q_in, kv_in, mask):
             q = F.linear(q_in, sd[pfx + "q_proj.weight"], sd[pfx + "q_proj.bias"]).view(b, -1, H, hd).transpose(1, 2)
@@ -191,7 +200,12 @@ class OracleSpeechEncoder:
             f = F.linear(F.relu(F.linear(x, sd[p + "ffn.inner_proj.weight"], sd[p + "ffn.inner_proj.bias"])),
                          sd[p + "ffn.output_proj.weight"], sd[p + "ffn.output_proj.bias"])
             x = lnorm(x + f, "ffn_layer_norm")
-        return F.linear(x, sd["encoder_pooler.projection_out.weight"]).squeeze(1)
+        return x
+
+    # ------------------------------------------------------------------ attention pooler
+    def pooler(self, enc: Tensor, key_ok: Tensor) -> Tensor:
+        x = self.pooler_layers(self.pooler_query(enc.shape[0]), enc, key_ok)
+        return F.linear(x, self.sd["encoder_pooler.projection_out.weight"]).squeeze(1)  # bias-free (factory.py:146-152)
 
     @torch.no_grad()
     def forward(self, fbank: Tensor, frame_lens: List[int]) -> Tuple[Tensor, Tensor, List[int]]:

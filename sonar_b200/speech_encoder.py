@@ -168,6 +168,14 @@ class B200SpeechEncoderModel(torch.nn.Module):
         self._relpos: Dict[int, Tensor] = {}
         self.return_encoded_seqs = False
 
+    @classmethod
+    def from_checkpoint(cls, path, config: Optional["SonarSpeechEncoderConfig"] = None,
+                        device: Union[str, torch.device] = "cuda") -> "B200SpeechEncoderModel":
+        """Load a fairseq2-layout checkpoint ``{"model": state_dict}`` (key names of ``sonar_speech/handler.py:63-110``)."""
+        ckpt = torch.load(str(path), map_location="cpu", weights_only=True)
+        sd = ckpt["model"] if "model" in ckpt else ckpt
+        return cls(config or sonar_speech_encoder_config("english"), sd, device)
+
     @property
     def dtype(self) -> torch.dtype:
         return torch.bfloat16

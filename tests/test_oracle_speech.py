@@ -68,3 +68,17 @@ def test_oracle_speech_padding_invariance():
     alone, _, _ = enc(fb[1:, :14], [14])
     assert lens == [12, 7]
     torch.testing.assert_close(both[1], alone[0], rtol=1e-5, atol=1e-5)
+
+
+def test_oracle_pooler_layers_match_hf_bart_post_ln_golden():
+    """The pooler's POST-LN decoder layers against an independent implementation (HuggingFace BartDecoderLayer; golden made
+    by tests/golden/make_pooler_golden.py): self-attention over the single query, cross-attention with a key-padding mask
+    (one utterance keeps a single valid key), ReLU FFN."""
+    from oracle.speech_encoder import OracleSpeechConfig, OracleSpeechEncoder
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pooler_layers_small.pt"), weights_only=True)
+    enc = OracleSpeechEncoder(OracleSpeechConfig(**g["config"]), g["state_dict"])
+    s = g["enc"].shape[1]
+    key_ok = torch.arange(s)[None, :] < g["lens"][:, None]
+    out = enc.pooler_layers(g["x0"], g["enc"], key_ok)
+    torch.testing.assert_close(out, g["out"], rtol=1e-5, atol=1e-5)
