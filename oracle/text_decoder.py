@@ -161,6 +161,9 @@ class BeamSearchConfig:
     pad_idx: int = 0            # tokenizer pad (NLLB: 0); never generated
     unk_idx: int = 1
     eos_idx: int = 3
+    # fairseq2 always scores the prompt (True).  False drops that per-sentence constant: HuggingFace's forced-BOS generation
+    # behaves that way, so tests/test_beam_vs_hf.py can pin every OTHER rule (divisor, EOS handling, closing) against it.
+    score_prompt: bool = True
 
 
 def beam_search_step(lprobs: Tensor, cum: Tensor, step: int, cfg: BeamSearchConfig, first: bool):
@@ -195,15 +198,18 @@ def constrain_lprobs(lprobs: Tensor, gen_len: int, cfg: BeamSearchConfig) -> Ten
     return lp
 
 
-def beam_search(lprob_fn, prompt: Tensor, n: int, cfg: BeamSearchConfig) -> List[List[Tuple[float, List[int]]]]:
+def beam_search(lprob_fn, prompt: Tensor, n: int, cfg: BeamSearchConfig,
+                dropped_eos: Optional[List[int]] = None) -> List[List[Tuple[float, List[int]]]]:
     """``lprob_fn(tokens [R,S]) -> [R,V]`` next-token log-probs for R = n*beam rows laid out sentence-major.
     ``prompt`` int64 [P] (SONAR target mode: [</s>, __lang__]).  Returns, per sentence, its finished hypotheses
-    sorted best first as (score, generated tokens incl. the final EOS)."""
+    sorted best first as (score, generated tokens incl. the final EOS).  ``dropped_eos`` (optional, length n) counts per
+    sentence the in-beam EOS candidates that arrived when the sentence already owned ``beam`` hypotheses (fairseq2 drops them;
+    HuggingFace would let them compete -- tests/test_beam_vs_hf.py uses the count to recognise that divergence)."""
     beam = cfg.beam_size
     P = prompt.numel()
     seqs = prompt[None, None, :].repeat(n, beam, 1)  # [N, beam, S]
     cum = torch.zeros(n, beam)
-    for p in range(1, P):  # _prefill: score of the prompt itself
+    for p in range(1, P if cfg.score_prompt else 1):  # _prefill: score of the prompt itself
         lp = lprob_fn(seqs[:, :, :p].reshape(n * beam, -1)).reshape(n, beam, -1).float()
         cum = cum + lp[:, :, int(prompt[p])]
     finished: List[List[Tuple[float, List[int]]]] = [[] for _ in range(n)]
@@ -230,6 +236,8 @@ def beam_search(lprob_fn, prompt: Tensor, n: int, cfg: BeamSearchConfig) -> List
                 b, t = int(cbeam[i, r]), int(ctok[i, r])
                 if t == cfg.eos_idx:
                     # only EOS candidates ranked inside the beam finish a hypothesis, and only until the sentence owns `beam`
+                    if r < beam and len(finished[i]) >= beam and dropped_eos is not None:
+                        dropped_eos[i] += 1
                     if r < beam and len(finished[i]) < beam:
                         toks = seqs[i, b, P:].tolist() + [t]
                         # IEEE float32 division, like the product (torch / CUDA)
