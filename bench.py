@@ -603,8 +603,8 @@ def main():
     ap.add_argument("--seq-len", type=int, default=SEQ)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--cta-group", type=int, default=2)
-    ap.add_argument("--ln-fold", type=int, default=1, choices=[0, 1],
-                    help="1 = LayerNorm folded into the GEMMs (default schedule), 0 = separate LayerNorm kernels")
+    ap.add_argument("--ln-fold", type=int, default=0, choices=[0, 1],
+                    help="0 = separate LayerNorm kernels (default schedule), 1 = LayerNorm folded into the GEMMs")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-secondary", action="store_true", help="N=1: skip the predict / speech / decoder / xsim blocks")
     ap.add_argument("--only", default="", help="N=1: comma list of secondary blocks to run (predict,speech,decoder,xsim)")

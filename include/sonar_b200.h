@@ -147,9 +147,9 @@ int sb_encoder_check_inputs(SbEncoder* enc, void* workspace, void* stream);
  *   LN(x; gamma, beta) . W^T + b  =  rstd * (x . Wf^T - mean * colsum) + bias_f
  * sb_fold_layernorm prepares Wf = bf16(W diag(gamma)) [N,K], colsum[n] = sum_k Wf[n,k], bias_f = bias + W beta;
  * sb_gemm_residual_stats computes x += A . W^T + bias (fp32, in place) and emits h_out = bf16(x) plus stats_out
- *   [M, N/256, 2] = (mean, M2) of every 256-column chunk of the new rows;
+ *   [M, N/128, 2] = (mean, M2) of N/128 disjoint 128-column subsets of the new rows (one per epilogue warpgroup and tile);
  * sb_gemm_ln_consumer computes C (bf16) = [relu](rstd * (A . Wf^T - mean * colsum) + bias_f) with A = the bf16 copy and
- *   (mean, rstd) merged from `stats` [M, K/256, 2].  K = 256, 512, 768 or 1024. */
+ *   (mean, rstd) merged from `stats` [M, K/128, 2].  K = a multiple of 128, <= 1024. */
 int sb_fold_layernorm(const void* W, const float* bias, const float* gamma, const float* beta, int32_t N, int32_t K,
                       void* Wf, float* colsum, float* bias_f, void* stream);
 int sb_gemm_ln_consumer(const void* A, int64_t lda, const void* Wf, int64_t ldw, void* C, int64_t ldc, const float* bias_f,

@@ -30,6 +30,13 @@ elif which == "gemm_res":  # out-proj (bias + fp32 residual in place)
     x = torch.randn((T, D), device=dev, generator=g)
     for _ in range(4):
         ops.gemm_bf16(a, w, b, epilogue="residual", residual=x, out=x)
+elif which == "gemm_resstats":  # out-proj with the LayerNorm-folding producer epilogue (x += ..., bf16 copy, row statistics)
+    a = torch.randn((T, D), device=dev, generator=g).to(torch.bfloat16)
+    w = (torch.randn((D, D), device=dev, generator=g) / math.sqrt(D)).to(torch.bfloat16)
+    b = torch.randn((D,), device=dev, generator=g)
+    x = torch.randn((T, D), device=dev, generator=g)
+    for _ in range(4):
+        ops.gemm_residual_stats(a, w, b, x)
 elif which == "attention":
     qkv = torch.randn((T, 3 * D), device=dev, generator=g).to(torch.bfloat16)
     cu = ops.cu_seqlens_of([128] * (T // 128)).to(dev)

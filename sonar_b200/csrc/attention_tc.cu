@@ -14,17 +14,18 @@
 // nq x nkv units with the usual online-softmax rescaling of a register accumulator between key tiles.
 //
 // One persistent CTA per SM, warp-specialised, everything asynchronous:
-//   warp 0   TMA producer: Q, K, V tiles [128 x 64] bf16 (SWIZZLE_128B) of the next units into a 4-stage ring (192 KB),
-//            so up to ~100 KB of loads are in flight per SM at any time -- the op is HBM-bound (reads 6 B, writes 2 B per
-//            token and dim; 1.2 % of the encoder FLOPs)
+//   warp 0   TMA producer: [128 x 64] bf16 tiles (SWIZZLE_128B) of the next units into two rings -- Q|K pairs (3 stages,
+//            released as soon as S = Q K^T has retired) and V tiles (6 stages, released when P.V has retired) -- so loads
+//            run 3 units ahead of the S products and 6 ahead of the P.V products: the op is HBM-bound (reads 6 B, writes
+//            2 B per token and dim; 1.2 % of the encoder FLOPs) and what matters is bytes in flight per SM
 //   warp 1   MMA issuer (one elected lane): S for unit u, then P.V for unit u-1, so the tensor core always has the other
 //            softmax group's S queued while one group is busy with exponentials
-//   warp 2   TMEM allocator (512 columns: S0 | S1 | O0 | O1)
+//   warp 2   TMEM allocator (512 columns: S0 | S1 | O0 | O1 | P0 | P1)
 //   warps 4-7 / 8-11   two softmax + epilogue warpgroups (TMEM lane quarter = warp % 4); group g owns the items with
-//            g = local item index & 1 and the TMEM buffers S[g], O[g]
+//            g = local item index & 1 and the TMEM buffers S[g], O[g], P[g]
 // The softmax is two-pass over TMEM (row maximum, then exponentials), 32 columns at a time, so a thread never holds more
-// than one chunk of the score row; P (bf16, K-major SW128) is written over the unit's own Q and K tiles, which are dead
-// once S has been computed.
+// than one chunk of the score row.  P never touches shared memory: the bf16 probabilities go back to TENSOR MEMORY
+// (tcgen05.st, two per 32-bit column) and P.V reads its A operand from there (tcgen05.mma with A in TMEM).
 
 #include "common.cuh"
 #include "sonar_b200_internal.h"
@@ -34,12 +35,15 @@
 namespace sb {
 namespace {
 
-constexpr int kTile = 128 * 64 * 2;    // one [128 x 64] bf16 operand tile = 16 KB
-constexpr int kStageBytes = 3 * kTile;  // Q | K | V
-constexpr int kStages = 4;
-constexpr int kBarBytes = 256;
+constexpr int kTile = 128 * 64 * 2;  // one [128 x 64] bf16 operand tile = 16 KB
+constexpr int kQkStages = 3;         // Q | K pairs (32 KB each)
+constexpr int kVStages = 6;          // V tiles (16 KB each)
+constexpr int kRingBytes = kQkStages * 2 * kTile + kVStages * kTile;  // 192 KB
+constexpr int kBarBytes = 512;
 constexpr int kCuSmemInts = 8192;  // cu_seqlens is staged in shared memory when the batch has < 8192 sentences
-constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kCuSmemInts * 4 + 1024;  // + alignment slack
+constexpr int kSmemBytes = kRingBytes + kBarBytes + kCuSmemInts * 4 + 1024;  // + alignment slack
+// TMEM columns: S[g] = g * 128 (fp32 scores), O[g] = 256 + g * 64 (fp32), P[g] = 384 + g * 64 (bf16 pairs)
+constexpr uint32_t kTmemO = 256, kTmemP = 384;
 constexpr int kThreads = 384;
 
 // MN-major B operand (V: rows = keys (K dim), 64 contiguous head dims = one 128 B swizzle row):
@@ -97,16 +101,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* c
                     __nv_bfloat16* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint64_t* full_qk = bars;               // [kStages] TMA: Q and K landed
-  uint64_t* full_v = bars + kStages;      // [kStages] TMA: V landed
-  uint64_t* empty = bars + 2 * kStages;   // [kStages] MMA: P.V retired -> the stage (and the P written over Q|K) is free
-  uint64_t* s_full = bars + 3 * kStages;  // [2] MMA: S[g] complete
-  uint64_t* p_ready = s_full + 2;         // [2] softmax group g: P written and S[g] fully read (4 warp arrivals)
-  uint64_t* o_full = s_full + 4;          // [2] MMA: O[g] complete
-  uint64_t* o_free = s_full + 6;          // [2] group g: O[g] read out of TMEM (4 warp arrivals)
+  uint8_t* smem_qk = smem;                              // [kQkStages][Q | K]
+  uint8_t* smem_v = smem + kQkStages * 2 * kTile;       // [kVStages]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRingBytes);
+  uint64_t* full_qk = bars;                       // [kQkStages] TMA: Q and K landed
+  uint64_t* empty_qk = full_qk + kQkStages;       // [kQkStages] MMA: S retired -> the Q | K pair is free
+  uint64_t* full_v = empty_qk + kQkStages;        // [kVStages] TMA: V landed
+  uint64_t* empty_v = full_v + kVStages;          // [kVStages] MMA: P.V retired -> the V tile is free
+  uint64_t* s_full = empty_v + kVStages;          // [2] MMA: S[g] complete
+  uint64_t* p_ready = s_full + 2;                 // [2] softmax group g: P[g] written and S[g] fully read (4 warp arrivals)
+  uint64_t* o_full = s_full + 4;                  // [2] MMA: O[g] complete (P[g] consumed)
+  uint64_t* o_free = s_full + 6;                  // [2] group g: O[g] read out of TMEM (4 warp arrivals)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_full + 8);
-  int32_t* cu_smem = reinterpret_cast<int32_t*>(smem + kStages * kStageBytes + kBarBytes);
+  int32_t* cu_smem = reinterpret_cast<int32_t*>(smem + kRingBytes + kBarBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = H * 64;
@@ -120,10 +127,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* c
 
   if (warp == 1 && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kQkStages; ++i) {
       mbar_init(&full_qk[i], 1);
+      mbar_init(&empty_qk[i], 1);
+    }
+    for (int i = 0; i < kVStages; ++i) {
       mbar_init(&full_v[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty_v[i], 1);
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
@@ -145,22 +155,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* c
       UnitStream s0, s1;  // (two named streams, selected by value: indexing an array of them would put them in local memory)
       s0.init(cu, H, num_items, blockIdx.x, 2 * gridDim.x);
       s1.init(cu, H, num_items, blockIdx.x + gridDim.x, 2 * gridDim.x);
-      int stage = 0;
-      uint32_t phase = 0;
+      int sq = 0, sv = 0;
+      uint32_t phq = 0, phv = 0;
       for (int turn = 0; s0.valid || s1.valid; ++turn) {
         const bool g1 = (turn & 1) ? s1.valid : !s0.valid;
         const int col = (g1 ? s1.h : s0.h) * 64;
         const int qrow = g1 ? s1.tok0 + s1.qt * 128 : s0.tok0 + s0.qt * 128;
         const int krow = g1 ? s1.tok0 + s1.kt * 128 : s0.tok0 + s0.kt * 128;
-        uint8_t* base = smem + stage * kStageBytes;
-        mbar_wait(&empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_qk[stage], 2 * kTile);
-        tma_load_2d(base, &tm_qkv, &full_qk[stage], col, qrow);
-        tma_load_2d(base + kTile, &tm_qkv, &full_qk[stage], D + col, krow);
-        mbar_arrive_expect_tx(&full_v[stage], kTile);
-        tma_load_2d(base + 2 * kTile, &tm_qkv, &full_v[stage], 2 * D + col, krow);
+        uint8_t* qk = smem_qk + sq * 2 * kTile;
+        mbar_wait(&empty_qk[sq], phq ^ 1);
+        mbar_arrive_expect_tx(&full_qk[sq], 2 * kTile);
+        tma_load_2d(qk, &tm_qkv, &full_qk[sq], col, qrow);
+        tma_load_2d(qk + kTile, &tm_qkv, &full_qk[sq], D + col, krow);
+        mbar_wait(&empty_v[sv], phv ^ 1);
+        mbar_arrive_expect_tx(&full_v[sv], kTile);
+        tma_load_2d(smem_v + sv * kTile, &tm_qkv, &full_v[sv], 2 * D + col, krow);
         if (g1) s1.advance(); else s0.advance();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++sq == kQkStages) { sq = 0; phq ^= 1; }
+        if (++sv == kVStages) { sv = 0; phv ^= 1; }
       }
     }
     __syncwarp();
@@ -172,27 +184,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* c
       UnitStream s0, s1;
       s0.init(cu, H, num_items, blockIdx.x, 2 * gridDim.x);
       s1.init(cu, H, num_items, blockIdx.x + gridDim.x, 2 * gridDim.x);
-      int stage = 0;
-      uint32_t phase = 0;
+      int sq = 0, sv = 0;
+      uint32_t phq = 0, phv = 0;
       uint32_t n0 = 0, n1 = 0;  // units issued per group
       // the unit whose P.V is still to be issued (one behind the S issue)
-      int pend_g = -1, pend_stage = 0, pend_ksteps = 0;
-      uint32_t pend_stage_phase = 0, pend_n = 0;
+      int pend_g = -1, pend_sv = 0, pend_ksteps = 0;
+      uint32_t pend_phv = 0, pend_n = 0;
       auto issue_pv = [&]() {
         const int g = pend_g;
-        uint8_t* base = smem + pend_stage * kStageBytes;
-        mbar_wait(&p_ready[g], pend_n & 1);             // P in smem, S[g] read
-        mbar_wait(&full_v[pend_stage], pend_stage_phase);
+        mbar_wait(&p_ready[g], pend_n & 1);             // P[g] in tensor memory, S[g] read
+        mbar_wait(&full_v[pend_sv], pend_phv);
         if (pend_n > 0) mbar_wait(&o_free[g], (pend_n - 1) & 1);  // the group's previous O has been read out
         tc_fence_after();
-        const uint32_t tmem_o = tmem_base + 256 + g * 64;
-        for (int k = 0; k < pend_ksteps; ++k) {
-          const uint64_t pd = umma_desc_kmajor_sw128(smem_u32(base + (k >> 2) * kTile)) + uint64_t(2 * (k & 3));
-          const uint64_t vd = umma_desc_mnmajor_sw128(smem_u32(base + 2 * kTile + k * 2048));  // 16 keys * 128 B
-          umma_bf16<1>(tmem_o, pd, vd, idesc_o, k != 0);
+        const uint32_t tmem_o = tmem_base + kTmemO + g * 64;
+        const uint32_t tmem_p = tmem_base + kTmemP + g * 64;
+        const uint32_t v_addr = smem_u32(smem_v + pend_sv * kTile);
+        for (int k = 0; k < pend_ksteps; ++k) {  // 16 keys per k-step: 8 TMEM columns of P, 16 rows (2 KB) of V
+          const uint64_t vd = umma_desc_mnmajor_sw128(v_addr + k * 2048);
+          umma_bf16_ts(tmem_o, tmem_p + 8 * k, vd, idesc_o, k != 0);
         }
         umma_commit<1>(&o_full[g]);
-        umma_commit<1>(&empty[pend_stage]);
+        umma_commit<1>(&empty_v[pend_sv]);
         pend_g = -1;
       };
       for (int turn = 0; s0.valid || s1.valid; ++turn) {
@@ -200,11 +212,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* c
         const int g = g1 ? 1 : 0;
         const uint32_t ng = g1 ? n1 : n0;
         const int kv_valid = g1 ? min(128, s1.len - s1.kt * 128) : min(128, s0.len - s0.kt * 128);
-        uint8_t* base = smem + stage * kStageBytes;
+        uint8_t* base = smem_qk + sq * 2 * kTile;
         // a P that is already waiting goes to the tensor core before this thread blocks on the next unit's loads
         if (pend_g >= 0 && mbar_try_wait(&p_ready[pend_g], pend_n & 1)) issue_pv();
         // ---- S = Q K^T for this unit ----
-        mbar_wait(&full_qk[stage], phase);
+        mbar_wait(&full_qk[sq], phq);
         if (ng > 0) {
           if (pend_g == g) issue_pv();                 // same group twice in a row: its P.V must go first
           mbar_wait(&p_ready[g], (ng - 1) & 1);        // S[g] of the group's previous unit has been read
@@ -217,16 +229,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* c
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16<1>(tmem_s, qd + uint64_t(2 * k), kd + uint64_t(2 * k), idesc_s, k != 0);
           umma_commit<1>(&s_full[g]);
+          umma_commit<1>(&empty_qk[sq]);  // Q and K are dead once S has retired: their slot goes straight back to the producer
         }
         // ---- P.V of the previous unit (normally the other group's) ----
         if (pend_g >= 0) issue_pv();
         pend_g = g;
-        pend_stage = stage;
-        pend_stage_phase = phase;
+        pend_sv = sv;
+        pend_phv = phv;
         pend_ksteps = (kv_valid + 15) >> 4;
         pend_n = ng;
         if (g1) { ++n1; s1.advance(); } else { ++n0; s0.advance(); }
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++sq == kQkStages) { sq = 0; phq ^= 1; }
+        if (++sv == kVStages) { sv = 0; phv ^= 1; }
       }
       if (pend_g >= 0) issue_pv();
     }
@@ -238,30 +252,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* c
     const int row = wq * 32 + lane;
     const uint32_t lane_base = uint32_t(wq * 32) << 16;
     const uint32_t tmem_s = tmem_base + g * 128 + lane_base;
-    const uint32_t tmem_o = tmem_base + 256 + g * 64 + lane_base;
+    const uint32_t tmem_o = tmem_base + kTmemO + g * 64 + lane_base;
+    const uint32_t tmem_p = tmem_base + kTmemP + g * 64 + lane_base;
     const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
     UnitStream u;
     u.init(cu, H, num_items, blockIdx.x + g * gridDim.x, 2 * gridDim.x);
-    // ring position of this group's next unit: both producers of the interleaving (turn order) are replayed here
-    UnitStream other;
-    other.init(cu, H, num_items, blockIdx.x + (g ^ 1) * gridDim.x, 2 * gridDim.x);
-    int turn = 0, ring = 0;  // `ring` = units issued so far by both groups = stage index modulo kStages
     uint32_t n = 0;
     float m_run = -CUDART_INF_F, l_run = 0.f;
     float o_acc[64];
     while (u.valid) {
-      // advance the interleaving until it is this group's turn
-      for (;;) {
-        const int tg = (turn & 1);
-        const int pick = (tg == g ? u.valid : other.valid) ? tg : (tg ^ 1);
-        ++turn;
-        if (pick == g) break;
-        other.advance();
-        ++ring;
-      }
-      const int stage = ring % kStages;
-      ++ring;
-      uint8_t* sP = smem + stage * kStageBytes;  // P overwrites the unit's Q | K tiles
       const int kv_valid = min(128, u.len - u.kt * 128);
       const int nch = (kv_valid + 31) >> 5;  // 32-key chunks holding valid keys
       const bool single = (u.nt == 1);
@@ -276,49 +275,50 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* c
         tmem_ld_32x32(tmem_s + c * 32, v);
         tmem_ld_wait();
         const int lim = kv_valid - c * 32;  // keys >= lim of this chunk are beyond the sentence
-        float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
+        if (lim < 32) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          m0 = fmaxf(m0, j < lim ? __uint_as_float(v[j]) : -CUDART_INF_F);
-          m1 = fmaxf(m1, j + 1 < lim ? __uint_as_float(v[j + 1]) : -CUDART_INF_F);
+          for (int j = 0; j < 32; ++j)
+            if (j >= lim) v[j] = __float_as_uint(-CUDART_INF_F);
+        }
+        float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]);
+#pragma unroll
+        for (int j = 2; j < 32; j += 2) {
+          m0 = fmaxf(m0, __uint_as_float(v[j]));
+          m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
         }
         mx = fmaxf(mx, fmaxf(m0, m1));
       }
       const float m_new = fmaxf(m_run, mx);
       const float alpha = fast_exp2((m_run - m_new) * sl2);  // 0 on the first key tile (m_run = -inf)
       const float mxs = m_new * sl2;
-      // ---- pass 2: p = exp2(s*c - m*c), row sum, bf16 P row -> swizzled K-major smem ----
+      // ---- pass 2: p = exp2(s*c - m*c), row sum, bf16 pairs -> tensor memory (the A operand of P.V) ----
       float sum0 = 0.f, sum1 = 0.f;
-      uint8_t* prow = sP + row * 128;
       for (int c = 0; c < nch; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_s + c * 32, v);
         tmem_ld_wait();
         const int lim = kv_valid - c * 32;
-        float p[32];
+        if (lim < 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j >= lim) v[j] = __float_as_uint(-CUDART_INF_F);  // -inf -> probability exactly 0
+        }
+        uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          const float a = j < lim ? __uint_as_float(v[j]) : -CUDART_INF_F;  // -inf -> probability exactly 0
-          const float bq = j + 1 < lim ? __uint_as_float(v[j + 1]) : -CUDART_INF_F;
-          p[j] = fast_exp2(fmaf(a, sl2, -mxs));
-          p[j + 1] = fast_exp2(fmaf(bq, sl2, -mxs));
-          sum0 += p[j];
-          sum1 += p[j + 1];
+          const float p0 = fast_exp2(fmaf(__uint_as_float(v[j]), sl2, -mxs));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), sl2, -mxs));
+          sum0 += p0;
+          sum1 += p1;
+          pk[j >> 1] = pack_bf16x2(p0, p1);  // key j in the low half: K runs along the column, two keys per column
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = (c & 1) * 4 + q;  // 16-byte chunk inside the 64-key tile
-          *reinterpret_cast<uint4*>(prow + (c >> 1) * kTile + ((chunk ^ (row & 7)) << 4)) =
-              make_uint4(pack_bf16x2(p[8 * q], p[8 * q + 1]), pack_bf16x2(p[8 * q + 2], p[8 * q + 3]),
-                         pack_bf16x2(p[8 * q + 4], p[8 * q + 5]), pack_bf16x2(p[8 * q + 6], p[8 * q + 7]));
-        }
+        tmem_st_32x16(tmem_p + c * 16, pk);
       }
-      // P.V consumes whole 16-key k-steps: with an odd number of valid 16-key groups inside the last 32-key chunk
-      // nothing more is needed (the chunk was written in full, masked keys as zeros)
+      // P.V consumes whole 16-key k-steps and every written 32-key chunk is complete (masked keys as zeros)
       l_run = l_run * alpha + (sum0 + sum1);
       m_run = m_new;
+      tmem_st_wait();
       tc_fence_before();
-      fence_proxy_async_smem();  // generic-proxy writes of P -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[g]);
       // ---- O tile: accumulate / write out ----

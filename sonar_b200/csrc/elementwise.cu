@@ -37,8 +37,8 @@ embed_kernel(const int64_t* __restrict__ ids, long long ids_stride, const int32_
   const uint4* erow = reinterpret_cast<const uint4*>(embed + id * (long long)D);
   const float4* prow = reinterpret_cast<const float4*>(pos_table + (long long)(pos + pos_offset) * D);
   float4* xrow = reinterpret_cast<float4*>(x + (long long)(start + pos) * D);
-  // LnFold producer side (optional): bf16 copy of the row and (mean, M2) of each 256-column chunk -- chunk k is covered by
-  // iteration k of the loop below (32 lanes x 8 columns), so one warp reduction per iteration gives its statistics
+  // LnFold producer side (optional): bf16 copy of the row and (mean, M2) of each kLnPartCols (128)-column chunk -- iteration
+  // k of the loop below covers columns [256k, 256k + 256) with 8 columns per lane, so each HALF warp reduces one chunk
   uint4* hrow = h_out ? reinterpret_cast<uint4*>(h_out + (long long)(start + pos) * D) : nullptr;
   for (int c = lane; c < D / 8; c += 32) {
     const uint4 e = __ldg(erow + c);
@@ -60,15 +60,20 @@ embed_kernel(const int64_t* __restrict__ ids, long long ids_stride, const int32_
     xrow[2 * c + 1] = o1;
     if (hrow != nullptr) {
       hrow[c] = make_uint4(pack_bf16x2(o0.x, o0.y), pack_bf16x2(o0.z, o0.w), pack_bf16x2(o1.x, o1.y), pack_bf16x2(o1.z, o1.w));
-      const float mean = warp_sum((o0.x + o0.y) + (o0.z + o0.w) + (o1.x + o1.y) + (o1.z + o1.w)) * (1.0f / 256.0f);
+      float hs = (o0.x + o0.y) + (o0.z + o0.w) + (o1.x + o1.y) + (o1.z + o1.w);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) hs += __shfl_xor_sync(0xffffffffu, hs, o);  // stays inside each 16-lane half
+      const float mean = hs * (1.0f / 128.0f);
       float q = 0.f;
       q = fmaf(o0.x - mean, o0.x - mean, q); q = fmaf(o0.y - mean, o0.y - mean, q);
       q = fmaf(o0.z - mean, o0.z - mean, q); q = fmaf(o0.w - mean, o0.w - mean, q);
       q = fmaf(o1.x - mean, o1.x - mean, q); q = fmaf(o1.y - mean, o1.y - mean, q);
       q = fmaf(o1.z - mean, o1.z - mean, q); q = fmaf(o1.w - mean, o1.w - mean, q);
-      q = warp_sum(q);
-      if (lane == 0)
-        reinterpret_cast<float2*>(stats_out)[(long long)(start + pos) * (D / 256) + (c >> 5)] = make_float2(mean, q);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      if ((lane & 15) == 0)
+        reinterpret_cast<float2*>(stats_out)[(long long)(start + pos) * (D / 128) + 2 * (c >> 5) + (lane >> 4)] =
+            make_float2(mean, q);
     }
   }
 }

@@ -12,12 +12,13 @@
 //   qkv bf16 [T, 3D]  fused q|k|v projections (its first [T, D] doubles as the bf16 copy of x behind the out-projection)
 //   f   bf16 [T, F]   FFN inner activations
 //
-// Default schedule (cfg.ln_fold = 1), 5 launches per layer, no LayerNorm kernel:
+// Schedule with cfg.ln_fold = 1, 5 launches per layer, no LayerNorm kernel:
 //   embed -> x, h = bf16(x), row stats
 //   24 x [ QKV GEMM (folds LN1: stats + gamma/beta prepared into W', c, b') -> attention (tcgen05) ->
 //          out-proj GEMM (+residual; emits x, bf16(x), stats) -> FFN1 GEMM (folds LN2, +ReLU) ->
 //          FFN2 GEMM (+residual; emits x, bf16(x), stats) ] -> final LN + pool
-// cfg.ln_fold = 0 keeps the classic schedule (separate LayerNorm kernels, residual adds by TMA reduce-add).
+// cfg.ln_fold = 0 (what the Python wrapper selects by default: measured faster, see bench.py `ab_layernorm_schedule`) keeps
+// the classic schedule: separate LayerNorm kernels, residual adds by TMA reduce-add, 7 launches per layer.
 
 #include "../../include/sonar_b200.h"
 #include <stdlib.h>
@@ -46,7 +47,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 struct Workspace {
   int32_t* cu;
-  float* ln_stats;  // [T, D/256, 2] per-row LayerNorm partials (LnFold)
+  float* ln_stats;  // [T, D/128, 2] per-row LayerNorm partials (LnFold)
   float* x;
   __nv_bfloat16* h;
   __nv_bfloat16* qkv;
@@ -98,7 +99,7 @@ static Workspace carve(const SbEncoder* e, int32_t max_batch, int64_t max_tokens
   w.cu = reinterpret_cast<int32_t*>(p + off);
   off = align_up(off + sizeof(int32_t) * ((size_t)max_batch + 1), 1024);
   w.ln_stats = reinterpret_cast<float*>(p + off);
-  off = align_up(off + T * (D / 256) * 2 * sizeof(float), 1024);
+  off = align_up(off + T * (D / kLnPartCols) * 2 * sizeof(float), 1024);
   w.x = reinterpret_cast<float*>(p + off);
   off = align_up(off + T * D * 4, 1024);
   w.h = reinterpret_cast<__nv_bfloat16*>(p + off);
@@ -310,7 +311,7 @@ int sb_encoder_forward(SbEncoder* e, const int64_t* ids, int64_t ids_row_stride,
   g.M = (int)T;
   LnFold consume;  // what a LayerNorm-consuming GEMM needs
   consume.stats_in = w.ln_stats;
-  consume.chunks = D / 256;
+  consume.chunks = D / kLnPartCols;
   consume.eps = e->cfg.ln_eps;
   for (int li = 0; li < e->cfg.num_layers; ++li) {
     const SbLayerWeights& L = e->layers[li];
@@ -455,7 +456,7 @@ int sb_gemm_ln_consumer(const void* A, int64_t lda, const void* Wf, int64_t ldw,
   g.C = C; g.ldc = ldc; g.out_fp32 = 0; g.bias = bias_f; g.residual = nullptr; g.ldr = 0;
   g.M = M; g.N = N; g.K = K; g.epi = relu ? EPI_BIAS_RELU : EPI_BIAS;
   g.cta_group = 2;
-  g.lf.stats_in = stats; g.lf.colsum = colsum; g.lf.chunks = K / 256; g.lf.eps = eps;
+  g.lf.stats_in = stats; g.lf.colsum = colsum; g.lf.chunks = K / kLnPartCols; g.lf.eps = eps;
   int dev = 0, sms = 0;
   SB_CUDA_CHECK(cudaGetDevice(&dev));
   SB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

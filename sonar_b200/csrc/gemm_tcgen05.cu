@@ -11,8 +11,10 @@
 //   of the leader CTA; each CTA's TMEM holds its 128 rows x 256 fp32 columns, double
 //   buffered (2 x 256 = all 512 columns) so the epilogue of tile i overlaps the
 //   mainloop of tile i+1.  cta_group::1 variant: 128 x 256 x 64 per CTA.
-// Warp roles (256 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM alloc/dealloc,
-//   w3 idle, w4-7 epilogue (TMEM -> regs -> bias/ReLU/residual -> swizzled smem -> TMA store).
+// Warp roles (384 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM alloc/dealloc, w3 idle,
+//   w4-7 and w8-11 two epilogue warpgroups (TMEM lane quarter = warp % 4) that take alternate column chunks of every
+//   accumulator tile (TMEM -> regs -> bias/ReLU/residual -> swizzled smem -> TMA store): with K = 1024 a 256 x 256 tile is
+//   only ~4 us of MMA, which ONE warpgroup's epilogue does not fit under.
 // LayerNorm folding (LnFold, sonar_b200_internal.h): a consumer GEMM scales its accumulator rows by the LayerNorm
 // statistics of its input; the residual-stream GEMMs emit those statistics and the bf16 copy of the stream.
 // Operand smem layout: K-major, 128-byte rows, SWIZZLE_128B (TMA writes it, UMMA reads it).
@@ -32,14 +34,15 @@ struct GemmCfg {
   static constexpr int LOAD_N = BLOCK_N / kCtaGroup;  // W rows each CTA stages
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = LOAD_N * BLOCK_K * 2;
-  static constexpr int STAGES = (kCtaGroup == 2) ? 6 : 4;
+  static constexpr int STAGES = (kCtaGroup == 2) ? 5 : 3;
   static constexpr int CD_STAGE_BYTES = 128 * 128;  // 128 rows x 128 B
-  static constexpr int CD_STAGES = 2;
+  static constexpr int EPI_GROUPS = 2;              // epilogue warpgroups (4 warps each), alternating column chunks
+  static constexpr int CD_STAGES = 2;               // staging buffers per epilogue warpgroup
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES =
-      STAGES * (A_BYTES + B_BYTES) + CD_STAGES * CD_STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
+      STAGES * (A_BYTES + B_BYTES) + EPI_GROUPS * CD_STAGES * CD_STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int THREADS = 256;
+  static constexpr int THREADS = 128 + 128 * EPI_GROUPS;
 };
 
 // Tile scheduler shared by the three warp roles (each role walks an identical copy).
@@ -103,7 +106,7 @@ __device__ __forceinline__ void topk_insert(float (&tv)[KC], int (&ti)[KC], floa
 }
 
 template <int kCtaGroup, int kEpi, typename OutT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(GemmCfg<kCtaGroup>::THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                          const __grid_constant__ CUtensorMap tm_c, const float* __restrict__ bias,
                          const OutT* residual, long long ldr, int M, int N, int K, float* __restrict__ cand_val,
@@ -115,7 +118,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + Cfg::STAGES * Cfg::A_BYTES;
   uint8_t* smem_cd = smem_b + Cfg::STAGES * Cfg::B_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_cd + Cfg::CD_STAGES * Cfg::CD_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_cd + Cfg::EPI_GROUPS * Cfg::CD_STAGES * Cfg::CD_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -140,7 +143,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);               // one tcgen05.commit
-      mbar_init(&tmem_empty_bar[i], 4 * kCtaGroup);  // one arrive per epilogue warp of every CTA
+      mbar_init(&tmem_empty_bar[i], 4 * Cfg::EPI_GROUPS * kCtaGroup);  // one arrive per epilogue warp of every CTA
     }
     fence_mbar_init();
   }
@@ -222,50 +225,74 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       }
     }
   } else if (warp_idx >= 4) {
-    // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
-    const int ew = warp_idx - 4;          // == warp_idx % 4 -> TMEM lane quarter
+    // ===================== epilogue: 2 warpgroups x 4 warps (each group spans the 128 TMEM lanes) =====================
+    const int wg = (warp_idx - 4) >> 2;   // epilogue warpgroup: takes the column chunks c with c % 2 == wg
+    const int ew = warp_idx & 3;          // TMEM lane quarter
     const int row_in_tile = ew * 32 + lane;
     constexpr int CHUNK_COLS = 128 / int(sizeof(OutT));  // one 128-byte smem row per output row
     constexpr int NUM_CHUNKS = Cfg::BLOCK_N / CHUNK_COLS;
     constexpr int SUBS = CHUNK_COLS / 32;
+    static_assert(NUM_CHUNKS % Cfg::EPI_GROUPS == 0, "column chunks must split evenly over the epilogue warpgroups");
+    uint8_t* smem_cd_wg = smem_cd + wg * Cfg::CD_STAGES * Cfg::CD_STAGE_BYTES;
+    const uint32_t bar_id = 1 + wg;  // named barrier of this warpgroup
     int cd_stage = 0;
     constexpr int KC = kTopkCandidates;
     [[maybe_unused]] float tv[KC];
     [[maybe_unused]] int ti[KC];
     [[maybe_unused]] float run_max = -CUDART_INF_F, run_sum = 0.f;  // online log-sum-exp of the row (optional)
+    // ---- LayerNorm folding, consumer side: the (mean, M2) partials of this thread's input row are fetched ONE TILE AHEAD
+    // (a lookahead copy of the scheduler names the next tile) so their latency hides under the current tile's epilogue ----
+    [[maybe_unused]] bool fold_in = false;
+    [[maybe_unused]] float2 part_next[8];
+    [[maybe_unused]] TileSched<kSweep> sched_ahead = sched;
+    [[maybe_unused]] auto fetch_parts = [&]() {
+      int mb, nb, ch;
+      bool f0, f1;
+      if (!sched_ahead.next(mb, nb, ch, f0, f1)) return;
+      const int r = mb * tile_m + int(cta_rank) * Cfg::BLOCK_M + row_in_tile;
+      if (r < M) {
+        const float2* sp = reinterpret_cast<const float2*>(lf.stats_in) + (long long)r * lf.chunks;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i < lf.chunks) part_next[i] = sp[i];
+      }
+    };
+    if constexpr (kEpi == EPI_BIAS || kEpi == EPI_BIAS_RELU) {
+      fold_in = lf.stats_in != nullptr;
+      if (fold_in) fetch_parts();
+    }
     for (uint32_t iter = 0; sched.next(m_blk, n_blk, chunk, first_in_item, last_in_item); ++iter) {
       const int m0 = m_blk * tile_m + int(cta_rank) * Cfg::BLOCK_M;
       const int n0 = n_blk * Cfg::BLOCK_N;
       const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
       const int grow = m0 + row_in_tile;
-      // ---- LayerNorm folding, consumer side: (mean, rstd) of this thread's input row from its 256-column partials ----
       [[maybe_unused]] float ln_mean = 0.f, ln_rstd = 1.f;
-      [[maybe_unused]] bool fold_in = false;
       if constexpr (kEpi == EPI_BIAS || kEpi == EPI_BIAS_RELU) {
-        fold_in = lf.stats_in != nullptr;
-        if (fold_in && grow < M) {
-          const float2* sp = reinterpret_cast<const float2*>(lf.stats_in) + (long long)grow * lf.chunks;
-          float2 part[4];
-          float msum = 0.f;
+        if (fold_in) {
+          if (grow < M) {  // Chan merge of `chunks` partials of kLnPartCols columns each
+            float msum = 0.f;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i < lf.chunks) { part[i] = sp[i]; msum += part[i].x; }
-          ln_mean = msum / float(lf.chunks);
-          float m2 = 0.f;
+            for (int i = 0; i < 8; ++i)
+              if (i < lf.chunks) msum += part_next[i].x;
+            ln_mean = msum / float(lf.chunks);
+            float m2 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i < lf.chunks) { const float dm = part[i].x - ln_mean; m2 += part[i].y + 256.f * dm * dm; }
-          ln_rstd = 1.0f / sqrtf(m2 / float(256 * lf.chunks) + lf.eps);
+            for (int i = 0; i < 8; ++i)
+              if (i < lf.chunks) { const float dm = part_next[i].x - ln_mean; m2 += part_next[i].y + float(kLnPartCols) * dm * dm; }
+            ln_rstd = 1.0f / sqrtf(m2 / float(kLnPartCols * lf.chunks) + lf.eps);
+          }
+          fetch_parts();  // for the next tile
         }
       }
-      // ---- producer side: the first 32 residual columns of this thread's row are fetched while the MMAs still run ----
+      // ---- producer side: the first residual chunk of this thread's row is fetched while the MMAs still run ----
       [[maybe_unused]] float4 rnext[8];
       [[maybe_unused]] float st_n = 0.f, st_mean = 0.f, st_m2 = 0.f;
       if constexpr (kEpi == EPI_BIAS_RESIDUAL_STATS) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) rnext[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (grow < M) {
-          const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(residual) + (long long)grow * ldr + n0);
+          const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(residual) + (long long)grow * ldr +
+                                                             n0 + wg * CHUNK_COLS);
 #pragma unroll
           for (int q = 0; q < 8; ++q) rnext[q] = rp[q];
         }
@@ -273,6 +300,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       if constexpr (kEpi == EPI_TOPK) {
+        if (wg != 0) {  // (the sweep epilogue keeps its per-row state in ONE thread: the second warpgroup only arrives)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (kCtaGroup == 2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+            else mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          continue;
+        }
         // ---- running per-row top-KC over the whole sweep of n tiles (no C matrix is ever written) ----
         if (first_in_item) {
 #pragma unroll
@@ -341,10 +377,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         continue;
       }
 #pragma unroll 1
-      for (int c = 0; c < NUM_CHUNKS; ++c) {
+      for (int c = wg; c < NUM_CHUNKS; c += Cfg::EPI_GROUPS) {
         if (ew == 0 && lane == 0) tma_store_wait_read<Cfg::CD_STAGES - 1>();  // staging buffer free again
-        named_bar_sync(1, 128);
-        uint8_t* cd_row = smem_cd + cd_stage * Cfg::CD_STAGE_BYTES + row_in_tile * 128;
+        named_bar_sync(bar_id, 128);
+        uint8_t* cd_row = smem_cd_wg + cd_stage * Cfg::CD_STAGE_BYTES + row_in_tile * 128;
 #pragma unroll
         for (int s = 0; s < SUBS; ++s) {
           uint32_t v[32];
@@ -378,9 +414,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             float4 rcur[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) rcur[q] = rnext[q];
-            if (c + 1 < NUM_CHUNKS && grow < M) {
+            if (c + Cfg::EPI_GROUPS < NUM_CHUNKS && grow < M) {
               const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(residual) +
-                                                                 (long long)grow * ldr + gcol + CHUNK_COLS);
+                                                                 (long long)grow * ldr + gcol + Cfg::EPI_GROUPS * CHUNK_COLS);
 #pragma unroll
               for (int q = 0; q < 8; ++q) rnext[q] = rp[q];
             }
@@ -407,8 +443,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
               for (int q = 0; q < 4; ++q)
                 hp[q] = make_uint4(pack_bf16x2(f[8 * q], f[8 * q + 1]), pack_bf16x2(f[8 * q + 2], f[8 * q + 3]),
                                    pack_bf16x2(f[8 * q + 4], f[8 * q + 5]), pack_bf16x2(f[8 * q + 6], f[8 * q + 7]));
-              if (c == NUM_CHUNKS - 1)
-                reinterpret_cast<float2*>(lf.stats_out)[(long long)grow * num_n_tiles + n_blk] = make_float2(st_mean, st_m2);
+              if (c + Cfg::EPI_GROUPS >= NUM_CHUNKS)  // this warpgroup's share of the tile: kLnPartCols columns
+                reinterpret_cast<float2*>(lf.stats_out)[((long long)grow * num_n_tiles + n_blk) * Cfg::EPI_GROUPS + wg] =
+                    make_float2(st_mean, st_m2);
             }
           }
           if constexpr (kEpi == EPI_BIAS_RELU) {
@@ -461,8 +498,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             }
           }
         }
-        if (c == NUM_CHUNKS - 1) {
-          // all TMEM reads of this accumulator are complete -> hand it back to the MMA issuer
+        if (c + Cfg::EPI_GROUPS >= NUM_CHUNKS) {
+          // this warp's TMEM reads of the accumulator are complete -> hand it back to the MMA issuer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -471,12 +508,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        named_bar_sync(bar_id, 128);
         if (ew == 0 && lane == 0) {
           if constexpr (kEpi == EPI_BIAS_ACCUM)
-            tma_reduce_add_2d(&tm_c, smem_cd + cd_stage * Cfg::CD_STAGE_BYTES, n0 + c * CHUNK_COLS, m0);
+            tma_reduce_add_2d(&tm_c, smem_cd_wg + cd_stage * Cfg::CD_STAGE_BYTES, n0 + c * CHUNK_COLS, m0);
           else
-            tma_store_2d(&tm_c, smem_cd + cd_stage * Cfg::CD_STAGE_BYTES, n0 + c * CHUNK_COLS, m0);
+            tma_store_2d(&tm_c, smem_cd_wg + cd_stage * Cfg::CD_STAGE_BYTES, n0 + c * CHUNK_COLS, m0);
           tma_store_commit();
         }
         cd_stage ^= 1;
@@ -651,9 +688,9 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
 
   // ---- LayerNorm folding (LnFold) ----
   if (g.lf.stats_in != nullptr) {  // consumer
-    if ((epi != EPI_BIAS && epi != EPI_BIAS_RELU) || !g.lf.colsum || g.lf.chunks < 1 || g.lf.chunks > 4 ||
-        g.K != 256 * g.lf.chunks) {
-      set_last_error("gemm_bf16: folded LayerNorm input needs a bias / bias+ReLU epilogue and K = 256 * chunks <= 1024 "
+    if ((epi != EPI_BIAS && epi != EPI_BIAS_RELU) || !g.lf.colsum || g.lf.chunks < 1 || g.lf.chunks > 8 ||
+        g.K != kLnPartCols * g.lf.chunks) {
+      set_last_error("gemm_bf16: folded LayerNorm input needs a bias / bias+ReLU epilogue and K = 128 * chunks <= 1024 "
                      "(K=%d chunks=%d)", g.K, g.lf.chunks);
       return -1;
     }

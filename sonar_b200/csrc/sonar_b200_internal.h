@@ -38,16 +38,18 @@ inline bool first_use_on_device(bool (&flags)[64]) {
 // so the GEMM that CONSUMES a LayerNorm runs on the un-normalised bf16 copy of the residual stream and applies the
 // per-row (mean, rstd) in its epilogue (`stats_in`, `colsum`), and the GEMM that PRODUCES the residual stream
 // (EPI_BIAS_RESIDUAL_STATS) emits, next to x, that bf16 copy (`h_out`) and per-row partial statistics (`stats_out`):
-// one (mean, M2) pair per 256-column tile of the row, merged by the consumer with Chan's formula (no E[x^2]-mean^2
-// cancellation).  Saves the LayerNorm kernel's read of x and one of the two passes over h per LayerNorm.
+// one (mean, M2) pair per kLnPartCols columns of the row (each epilogue warpgroup's share of a 256-column tile), merged by
+// the consumer with Chan's formula (no E[x^2]-mean^2 cancellation).  Saves the LayerNorm kernel's read of x and one of
+// the two passes over h per LayerNorm.
+constexpr int kLnPartCols = 128;
 struct LnFold {
-  const float* stats_in = nullptr;  // [M, chunks, 2] (mean, M2) of each 256-column chunk of the consumer's input rows
+  const float* stats_in = nullptr;  // [M, chunks, 2] (mean, M2) of `chunks` disjoint kLnPartCols-column subsets of the input rows
   const float* colsum = nullptr;    // [N] c[n]
-  int chunks = 0;                   // K / 256 of the LayerNorm the consumer folds
+  int chunks = 0;                   // K / kLnPartCols of the LayerNorm the consumer folds (<= 8)
   float eps = 0.f;
   __nv_bfloat16* h_out = nullptr;   // producer: [M, N] bf16 copy of the new residual stream, leading dimension ldh
   long long ldh = 0;
-  float* stats_out = nullptr;       // producer: [M, N / 256, 2]
+  float* stats_out = nullptr;       // producer: [M, N / kLnPartCols, 2]
 };
 
 struct GemmArgs {

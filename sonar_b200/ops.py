@@ -90,13 +90,14 @@ def fold_layernorm(w: Tensor, bias: Tensor, gamma: Tensor, beta: Tensor):
 
 
 def gemm_residual_stats(a: Tensor, w: Tensor, bias: Tensor, x: Tensor):
-    """x += a . w^T + bias in place (fp32); -> (h = bf16(x) [M,N], stats fp32 [M, N/256, 2])."""
+    """x += a . w^T + bias in place (fp32); -> (h = bf16(x) [M,N], stats fp32 [M, N/128, 2]): partial 2*t + g holds (mean, M2)
+    of the 128 columns {256 t + 32 c + j : c % 2 == g, j < 32} of the new row (epilogue warpgroup g's share of tile t)."""
     _need_cuda(a, w, bias, x)
     m, k = a.shape
     n = w.shape[0]
     assert x.shape == (m, n) and x.dtype == torch.float32 and x.is_contiguous() and n % 256 == 0
     h = torch.empty((m, n), dtype=torch.bfloat16, device=a.device)
-    stats = torch.empty((m, n // 256, 2), dtype=torch.float32, device=a.device)
+    stats = torch.empty((m, n // 128, 2), dtype=torch.float32, device=a.device)
     rc = _lib.load().sb_gemm_residual_stats(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), x.data_ptr(), n,
                                             bias.data_ptr(), h.data_ptr(), n, stats.data_ptr(), m, n, k, _stream())
     _lib.check(rc, "sb_gemm_residual_stats")
@@ -105,7 +106,8 @@ def gemm_residual_stats(a: Tensor, w: Tensor, bias: Tensor, x: Tensor):
 
 def gemm_ln_consumer(a: Tensor, wf: Tensor, bias_f: Tensor, colsum: Tensor, stats: Tensor, eps: float = 1e-5,
                      relu: bool = False) -> Tensor:
-    """bf16 [M,N] = [relu](rstd * (a . wf^T - mean * colsum) + bias_f), (mean, rstd) merged from stats [M, K/256, 2]."""
+    """bf16 [M,N] = [relu](rstd * (a . wf^T - mean * colsum) + bias_f), (mean, rstd) merged from stats [M, K/128, 2]
+    (any partition of the row into 128-column subsets)."""
     _need_cuda(a, wf, bias_f, colsum, stats)
     m, k = a.shape
     n = wf.shape[0]

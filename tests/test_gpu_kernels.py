@@ -262,7 +262,8 @@ def test_ln_pool_matches_torch(ops, cuda_device):
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("m,k", [(1000, 1024), (4096, 8192), (300, 256), (77, 1024)])
 def test_gemm_residual_stats(ops, cuda_device, m, k):
-    """x += a.W^T + b (fp32, in place) with the bf16 copy and the per-256-column (mean, M2) partials of the NEW rows.
+    """x += a.W^T + b (fp32, in place) with the bf16 copy and the (mean, M2) partials of the NEW rows: partial 2t + g covers
+    the 128 columns of 256-column tile t that epilogue warpgroup g handles (32-column chunks c with c % 2 == g).
     The rows get a large common offset (mean >> std) so a sum-of-squares style variance would visibly cancel."""
     n = 1024
     a = _rand((m, k), 1.0, 31, cuda_device, torch.bfloat16)
@@ -275,7 +276,7 @@ def test_gemm_residual_stats(ops, cuda_device, m, k):
     ref = x0.double() + a.double() @ w.double().T + bias.double()
     torch.testing.assert_close(x.double(), ref, rtol=1e-5, atol=2e-3)  # fp32 accumulate over K products + fp32 add
     assert torch.equal(h, x.to(torch.bfloat16))                       # the bf16 copy is the rounding of what was stored
-    xc = x.double().view(m, n // 256, 256)
+    xc = x.double().view(m, n // 256, 4, 2, 32).transpose(2, 3).reshape(m, n // 128, 128)  # [row, 2t + g, 128]
     torch.testing.assert_close(stats[..., 0].double(), xc.mean(-1), rtol=1e-6, atol=1e-5)
     m2 = ((xc - xc.mean(-1, keepdim=True)) ** 2).sum(-1)
     torch.testing.assert_close(stats[..., 1].double(), m2, rtol=2e-5, atol=1e-4)
@@ -295,8 +296,8 @@ def test_gemm_ln_consumer_equals_layernorm_then_linear(ops, cuda_device, relu, m
     torch.testing.assert_close(wf.float(), (w.float() * gamma).to(torch.bfloat16).float(), rtol=0, atol=0)
     torch.testing.assert_close(colsum, wf.float().sum(1), rtol=1e-5, atol=1e-4)
     torch.testing.assert_close(bias_f, bias + w.float() @ beta, rtol=1e-5, atol=1e-4)
-    # statistics as a producer would emit them: (mean, M2) per 256-column chunk
-    xc = x.double().view(m, k // 256, 256)
+    # statistics as a producer would emit them: (mean, M2) of 128-column subsets (any partition merges to the same result)
+    xc = x.double().view(m, k // 128, 128)
     stats = torch.stack([xc.mean(-1), ((xc - xc.mean(-1, keepdim=True)) ** 2).sum(-1)], -1).float().contiguous()
     out = ops.gemm_ln_consumer(x.to(torch.bfloat16), wf, bias_f, colsum, stats, 1e-5, relu=relu)
     torch.cuda.synchronize()
