@@ -603,8 +603,10 @@ def main():
     ap.add_argument("--seq-len", type=int, default=SEQ)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--cta-group", type=int, default=2)
-    ap.add_argument("--ln-fold", type=int, default=0, choices=[0, 1],
-                    help="0 = separate LayerNorm kernels (default schedule), 1 = LayerNorm folded into the GEMMs")
+    ap.add_argument("--ln-fold", type=int, default=0, choices=[0, 1, 2],
+                    help="0 = separate LayerNorm kernels (default schedule), 1 = LayerNorms folded into the GEMMs, "
+                         "2 = only the attention-block LayerNorm folded")
+    ap.add_argument("--epi-groups", type=int, default=2, choices=[1, 2], help="epilogue warpgroups per GEMM CTA")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-secondary", action="store_true", help="N=1: skip the predict / speech / decoder / xsim blocks")
     ap.add_argument("--only", default="", help="N=1: comma list of secondary blocks to run (predict,speech,decoder,xsim)")
@@ -639,11 +641,15 @@ def main():
     B, S = args.batch, args.seq_len
     sd = synthetic_state_dict(dev)
     model = B200TextEncoderModel(sonar_text_encoder_config("basic"), sd, dev, cta_group=args.cta_group,
-                                 ln_fold=bool(args.ln_fold))
-    model_alt = None
-    if rank == 0 and world == 1 and not args.skip_secondary:  # same-box A/B of the other LayerNorm schedule
-        model_alt = B200TextEncoderModel(sonar_text_encoder_config("basic"), sd, dev, cta_group=args.cta_group,
-                                         ln_fold=not bool(args.ln_fold))
+                                 ln_fold=args.ln_fold, epi_groups=args.epi_groups)
+    # same-box A/B of the engine's schedule variants (clock and power state differ box to box by ~10 %, so variants are only
+    # comparable inside one run): (ln_fold, epi_groups)
+    variants = {}
+    if rank == 0 and world == 1 and not args.skip_secondary:
+        for lf_, eg_ in ((0, 2), (0, 1), (2, 2), (1, 2)):
+            if (lf_, eg_) != (args.ln_fold, args.epi_groups):
+                variants[(lf_, eg_)] = B200TextEncoderModel(sonar_text_encoder_config("basic"), sd, dev,
+                                                            cta_group=args.cta_group, ln_fold=lf_, epi_groups=eg_)
     sd_cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         sd_cpu = {k: v.cpu() for k, v in sd.items()}
@@ -763,9 +769,9 @@ def main():
                     "whole_step_frac": (value / world) * flops_per_sentence(S) / 1e12 / peak}
         del a, f
 
-    # ---- same-box A/B: the other LayerNorm schedule, alternating 3-step blocks so clock drift hits both alike ----
+    # ---- same-box A/B of the schedule variants: alternating 3-step blocks so clock drift hits all of them alike ----
     ab = None
-    if model_alt is not None and (B, S) == (BATCH, SEQ):
+    if variants and (B, S) == (BATCH, SEQ):
         def run_n(m, k):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -775,20 +781,25 @@ def main():
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / k
 
-        run_n(model_alt, 2)
-        t_main, t_alt = [], []
-        for _ in range(2):
-            t_main.append(run_n(model, 3))
-            t_alt.append(run_n(model_alt, 3))
-        got_a = model(batch_dev).sentence_embeddings[:256].double()
-        got_b = model_alt(batch_dev).sentence_embeddings[:256].double()
-        rel = float(((got_a - got_b).norm(dim=1) / got_b.norm(dim=1)).max())
-        name = {True: "ln_folded", False: "ln_separate"}
-        ab = {name[bool(args.ln_fold)] + "_ms": t_main, name[not bool(args.ln_fold)] + "_ms": t_alt,
-              "sentences_per_s": {name[bool(args.ln_fold)]: B / (sum(t_main) / len(t_main)) * 1e3,
-                                  name[not bool(args.ln_fold)]: B / (sum(t_alt) / len(t_alt)) * 1e3},
-              "rel_l2_between_schedules_max": rel}
-        model_alt = None
+        def vname(lf_, eg_):
+            return {0: "ln_separate", 1: "ln_folded", 2: "ln1_folded"}[lf_] + f"/epi_groups{eg_}"
+
+        allv = {(args.ln_fold, args.epi_groups): model, **variants}
+        for m in variants.values():
+            run_n(m, 1)
+        times = {k: [] for k in allv}
+        for _ in range(3):
+            for k, m in allv.items():
+                times[k].append(run_n(m, 3))
+        ref_out = model(batch_dev).sentence_embeddings[:256].double()
+        ab = {"ms_per_step": {vname(*k): v for k, v in times.items()},
+              "sentences_per_s": {vname(*k): B / (sum(v) / len(v)) * 1e3 for k, v in times.items()},
+              "default": vname(args.ln_fold, args.epi_groups), "rel_l2_vs_default_max": {}}
+        for k, m in variants.items():
+            got = m(batch_dev).sentence_embeddings[:256].double()
+            ab["rel_l2_vs_default_max"][vname(*k)] = float(((got - ref_out).norm(dim=1) / ref_out.norm(dim=1)).max())
+        variants.clear()
+        allv.clear()
         torch.cuda.empty_cache()
 
     # ---- ragged variant: lengths U{16..128}; the engine packs tokens, the reference would pad to 128 ----
@@ -861,7 +872,7 @@ def main():
             torch.cuda.empty_cache()
 
     if rank == 0:
-        launches_per_step = 1 + LAYERS * (5 if args.ln_fold else 7) + 1  # embed, per layer 4 GEMMs + attention (+ 2 LN), pool
+        launches_per_step = 1 + LAYERS * {0: 7, 1: 5, 2: 6}[args.ln_fold] + 1  # embed, per layer 4 GEMMs + attention (+ LNs), pool
         line = {
             "metric": "sentences/sec->1024-d", "value": value, "unit": "sentences/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -872,8 +883,10 @@ def main():
                        "l2": "inputs larger than L2 (per-step activations ~15 GB vs 126 MB L2)",
                        "parallelism": f"dp{world}" + (" + all_gather of embeddings" if world > 1 else ""),
                        "cta_group": args.cta_group,
-                       "layernorm": "folded into the QKV / FFN1 GEMMs (statistics from the residual GEMMs' epilogues)"
-                                    if args.ln_fold else "separate kernels"},
+                       "layernorm": {0: "separate kernels", 1: "folded into the QKV / FFN1 GEMMs (statistics from the residual "
+                                     "GEMMs' epilogues)", 2: "attention-block LayerNorm folded (FFN2 -> QKV), FFN-block LayerNorm "
+                                     "a kernel"}[args.ln_fold],
+                       "epi_groups": args.epi_groups},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "sentences/s", "h2d_bytes_per_step": B * S * 8,
                     "d2h_bytes_per_step": B * D * 4, "ms_per_step": e2e_ms / args.steps},
@@ -881,7 +894,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "ragged": ragged,
-            "ab_layernorm_schedule": ab,
+            "ab_schedule_variants": ab,
             **extra,
         }
         if config5 is not None:

@@ -73,7 +73,11 @@ typedef struct SbEncoderConfig {
                           *     the residual GEMMs emit per-row statistics + a bf16 copy of the stream, the QKV / FFN1 GEMMs
                           *     apply (mean, rstd) in their epilogue on weights pre-multiplied by gamma; sb_encoder_create
                           *     prepares those weights in device memory it owns -- the caller's weights are not modified);
+                          * 2 = fold only the attention-block LayerNorm (FFN2 emits, QKV applies); the FFN-block LayerNorm
+                          *     stays a kernel (the out-projection is HBM-bound, its epilogue has no slack for the extra work);
                           * 0 = separate LayerNorm kernels (the round-1 schedule) */
+  int32_t epi_groups;    /* 0/2 = two epilogue warpgroups per GEMM CTA (default); 1 = one (round-1 kernel, kept for A/B runs;
+                          *     needs ln_fold = 0) */
 } SbEncoderConfig;
 
 /* All pointers are DEVICE pointers and stay owned by the caller (must outlive the handle).

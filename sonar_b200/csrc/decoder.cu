@@ -338,9 +338,9 @@ struct DecWs {
   float* cross;           // [L, N, D] per-sentence cross-attention constants
   __nv_bfloat16* ebf;     // [N, D] bf16 sentence embeddings
   __nv_bfloat16* vtmp;    // [N, D]
-  float* cand_val;        // [R, n_chunks, 16]
+  float* cand_val;        // [R, n_lists, 16]   n_lists = gemm_topk_lists(n_chunks)
   int* cand_idx;
-  float* lse_part;        // [R, n_chunks, 2]
+  float* lse_part;        // [R, n_lists, 2]
   __nv_bfloat16* kcache;  // [L, R, Tmax, D]
   __nv_bfloat16* vcache;
   int n_chunks;
@@ -363,9 +363,10 @@ DecWs carve_dec(const SbDecoder* d, int N, int beam, int Tmax, void* base) {
   w.cross = reinterpret_cast<float*>(take(L * (size_t)N * D * 4));
   w.ebf = reinterpret_cast<__nv_bfloat16*>(take((size_t)N * D * 2));
   w.vtmp = reinterpret_cast<__nv_bfloat16*>(take((size_t)N * D * 2));
-  w.cand_val = reinterpret_cast<float*>(take(R * w.n_chunks * kTopkCandidates * 4));
-  w.cand_idx = reinterpret_cast<int*>(take(R * w.n_chunks * kTopkCandidates * 4));
-  w.lse_part = reinterpret_cast<float*>(take(R * w.n_chunks * 2 * 4));
+  const size_t n_lists = (size_t)gemm_topk_lists(w.n_chunks);
+  w.cand_val = reinterpret_cast<float*>(take(R * n_lists * kTopkCandidates * 4));
+  w.cand_idx = reinterpret_cast<int*>(take(R * n_lists * kTopkCandidates * 4));
+  w.lse_part = reinterpret_cast<float*>(take(R * n_lists * 2 * 4));
   w.kcache = reinterpret_cast<__nv_bfloat16*>(take(L * R * (size_t)Tmax * D * 2));
   w.vcache = reinterpret_cast<__nv_bfloat16*>(take(L * R * (size_t)Tmax * D * 2));
   w.bytes = off;
@@ -385,7 +386,7 @@ int check_ws(const SbDecoder* d, int N, int beam, int Tmax, void* workspace, siz
                    (size_t)(base - reinterpret_cast<uintptr_t>(workspace)) + out->bytes);
     return SB_ERR_INVALID;
   }
-  if (out->n_chunks > 128) { set_last_error("sb_decoder: vocabulary split into too many chunks"); return SB_ERR_INVALID; }
+  if (gemm_topk_lists(out->n_chunks) > 128) { set_last_error("sb_decoder: vocabulary split into too many chunks"); return SB_ERR_INVALID; }
   return SB_OK;
 }
 
@@ -564,7 +565,7 @@ int sb_decoder_step(SbDecoder* d, const int64_t* tokens, const int32_t* table, i
                            w.cand_val, w.cand_idx, w.lse_part, w.n_chunks, 2, d->num_sms, stream)))
     return rc;
   vocab_merge_kernel<kTopkCandidates><<<row_blocks, 256, 0, stream>>>(
-      w.cand_val, w.cand_idx, w.lse_part, w.n_chunks, w.h, reinterpret_cast<const __nv_bfloat16*>(d->embed), D,
+      w.cand_val, w.cand_idx, w.lse_part, gemm_topk_lists(w.n_chunks), w.h, reinterpret_cast<const __nv_bfloat16*>(d->embed), D,
       d->cfg.eos_idx, R, out_lprob, out_tok, out_eos_lprob, probe_tokens, (long long)d->cfg.vocab_size, out_probe_lprob);
   SB_CUDA_CHECK(cudaGetLastError());
   return SB_OK;

@@ -130,7 +130,12 @@ int sb_encoder_create(const SbEncoderConfig* cfg, const SbEncoderWeights* w, SbE
     return SB_ERR_INVALID;
   }
   if (F <= 0 || F % 256 != 0) { set_last_error("sb_encoder_create: ffn_inner_dim must be a multiple of 256"); return SB_ERR_INVALID; }
-  if (cfg->ln_fold != 0 && cfg->ln_fold != 1) { set_last_error("sb_encoder_create: ln_fold must be 0 or 1"); return SB_ERR_INVALID; }
+  if (cfg->ln_fold < 0 || cfg->ln_fold > 2) { set_last_error("sb_encoder_create: ln_fold must be 0, 1 or 2"); return SB_ERR_INVALID; }
+  if (cfg->epi_groups < 0 || cfg->epi_groups > 2) { set_last_error("sb_encoder_create: epi_groups must be 0, 1 or 2"); return SB_ERR_INVALID; }
+  if (cfg->epi_groups == 1 && (cfg->ln_fold != 0 || cfg->cta_group == 1)) {
+    set_last_error("sb_encoder_create: epi_groups = 1 (the one-warpgroup epilogue kept for A/B runs) needs ln_fold = 0 and paired CTAs");
+    return SB_ERR_INVALID;
+  }
   if (cfg->num_layers < 0 || cfg->pos_rows <= 0 || cfg->vocab_size <= 0) {
     set_last_error("sb_encoder_create: bad num_layers / pos_rows / vocab_size");
     return SB_ERR_INVALID;
@@ -297,7 +302,8 @@ int sb_encoder_forward(SbEncoder* e, const int64_t* ids, int64_t ids_row_stride,
     return SB_OK;
   }
 
-  const bool fold = e->cfg.ln_fold != 0 && e->cfg.num_layers > 0;
+  const bool fold = e->cfg.ln_fold != 0 && e->cfg.num_layers > 0;  // LN1 (attention block) folded into FFN2 -> QKV
+  const bool fold2 = fold && e->cfg.ln_fold == 1;                   // LN2 (FFN block) folded into out-proj -> FFN1 as well
   __nv_bfloat16* hn = w.qkv;  // [T, D] view of the (dead after attention) qkv buffer: bf16(x) behind the out-projection
   int rc;
   if ((rc = embed_tokens(ids, ids_row_stride, w.cu, B, S, reinterpret_cast<const __nv_bfloat16*>(e->embed),
@@ -309,6 +315,7 @@ int sb_encoder_forward(SbEncoder* e, const int64_t* ids, int64_t ids_row_stride,
   g.cta_group = (e->cfg.cta_group == 1) ? 1 : 2;
   g.num_sms = e->num_sms;
   g.M = (int)T;
+  g.epi_groups = (e->cfg.epi_groups == 1) ? 1 : 2;
   LnFold consume;  // what a LayerNorm-consuming GEMM needs
   consume.stats_in = w.ln_stats;
   consume.chunks = D / kLnPartCols;
@@ -334,7 +341,7 @@ int sb_encoder_forward(SbEncoder* e, const int64_t* ids, int64_t ids_row_stride,
     g.A = w.h; g.lda = D; g.W = reinterpret_cast<const __nv_bfloat16*>(L.wo); g.ldw = D;
     g.C = w.x; g.ldc = D; g.out_fp32 = 1; g.bias = L.bo; g.residual = w.x; g.ldr = D;
     g.N = D; g.K = D; g.epi = EPI_BIAS_RESIDUAL;
-    if (fold) {  // emits x, hn = bf16(x) and the statistics LN2 needs
+    if (fold2) {  // emits x, hn = bf16(x) and the statistics LN2 needs
       g.epi = EPI_BIAS_RESIDUAL_STATS;
       g.lf.h_out = hn; g.lf.ldh = D; g.lf.stats_out = w.ln_stats;
     }
@@ -342,12 +349,12 @@ int sb_encoder_forward(SbEncoder* e, const int64_t* ids, int64_t ids_row_stride,
     g.lf = LnFold();
     if (rc) return rc;
     // --- feed-forward block: x += W2 . relu(W1 . LN2(x) + b1) + b2 ---
-    if (!fold)
+    if (!fold2)
       if ((rc = layernorm_bf16(w.x, L.ln2_g, L.ln2_b, e->cfg.ln_eps, w.h, T, D, stream))) return rc;
-    g.A = fold ? hn : w.h; g.lda = D; g.ldw = D;
+    g.A = fold2 ? hn : w.h; g.lda = D; g.ldw = D;
     g.C = w.f; g.ldc = F; g.out_fp32 = 0; g.residual = nullptr; g.ldr = 0;
     g.N = F; g.K = D; g.epi = EPI_BIAS_RELU;
-    if (fold) {
+    if (fold2) {
       const FoldedLayer& f = e->folded[li];
       g.W = f.w1; g.bias = f.b1; g.lf = consume; g.lf.colsum = f.c1;
     } else {
@@ -362,7 +369,7 @@ int sb_encoder_forward(SbEncoder* e, const int64_t* ids, int64_t ids_row_stride,
     g.A = w.f; g.lda = F; g.W = reinterpret_cast<const __nv_bfloat16*>(L.w2); g.ldw = F;
     g.C = w.x; g.ldc = D; g.out_fp32 = 1; g.bias = L.b2; g.residual = w.x; g.ldr = D;
     g.N = D; g.K = F; g.epi = EPI_BIAS_RESIDUAL;
-    if (fold) {  // emits x, h = bf16(x) and the statistics the next layer's LN1 needs
+    if (fold && li + 1 < e->cfg.num_layers) {  // emits x, h = bf16(x) and the statistics the next layer's LN1 needs
       g.epi = EPI_BIAS_RESIDUAL_STATS;
       g.lf.h_out = w.h; g.lf.ldh = D; g.lf.stats_out = w.ln_stats;
     }

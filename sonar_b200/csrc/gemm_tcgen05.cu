@@ -26,7 +26,7 @@
 
 namespace sb {
 
-template <int kCtaGroup>
+template <int kCtaGroup, int kEpiGroups = 2>
 struct GemmCfg {
   static constexpr int BLOCK_M = 128;                 // rows per CTA
   static constexpr int BLOCK_N = 256;                 // UMMA N
@@ -34,9 +34,11 @@ struct GemmCfg {
   static constexpr int LOAD_N = BLOCK_N / kCtaGroup;  // W rows each CTA stages
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = LOAD_N * BLOCK_K * 2;
-  static constexpr int STAGES = (kCtaGroup == 2) ? 5 : 3;
+  // 32 KB (cta_group::2) / 48 KB (cta_group::1) per mainloop stage; the staging buffers of the second epilogue warpgroup
+  // cost one stage
+  static constexpr int STAGES = (kCtaGroup == 2) ? (kEpiGroups == 2 ? 5 : 6) : (kEpiGroups == 2 ? 3 : 4);
   static constexpr int CD_STAGE_BYTES = 128 * 128;  // 128 rows x 128 B
-  static constexpr int EPI_GROUPS = 2;              // epilogue warpgroups (4 warps each), alternating column chunks
+  static constexpr int EPI_GROUPS = kEpiGroups;     // epilogue warpgroups (4 warps each), alternating column chunks
   static constexpr int CD_STAGES = 2;               // staging buffers per epilogue warpgroup
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES =
@@ -105,14 +107,14 @@ __device__ __forceinline__ void topk_insert(float (&tv)[KC], int (&ti)[KC], floa
   }
 }
 
-template <int kCtaGroup, int kEpi, typename OutT>
-__global__ void __launch_bounds__(GemmCfg<kCtaGroup>::THREADS, 1)
+template <int kCtaGroup, int kEpi, typename OutT, int kEpiGroups>
+__global__ void __launch_bounds__(GemmCfg<kCtaGroup, kEpiGroups>::THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                          const __grid_constant__ CUtensorMap tm_c, const float* __restrict__ bias,
                          const OutT* residual, long long ldr, int M, int N, int K, float* __restrict__ cand_val,
                          int* __restrict__ cand_idx, float* __restrict__ lse_part, int n_chunks, const LnFold lf) {
   constexpr bool kSweep = (kEpi == EPI_TOPK);
-  using Cfg = GemmCfg<kCtaGroup>;
+  using Cfg = GemmCfg<kCtaGroup, kEpiGroups>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -300,15 +302,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       if constexpr (kEpi == EPI_TOPK) {
-        if (wg != 0) {  // (the sweep epilogue keeps its per-row state in ONE thread: the second warpgroup only arrives)
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (kCtaGroup == 2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
-            else mbar_arrive(&tmem_empty_bar[acc]);
-          }
-          continue;
-        }
         // ---- running per-row top-KC over the whole sweep of n tiles (no C matrix is ever written) ----
         if (first_in_item) {
 #pragma unroll
@@ -316,8 +309,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           run_max = -CUDART_INF_F;
           run_sum = 0.f;
         }
+        // each epilogue warpgroup sweeps ITS 32-column sub-chunks (c % 2 == wg) and keeps its own list: a row ends up with
+        // EPI_GROUPS lists per n-chunk, merged by the caller's next kernel
 #pragma unroll 1
-        for (int c = 0; c < Cfg::BLOCK_N / 32; ++c) {
+        for (int c = wg; c < Cfg::BLOCK_N / 32; c += Cfg::EPI_GROUPS) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + (uint32_t(ew * 32) << 16) + acc * Cfg::BLOCK_N + c * 32, v);
           tmem_ld_wait();
@@ -363,7 +358,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           else mbar_arrive(&tmem_empty_bar[acc]);
         }
         if (last_in_item && grow < M) {
-          const long long slot = (long long)grow * n_chunks + chunk;
+          const long long slot = ((long long)grow * n_chunks + chunk) * Cfg::EPI_GROUPS + wg;
 #pragma unroll
           for (int p = 0; p < KC; ++p) {
             cand_val[slot * KC + p] = tv[p];
@@ -577,13 +572,13 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long ro
   return 0;
 }
 
-template <int kCtaGroup, int kEpi, typename OutT>
+template <int kCtaGroup, int kEpi, typename OutT, int kEpiGroups = 2>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const float* bias,
                        const void* residual, long long ldr, int M, int N, int K, int num_sms, cudaStream_t stream,
                        float* cand_val = nullptr, int* cand_idx = nullptr, float* lse_part = nullptr,
                        int n_chunks = 1, const LnFold& lf = LnFold()) {
-  using Cfg = GemmCfg<kCtaGroup>;
-  auto kern = gemm_bf16_tcgen05_kernel<kCtaGroup, kEpi, OutT>;
+  using Cfg = GemmCfg<kCtaGroup, kEpiGroups>;
+  auto kern = gemm_bf16_tcgen05_kernel<kCtaGroup, kEpi, OutT, kEpiGroups>;
   static bool attr_set[64] = {};
   if (first_use_on_device(attr_set)) {
     SB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -626,8 +621,9 @@ int gemm_topk_chunks(int M, int N, int cta_group, int num_sms) {
 }
 
 // Per-row top-kTopkCandidates of A[M,K] . W[N,K]^T (bf16 operands, fp32 accumulate) without materialising
-// the product.  Outputs are per (row, chunk): cand_val / cand_idx [M, n_chunks, kTopkCandidates] sorted by value
-// descending, and (optional) lse_part [M, n_chunks, 2] = (max, sum exp(v - max)) over the chunk's columns.
+// the product.  Outputs are per (row, list) with kTopkLists(n_chunks) = 2 * n_chunks lists per row (one per n-chunk and
+// epilogue warpgroup; a list covers a disjoint subset of the columns): cand_val / cand_idx [M, lists, kTopkCandidates]
+// sorted by value descending, and (optional) lse_part [M, lists, 2] = (max, sum exp(v - max)) over the list's columns.
 int gemm_bf16_topk(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
                    float* cand_val, int* cand_idx, float* lse_part, int n_chunks, int cta_group, int num_sms,
                    cudaStream_t stream) {
@@ -703,6 +699,20 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   } else if (g.lf.h_out != nullptr || g.lf.stats_out != nullptr) {
     set_last_error("gemm_bf16: h_out / stats_out are outputs of EPI_BIAS_RESIDUAL_STATS only");
     return -1;
+  }
+
+  // A/B variant: ONE epilogue warpgroup + 6 mainloop stages (the round-1 kernel) for the text encoder's four GEMMs
+  if (g.epi_groups == 1) {
+    if (cg != 2 || (epi != EPI_BIAS && epi != EPI_BIAS_RELU && epi != EPI_BIAS_ACCUM) || g.lf.stats_in != nullptr) {
+      set_last_error("gemm_bf16: epi_groups = 1 is only built for the paired-CTA bias / bias+ReLU / accumulate epilogues");
+      return -1;
+    }
+    if (epi == EPI_BIAS_ACCUM)
+      return launch_inst<2, EPI_BIAS_ACCUM, float, 1>(ta, tb, tc, g.bias, g.residual, g.ldr, g.M, g.N, g.K, sms, stream);
+    if (g.out_fp32) { set_last_error("gemm_bf16: epi_groups = 1 needs bf16 output for bias / bias+ReLU"); return -1; }
+    if (epi == EPI_BIAS)
+      return launch_inst<2, EPI_BIAS, __nv_bfloat16, 1>(ta, tb, tc, g.bias, g.residual, g.ldr, g.M, g.N, g.K, sms, stream);
+    return launch_inst<2, EPI_BIAS_RELU, __nv_bfloat16, 1>(ta, tb, tc, g.bias, g.residual, g.ldr, g.M, g.N, g.K, sms, stream);
   }
 
 #define SB_DISPATCH(CG, EPI, T)                                                                                   \

@@ -72,6 +72,9 @@ struct GemmArgs {
   // tiles, so a caller that promises results independent of the batch size across the M = 64 boundary (the text
   // encoder: bitwise batch-composition invariance) leaves it off; the decoder step and the speech pooler turn it on.
   int allow_skinny = 0;
+  // 2 (default) = two epilogue warpgroups / 5 mainloop stages; 1 = one epilogue warpgroup / 6 stages (A/B variant, only
+  // for the text encoder's bias, bias+ReLU and accumulate epilogues with paired CTAs)
+  int epi_groups = 2;
 };
 
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
@@ -81,6 +84,9 @@ bool gemm_skinny_eligible(const GemmArgs& g);
 int gemm_skinny(const GemmArgs& g, cudaStream_t stream);
 
 int gemm_topk_chunks(int M, int N, int cta_group, int num_sms);
+// candidate lists per row that gemm_bf16_topk writes for a given n_chunks (two epilogue warpgroups per n-chunk)
+constexpr int kTopkListsPerChunk = 2;
+inline int gemm_topk_lists(int n_chunks) { return kTopkListsPerChunk * n_chunks; }
 int gemm_bf16_topk(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
                    float* cand_val, int* cand_idx, float* lse_part, int n_chunks, int cta_group, int num_sms,
                    cudaStream_t stream);

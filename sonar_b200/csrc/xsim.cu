@@ -4,12 +4,12 @@
 //
 // Pipeline for knn(x[n,d], y[m,d], k):
 //   1. l2_normalize: fp32 rows -> unit-norm bf16 rows (+ fp64 norms)                     [HBM-bound]
-//   2. gemm_bf16_topk: tcgen05 GEMM x^ . y^T whose epilogue keeps a running top-16 per row
-//      in registers -- the n x m similarity matrix is never written                      [tensor-bound]
-//   3. exact re-rank of the 16 candidates per row in fp64 from the RAW fp32 embeddings
+//   2. gemm_bf16_topk: tcgen05 GEMM x^ . y^T whose two epilogue warpgroups each keep a running top-16 per row
+//      in registers (32 candidates per row) -- the n x m similarity matrix is never written  [tensor-bound]
+//   3. exact re-rank of the 16 best of those 32 (by bf16 score) in fp64 from the RAW fp32 embeddings
 //      (cos = <x,y> / (|x||y|)), order (score desc, index asc), keep k                   [gather, L2/HBM]
 // so the final neighbours/scores do not depend on bf16 rounding as long as the true top-k are among the
-// 16 bf16 candidates.
+// 16 best bf16 candidates.
 
 #include "../../include/sonar_b200.h"
 #include "common.cuh"
@@ -46,46 +46,64 @@ l2_normalize_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xn,
   if (lane == 0) norm[row] = nr;
 }
 
-// one warp per x row: exact fp64 cosine of the KC candidates, keep the best k by (score desc, index asc)
-template <int KC>
+// one warp per x row: the KC (<= 32) bf16 candidates of the row's lists are first cut to the KEEP best by bf16 score (one
+// candidate per lane, rank by 32 shuffles), those get their exact fp64 cosine, and the best k by (score desc, index asc)
+// are written
+template <int KC, int KEEP>
 __global__ void __launch_bounds__(256)
 rerank_kernel(const float* __restrict__ x, const float* __restrict__ y, const double* __restrict__ nx,
-              const double* __restrict__ ny, const int* __restrict__ cand_idx, int n, int m, int d, int k,
-              double* __restrict__ out_val, int* __restrict__ out_idx) {
+              const double* __restrict__ ny, const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int n,
+              int m, int d, int k, double* __restrict__ out_val, int* __restrict__ out_idx) {
+  static_assert(KC <= 32 && KEEP <= KC, "one candidate per lane");
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * d);
+  int cj = (lane < KC) ? cand_idx[(long long)row * KC + lane] : -1;
+  float cv = (lane < KC) ? cand_val[(long long)row * KC + lane] : -CUDART_INF_F;
+  if (cj < 0 || cj >= m) { cj = -1; cv = -CUDART_INF_F; }
+  int pre = 0;  // rank of this lane's candidate by (bf16 score desc, index asc); invalid ones rank last
+  for (int c = 0; c < 32; ++c) {
+    const float ov = __shfl_sync(0xffffffffu, cv, c);
+    const int oj = __shfl_sync(0xffffffffu, cj, c);
+    if (oj >= 0 && (cj < 0 || ov > cv || (ov == cv && oj < cj))) ++pre;
+  }
+  unsigned keep = __ballot_sync(0xffffffffu, cj >= 0 && pre < KEEP);
   double my_score = -CUDART_INF;
   int my_idx = 0x7fffffff;
-  for (int c = 0; c < KC; ++c) {
-    const int j = cand_idx[(long long)row * KC + c];
+  while (keep) {
+    const int c = __ffs(keep) - 1;
+    keep &= keep - 1;
+    const int j = __shfl_sync(0xffffffffu, cj, c);
+    const float4* yr = reinterpret_cast<const float4*>(y + (long long)j * d);
     double dot = 0.0;
-    if (j >= 0 && j < m) {
-      const float4* yr = reinterpret_cast<const float4*>(y + (long long)j * d);
-      for (int q = lane; q < d / 4; q += 32) {
-        const float4 a = xr[q], b = yr[q];
-        dot += (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
-      }
+    for (int q = lane; q < d / 4; q += 32) {
+      const float4 a = xr[q], b = yr[q];
+      dot += (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    if (lane == c && j >= 0 && j < m) {
+    if (lane == c) {
       my_score = dot / fmax(nx[row] * ny[j], 1e-300);
       my_idx = j;
     }
   }
-  // rank of lane's candidate among the KC (lanes >= KC hold -inf / INT_MAX and rank last)
+  // rank of lane's candidate among the rescored ones (the others hold -inf / INT_MAX and rank last)
   int rank = 0;
-  for (int c = 0; c < KC; ++c) {
+  for (int c = 0; c < 32; ++c) {
     const double s = __shfl_sync(0xffffffffu, my_score, c);
     const int i = __shfl_sync(0xffffffffu, my_idx, c);
     if (s > my_score || (s == my_score && i < my_idx)) ++rank;
   }
-  if (lane < KC && rank < k) {
-    const bool valid = my_idx != 0x7fffffff;
-    out_val[(long long)row * k + rank] = valid ? my_score : -CUDART_INF;
-    out_idx[(long long)row * k + rank] = valid ? my_idx : -1;
+  const bool valid = my_idx != 0x7fffffff;
+  if (valid && rank < k) {
+    out_val[(long long)row * k + rank] = my_score;
+    out_idx[(long long)row * k + rank] = my_idx;
+  }
+  const int nvalid = __popc(__ballot_sync(0xffffffffu, valid));
+  if (lane >= nvalid && lane < k) {  // fewer than k candidates (m < k): the tail is (-inf, -1)
+    out_val[(long long)row * k + lane] = -CUDART_INF;
+    out_idx[(long long)row * k + lane] = -1;
   }
 }
 
@@ -121,6 +139,10 @@ __global__ void margin_predict_kernel(const double* __restrict__ val_xy, const i
   pred[i] = best_j;
 }
 
+// bf16-similarity candidates per row handed to the exact re-rank: one n-chunk -> gemm_topk_lists(1) lists of 16
+constexpr int kXsimCands = kTopkListsPerChunk * kTopkCandidates;
+static_assert(kXsimCands <= 32, "rerank_kernel maps one candidate to one lane");
+
 struct XsimWs {
   __nv_bfloat16* xn;
   __nv_bfloat16* yn;
@@ -139,8 +161,8 @@ static XsimWs carve_xsim(int n, int m, int d, void* base) {
   w.yn = reinterpret_cast<__nv_bfloat16*>(p + off); off = align_up_sz(off + (size_t)m * d * 2, 1024);
   w.nx = reinterpret_cast<double*>(p + off); off = align_up_sz(off + (size_t)n * 8, 1024);
   w.ny = reinterpret_cast<double*>(p + off); off = align_up_sz(off + (size_t)m * 8, 1024);
-  w.cand_val = reinterpret_cast<float*>(p + off); off = align_up_sz(off + (size_t)n * kTopkCandidates * 4, 1024);
-  w.cand_idx = reinterpret_cast<int*>(p + off); off = align_up_sz(off + (size_t)n * kTopkCandidates * 4, 1024);
+  w.cand_val = reinterpret_cast<float*>(p + off); off = align_up_sz(off + (size_t)n * kXsimCands * 4, 1024);
+  w.cand_idx = reinterpret_cast<int*>(p + off); off = align_up_sz(off + (size_t)n * kXsimCands * 4, 1024);
   w.bytes = off;
   return w;
 }
@@ -178,7 +200,7 @@ int sb_xsim_knn(const float* x, const float* y, int32_t n, int32_t m, int32_t d,
   SB_CUDA_CHECK(cudaGetLastError());
   int rc = gemm_bf16_topk(w.xn, d, w.yn, d, n, m, d, w.cand_val, w.cand_idx, nullptr, 1, 2, sms, stream);
   if (rc) return rc;
-  rerank_kernel<kTopkCandidates><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(x, y, w.nx, w.ny, w.cand_idx, n, m, d, k,
+  rerank_kernel<kXsimCands, kTopkCandidates><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(x, y, w.nx, w.ny, w.cand_val, w.cand_idx, n, m, d, k,
                                                                              out_val, out_idx);
   SB_CUDA_CHECK(cudaGetLastError());
   return SB_OK;

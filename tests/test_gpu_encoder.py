@@ -209,8 +209,10 @@ def test_layernorm_folded_into_the_gemms_matches_the_separate_kernels(native_lib
             sd[k] = 0.5 * torch.randn(sd[k].shape, generator=g)
     cfg = sonar_text_encoder_config("basic", num_encoder_layers=3,
                                     vocab_info=VocabularyInfo(size=VOCAB, unk_idx=1, bos_idx=2, eos_idx=3, pad_idx=1))
-    folded = B200TextEncoderModel(cfg, sd, cuda_device, ln_fold=True)
-    classic = B200TextEncoderModel(cfg, sd, cuda_device, ln_fold=False)
+    folded = B200TextEncoderModel(cfg, sd, cuda_device, ln_fold=1)       # both LayerNorms of a layer folded
+    folded1 = B200TextEncoderModel(cfg, sd, cuda_device, ln_fold=2)      # only the attention-block LayerNorm
+    classic = B200TextEncoderModel(cfg, sd, cuda_device, ln_fold=0)
+    one_group = B200TextEncoderModel(cfg, sd, cuda_device, ln_fold=0, epi_groups=1)  # round-1 epilogue (A/B variant)
     if lens_kind == "dense":
         lens = [128] * 320  # 40 960 rows = 160 pair tiles x 4 n-tiles
     else:
@@ -225,6 +227,10 @@ def test_layernorm_folded_into_the_gemms_matches_the_separate_kernels(native_lib
     assert m["one_minus_cos_max"] <= 1e-5 and m["rel_l2_max"] <= 5e-3, m
     for _ in range(2):  # deterministic
         assert torch.equal(folded(SequenceBatch(ids.to(cuda_device), mask)).sentence_embeddings, got)
+    m1 = parity_metrics(folded1(SequenceBatch(ids.to(cuda_device), mask)).sentence_embeddings, want.cpu())
+    assert m1["one_minus_cos_max"] <= 1e-5 and m1["rel_l2_max"] <= 5e-3, m1
+    # one or two epilogue warpgroups: the same arithmetic per element, only who computes which column chunk differs
+    assert torch.equal(one_group(SequenceBatch(ids.to(cuda_device), mask)).sentence_embeddings, want)
     rows = list(range(0, len(lens), 23))
     ref, _ = OracleTextEncoder(ocfg, sd)(ids[rows], torch.tensor([lens[i] for i in rows]))
     _check(parity_metrics(got[rows], ref), "3-layer folded LayerNorm vs oracle")
