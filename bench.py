@@ -606,7 +606,7 @@ def main():
     ap.add_argument("--ln-fold", type=int, default=0, choices=[0, 1, 2],
                     help="0 = separate LayerNorm kernels (default schedule), 1 = LayerNorms folded into the GEMMs, "
                          "2 = only the attention-block LayerNorm folded")
-    ap.add_argument("--epi-groups", type=int, default=2, choices=[1, 2], help="epilogue warpgroups per GEMM CTA")
+    ap.add_argument("--epi-groups", type=int, default=1, choices=[1, 2], help="epilogue warpgroups per GEMM CTA")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-secondary", action="store_true", help="N=1: skip the predict / speech / decoder / xsim blocks")
     ap.add_argument("--only", default="", help="N=1: comma list of secondary blocks to run (predict,speech,decoder,xsim)")
@@ -646,7 +646,7 @@ def main():
     # comparable inside one run): (ln_fold, epi_groups)
     variants = {}
     if rank == 0 and world == 1 and not args.skip_secondary:
-        for lf_, eg_ in ((0, 2), (0, 1), (2, 2), (1, 2)):
+        for lf_, eg_ in ((0, 1), (0, 2), (2, 2), (1, 2)):
             if (lf_, eg_) != (args.ln_fold, args.epi_groups):
                 variants[(lf_, eg_)] = B200TextEncoderModel(sonar_text_encoder_config("basic"), sd, dev,
                                                             cta_group=args.cta_group, ln_fold=lf_, epi_groups=eg_)

@@ -258,13 +258,13 @@ vocab_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ c
   const int total = n_chunks * KC;
   const float* cv = cand_val + (long long)r * total;
   const int* ci = cand_idx + (long long)r * total;
-  unsigned long long taken = 0ull;  // lane-local bitmap over its slice (slice <= 64 entries: n_chunks <= 128)
+  unsigned long long taken0 = 0ull, taken1 = 0ull;  // lane-local bitmap over its slice (slice <= 128 entries: n_lists <= 256)
   for (int k = 0; k < KC; ++k) {
     float bv = -CUDART_INF_F;
     int bi = 0x7fffffff, bpos = -1;
     int s = 0;
     for (int p = lane; p < total; p += 32, ++s) {
-      if (taken & (1ull << s)) continue;
+      if (((s < 64) ? taken0 : taken1) & (1ull << (s & 63))) continue;
       const float v = cv[p];
       const int i = ci[p];
       if (i < 0) continue;
@@ -279,7 +279,9 @@ vocab_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ c
       const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
       if (ov > wv || (ov == wv && oi < wi)) { wv = ov; wi = oi; }
     }
-    if (bpos >= 0 && bv == wv && bi == wi) taken |= (1ull << bpos);  // token ids are unique -> exactly one lane
+    if (bpos >= 0 && bv == wv && bi == wi) {  // token ids are unique -> exactly one lane
+      if (bpos < 64) taken0 |= (1ull << bpos); else taken1 |= (1ull << (bpos - 64));
+    }
     if (lane == 0) {
       const bool valid = wi != 0x7fffffff;
       out_lprob[(long long)r * KC + k] = valid ? (wv - lse) : -CUDART_INF_F;
@@ -386,7 +388,7 @@ int check_ws(const SbDecoder* d, int N, int beam, int Tmax, void* workspace, siz
                    (size_t)(base - reinterpret_cast<uintptr_t>(workspace)) + out->bytes);
     return SB_ERR_INVALID;
   }
-  if (gemm_topk_lists(out->n_chunks) > 128) { set_last_error("sb_decoder: vocabulary split into too many chunks"); return SB_ERR_INVALID; }
+  if (gemm_topk_lists(out->n_chunks) > 256) { set_last_error("sb_decoder: vocabulary split into too many chunks"); return SB_ERR_INVALID; }
   return SB_OK;
 }
 

@@ -139,10 +139,12 @@ class B200TextEncoderModel(torch.nn.Module):
     """SONAR text encoder (24-layer pre-LN Transformer + final LN + pooling) on sm_100a kernels."""
 
     def __init__(self, config: SonarTextEncoderConfig, state_dict: Dict[str, Tensor],
-                 device: Union[str, torch.device] = "cuda", *, cta_group: int = 2, ln_fold: Union[bool, int] = False, epi_groups: int = 2) -> None:
+                 device: Union[str, torch.device] = "cuda", *, cta_group: int = 2, ln_fold: Union[bool, int] = False, epi_groups: int = 1) -> None:
         """``ln_fold=True``: the engine folds every encoder-layer LayerNorm into the GEMMs around it (see
         ``SbEncoderConfig.ln_fold`` in ``include/sonar_b200.h``); the default runs the separate LayerNorm kernels, which is
-        the faster schedule as measured (``bench.py`` reports both every run under ``ab_layernorm_schedule``)."""
+        the faster schedule as measured.  ``epi_groups``: epilogue warpgroups per GEMM CTA -- 1 (six mainloop stages) is the
+        default here: inside the power-capped 24-layer step it is 2 % faster than 2 (five stages), although 2 wins by 9-33 %
+        when a GEMM is timed alone at boost clocks (``bench.py`` A/Bs all of these in every run, ``ab_schedule_variants``)."""
         super().__init__()
         self.ln_fold = int(ln_fold)  # 0 = separate LayerNorm kernels, 1 = both folded, 2 = only the attention-block one
         self.epi_groups = int(epi_groups)
