@@ -242,6 +242,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     [[maybe_unused]] float tv[KC];
     [[maybe_unused]] int ti[KC];
     [[maybe_unused]] float run_max = -CUDART_INF_F, run_sum = 0.f;  // online log-sum-exp of the row (optional)
+    [[maybe_unused]] int q_n = 0;  // top-k sweep: candidates pending in this thread's shared-memory queue
     // ---- LayerNorm folding, consumer side: the (mean, M2) partials of this thread's input row are fetched ONE TILE AHEAD
     // (a lookahead copy of the scheduler names the next tile) so their latency hides under the current tile's epilogue ----
     [[maybe_unused]] bool fold_in = false;
@@ -310,7 +311,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           run_sum = 0.f;
         }
         // each epilogue warpgroup sweeps ITS 32-column sub-chunks (c % 2 == wg) and keeps its own list: a row ends up with
-        // EPI_GROUPS lists per n-chunk, merged by the caller's next kernel
+        // EPI_GROUPS lists per n-chunk, merged by the caller's next kernel.
+        // Candidates are not inserted where they are found: a thread PUSHES (value, column) of every element above its
+        // current 16th value into a small queue in shared memory (the idle output staging buffer) and the warp drains all
+        // 32 queues together when one fills up.  Inserting in place costs the whole warp ~80 instructions whenever ANY lane
+        // qualifies (32 rows with independent insertion events -> ~2500 instructions per tile per warp on random logits);
+        // drained together, a round of insertions serves every lane that has one pending.  Same elements, same order per
+        // row, same result bit for bit.
+        constexpr int kQ = 16;  // queue entries per thread; drained once any lane holds more than kQ - 8
+        uint2* queue = reinterpret_cast<uint2*>(smem_cd_wg) + row_in_tile;  // entry e of this thread at queue[e * 128]
+        auto drain = [&]() {
+          const int rounds = __reduce_max_sync(0xffffffffu, q_n);
+          for (int r = 0; r < rounds; ++r) {
+            if (r < q_n) {
+              const uint2 e = queue[r * 128];
+              const float x = __uint_as_float(e.x);
+              if (x > tv[KC - 1]) topk_insert<KC>(tv, ti, x, int(e.y));
+            }
+          }
+          q_n = 0;
+        };
 #pragma unroll 1
         for (int c = wg; c < Cfg::BLOCK_N / 32; c += Cfg::EPI_GROUPS) {
           uint32_t v[32];
@@ -322,10 +342,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             for (int j = 0; j < 32; ++j)
               if (gcol + j >= N) v[j] = __float_as_uint(-CUDART_INF_F);
           }
-          if (lse_part != nullptr) {  // online log-sum-exp over every column of the row (fp32, like log_softmax)
-            float cm = __uint_as_float(v[0]);
+          // maxima of the four 8-column groups: shared by the candidate pre-filter and the log-sum-exp
+          float gm[4];
 #pragma unroll
-            for (int j = 1; j < 32; ++j) cm = fmaxf(cm, __uint_as_float(v[j]));
+          for (int g8 = 0; g8 < 4; ++g8) {
+            float mx = __uint_as_float(v[g8 * 8]);
+#pragma unroll
+            for (int j = 1; j < 8; ++j) mx = fmaxf(mx, __uint_as_float(v[g8 * 8 + j]));
+            gm[g8] = mx;
+          }
+          if (lse_part != nullptr) {  // online log-sum-exp over every column of the row (fp32, like log_softmax)
+            const float cm = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
             if (cm > run_max) {
               run_sum *= __expf(run_max - cm);  // exp(-inf) = 0 on the first chunk
               run_max = cm;
@@ -337,20 +364,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
               run_sum += cs;
             }
           }
+          const float thr = tv[KC - 1];  // (stale between drains: a few extra pushes, rejected when drained)
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
-            float mx = __uint_as_float(v[g8 * 8]);
-#pragma unroll
-            for (int j = 1; j < 8; ++j) mx = fmaxf(mx, __uint_as_float(v[g8 * 8 + j]));
-            if (mx > tv[KC - 1]) {
+            if (gm[g8] > thr) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float x = __uint_as_float(v[g8 * 8 + j]);
-                if (x > tv[KC - 1]) topk_insert<KC>(tv, ti, x, gcol + g8 * 8 + j);
+                if (x > thr) {
+                  queue[q_n * 128] = make_uint2(__float_as_uint(x), uint32_t(gcol + g8 * 8 + j));
+                  ++q_n;
+                }
               }
             }
+            if (__any_sync(0xffffffffu, q_n > kQ - 8)) drain();
           }
         }
+        if (last_in_item) drain();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
