@@ -59,7 +59,7 @@ class SbDecoderWeights(C.Structure):
 class SbSpeechConfig(C.Structure):
     _fields_ = [("model_dim", C.c_int32), ("num_layers", C.c_int32), ("num_heads", C.c_int32),
                 ("ffn_inner_dim", C.c_int32), ("conv_kernel", C.c_int32), ("pooler_layers", C.c_int32),
-                ("pooler_ffn_inner_dim", C.c_int32), ("ln_eps", C.c_float)]
+                ("pooler_ffn_inner_dim", C.c_int32), ("ln_eps", C.c_float), ("attn_impl", C.c_int32)]
 
 
 CONFORMER_FIELDS = ("ffn1_ln_g", "ffn1_ln_b", "ffn1_w1", "ffn1_b1", "ffn1_w2", "ffn1_b2", "attn_ln_g", "attn_ln_b",

@@ -18,7 +18,7 @@ ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIB_DIR = ROOT / "lib"
 LIB_PATH = LIB_DIR / "libsonar_b200.so"
-SOURCES = ["encoder.cu", "gemm_tcgen05.cu", "gemm_skinny.cu", "attention.cu", "attention_tc.cu", "elementwise.cu", "xsim.cu", "decoder.cu", "beam.cu", "fbank.cu", "conformer.cu"]
+SOURCES = ["encoder.cu", "gemm_tcgen05.cu", "gemm_skinny.cu", "attention.cu", "attention_tc.cu", "elementwise.cu", "xsim.cu", "decoder.cu", "beam.cu", "fbank.cu", "conformer.cu", "attention_relpos_tc.cu"]
 HEADERS = ["common.cuh", "sonar_b200_internal.h", "../../include/sonar_b200.h"]
 
 NVCC_FLAGS = [

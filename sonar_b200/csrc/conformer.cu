@@ -579,6 +579,8 @@ struct SpWs {
   __nv_bfloat16* big;   // [T,max(F,3D,2D)]
   __nv_bfloat16* p;     // [Npad,D]
   float* vp;            // [H,Npad]
+  __nv_bfloat16* qu;    // [T,D]
+  __nv_bfloat16* qv;    // [T,D]
   __nv_bfloat16* e;     // [T,D] pooler memory
   float* px;            // [B,D]
   __nv_bfloat16* ph;    // [B,D]
@@ -604,6 +606,8 @@ SpWs carve_sp(const SbSpeechEncoder* e, int B, long long T, int smax, void* base
   w.big = reinterpret_cast<__nv_bfloat16*>(take(t * wide * 2));
   w.p = reinterpret_cast<__nv_bfloat16*>(take(np * D * 2));
   w.vp = reinterpret_cast<float*>(take(H * np * 4));
+  w.qu = reinterpret_cast<__nv_bfloat16*>(take(t * D * 2));  // bf16(q + u), bf16(q + v): A operands of the tcgen05 attention
+  w.qv = reinterpret_cast<__nv_bfloat16*>(take(t * D * 2));
   w.e = reinterpret_cast<__nv_bfloat16*>(take(t * D * 2));
   w.px = reinterpret_cast<float*>(take((size_t)B * D * 4));
   w.ph = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * D * 2));
@@ -622,7 +626,8 @@ int sb_speech_encoder_create(const SbSpeechConfig* cfg, const SbSpeechWeights* w
   *out = nullptr;
   const int D = cfg->model_dim, H = cfg->num_heads;
   if (D <= 0 || D % 256 != 0 || D > 1024 || H <= 0 || D != 64 * H || cfg->ffn_inner_dim % 256 != 0 ||
-      cfg->pooler_ffn_inner_dim % 256 != 0 || cfg->conv_kernel != 31 || cfg->num_layers < 0 || cfg->pooler_layers < 0) {
+      cfg->pooler_ffn_inner_dim % 256 != 0 || cfg->conv_kernel != 31 || cfg->num_layers < 0 || cfg->pooler_layers < 0 ||
+      cfg->attn_impl < 0 || cfg->attn_impl > 1) {
     set_last_error("sb_speech_encoder_create: unsupported configuration (need d%%256==0 <=1024, head_dim 64, conv kernel 31)");
     return SB_ERR_INVALID;
   }
@@ -741,11 +746,17 @@ int sb_speech_encoder_forward(SbSpeechEncoder* e, const float* fbank, int32_t pa
     if ((rc = layernorm_bf16(w.x, L.attn_ln_g, L.attn_ln_b, eps, w.h, T, D, stream))) return rc;
     if ((rc = gemm(w.h, D, L.wqkv, D, w.big, 3 * D, 0, L.bqkv, (int)T, 3 * D, D, EPI_BIAS))) return rc;
     if ((rc = gemm(reinterpret_cast<const __nv_bfloat16*>(relpos_table), D, L.wr, D, w.p, D, 0, e->w.zeros, Npad, D, D, EPI_BIAS))) return rc;
-    relpos_bias_kernel<<<dim3((unsigned)((Npad + 7) / 8), (unsigned)H), 256, 0, stream>>>(w.p, L.v_bias, Npad, H, w.vp);
-    SB_CUDA_CHECK(cudaGetLastError());
-    attention_relpos_kernel<<<dim3((unsigned)((smax + 127) / 128), (unsigned)H, (unsigned)B), kRpThreads, kRpSmem, stream>>>(
-        tm_qkv, tm_p, cu_dev, H, L.u_bias, w.vp, Npad, smax, w.h);
-    SB_CUDA_CHECK(cudaGetLastError());
+    if (e->cfg.attn_impl == 1 || B > 2047) {  // mma.sync kernel (A/B runs, second implementation in the tests)
+      relpos_bias_kernel<<<dim3((unsigned)((Npad + 7) / 8), (unsigned)H), 256, 0, stream>>>(w.p, L.v_bias, Npad, H, w.vp);
+      SB_CUDA_CHECK(cudaGetLastError());
+      attention_relpos_kernel<<<dim3((unsigned)((smax + 127) / 128), (unsigned)H, (unsigned)B), kRpThreads, kRpSmem, stream>>>(
+          tm_qkv, tm_p, cu_dev, H, L.u_bias, w.vp, Npad, smax, w.h);
+      SB_CUDA_CHECK(cudaGetLastError());
+    } else {  // tcgen05 (attention_relpos_tc.cu)
+      if ((rc = attention_relpos_tc(w.big, w.p, L.u_bias, L.v_bias, cu_dev, B, H, T, Npad, smax, w.qu, w.qv, w.h, e->num_sms,
+                                    stream)))
+        return rc;
+    }
     if ((rc = gemm(w.h, D, L.wo, D, w.x, D, 1, L.bo, (int)T, D, D, EPI_BIAS_RESIDUAL))) return rc;
     // (c) convolution module
     if ((rc = layernorm_bf16(w.x, L.conv_ln_g, L.conv_ln_b, eps, w.h, T, D, stream))) return rc;

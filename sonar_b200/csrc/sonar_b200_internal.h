@@ -119,6 +119,12 @@ int attention_packed(const __nv_bfloat16* qkv, const int32_t* cu_seqlens, int B,
 int attention_packed_tc(const __nv_bfloat16* qkv, const int32_t* cu_seqlens, int B, int H, long long total_tokens,
                         __nv_bfloat16* out, int num_sms, cudaStream_t stream);
 
+// Transformer-XL relative-position attention of the Conformer blocks on tcgen05 (attention_relpos_tc.cu):
+// score(i,j) = ((q_i+u).k_j + (q_i+v).p[S_center-1-i+j]) / 8; qu / qv = [T, D] bf16 scratch for the biased queries
+int attention_relpos_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* p, const float* u_bias, const float* v_bias,
+                        const int32_t* cu_seqlens, int B, int H, long long total_tokens, int Npad, int S_center,
+                        __nv_bfloat16* qu, __nv_bfloat16* qv, __nv_bfloat16* out, int num_sms, cudaStream_t stream);
+
 // optional final LayerNorm + pooling over packed sequences -> out [B, D] fp32;
 // optionally also scatters the (normalised) rows to a padded [B, S, D] fp32 tensor.
 int ln_pool(const float* x, const int32_t* cu_seqlens, int B, int D, const float* gamma, const float* beta,

@@ -71,8 +71,13 @@ def relative_position_table(max_len: int, dim: int, rows: int) -> Tensor:
 
 class B200SpeechEncoderModel(torch.nn.Module):
     def __init__(self, config: SonarSpeechEncoderConfig, state_dict: Dict[str, Tensor],
-                 device: Union[str, torch.device] = "cuda") -> None:
+                 device: Union[str, torch.device] = "cuda", *, attn_impl: str = "tcgen05") -> None:
+        """``attn_impl``: relative-position attention kernel -- "tcgen05" (default) or "mma_sync" (the round-1 kernel, kept as
+        a second implementation for tests and A/B timing)."""
         super().__init__()
+        if attn_impl not in ("tcgen05", "mma_sync"):
+            raise ValueError("attn_impl must be 'tcgen05' or 'mma_sync'")
+        self.attn_impl = attn_impl
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("B200SpeechEncoderModel needs a CUDA device (there is no CPU path)")
@@ -158,7 +163,8 @@ class B200SpeechEncoderModel(torch.nn.Module):
         cfg_c = _lib.SbSpeechConfig(model_dim=d, num_layers=config.num_encoder_layers, num_heads=config.num_encoder_attn_heads,
                                     ffn_inner_dim=config.ffn_inner_dim, conv_kernel=config.depthwise_conv_kernel_size,
                                     pooler_layers=config.num_decoder_layers,
-                                    pooler_ffn_inner_dim=config.decoder_ffn_inner_dim, ln_eps=1e-5)
+                                    pooler_ffn_inner_dim=config.decoder_ffn_inner_dim, ln_eps=1e-5,
+                                    attn_impl=1 if attn_impl == "mma_sync" else 0)
         handle = C.c_void_p()
         with torch.cuda.device(dev):
             _lib.check(self._lib.sb_speech_encoder_create(C.byref(cfg_c), C.byref(w_c), C.byref(handle)),

@@ -200,3 +200,39 @@ def test_tsv_pipelines_match_the_model_pipelines(speech_small, cuda_device, tmp_
     texts = [t for bucket_texts in SpeechToTextPipeline(enc, dec, tok).build_pipeline(ctx, max_seq_len=10) for t in bucket_texts]
     assert texts == SpeechToTextModelPipeline(enc, dec, tok, device=cuda_device).predict(waves, target_lang="fra_Latn",
                                                                                        batch_size=2, max_seq_len=10)
+
+
+def test_relpos_attention_tcgen05_agrees_with_mma_sync_and_is_batch_invariant(native_lib, cuda_device):
+    """The relative-position attention has two implementations: the tcgen05 kernel (attention_relpos_tc.cu: S and the band
+    product on the 5th-gen tensor cores, the Transformer-XL shift as a register barrel shifter, P in tensor memory) and the
+    round-1 mma.sync kernel.  Same model, both kernels, utterances whose position counts sit on and around the 128-row tile
+    edges; both must agree with each other and with the oracle, and the tcgen05 path must give an utterance the same bits
+    whatever batch it is in (the band window it reads depends on the utterance, not on the batch maximum)."""
+    from oracle.speech_encoder import OracleSpeechConfig, OracleSpeechEncoder, make_synthetic_speech_state_dict
+    from sonar_b200 import B200SpeechEncoderModel, PaddingMask, SequenceBatch, sonar_speech_encoder_config
+    from tests.helpers import parity_metrics
+
+    ocfg = OracleSpeechConfig(num_layers=2, pooler_layers=2)
+    sd = make_synthetic_speech_state_dict(ocfg, seed=11)
+    cfg = sonar_speech_encoder_config("english", num_encoder_layers=2, num_decoder_layers=2)
+    tc = B200SpeechEncoderModel(cfg, sd, cuda_device, attn_impl="tcgen05")
+    ms = B200SpeechEncoderModel(cfg, sd, cuda_device, attn_impl="mma_sync")
+    g = torch.Generator().manual_seed(12)
+    frames = [998, 258, 256, 2, 514, 770, 254, 600]  # positions 499, 129, 128, 1, 257, 385, 127, 300
+    tmax = 998
+    fb = torch.zeros((len(frames), tmax, 80))
+    for i, n in enumerate(frames):
+        fb[i, :n] = torch.randn((n, 80), generator=g)
+    batch = SequenceBatch(fb.to(cuda_device), PaddingMask(torch.tensor(frames), tmax, frames))
+    a = tc(batch).sentence_embeddings
+    b = ms(batch).sentence_embeddings
+    m = parity_metrics(a, b.cpu())
+    print("tcgen05 vs mma.sync rel-pos attention:", m)
+    assert m["one_minus_cos_max"] <= 1e-5 and m["rel_l2_max"] <= 5e-3, m
+    ref, _, _ = OracleSpeechEncoder(ocfg, sd)(fb, frames)
+    _speech_check(parity_metrics(a, ref), "speech tcgen05 attention vs oracle")
+    assert torch.equal(tc(batch).sentence_embeddings, a)  # deterministic
+    for i in (1, 4, 7):  # alone in a batch of one: a different batch maximum, the same bits
+        n = frames[i]
+        alone = tc(SequenceBatch(fb[i : i + 1, :n].contiguous().to(cuda_device), None)).sentence_embeddings
+        assert torch.equal(alone[0], a[i]), i
