@@ -227,9 +227,9 @@ attention_relpos_tc_kernel(const __grid_constant__ CUtensorMap tm_qu, const __gr
         const uint32_t sbase = smem_u32(smem + g * kGroupBytes);
         const uint32_t tS = tmem_base + g * 256, tB = tS + 128;
         if (ph == 0) {  // S1 = Qu K^T, B_lo = Qv P_lo^T
-          if (kt == 0 && !mbar_try_wait(&bar[Q_FULL], ni & 1)) continue;
-          if (!mbar_try_wait(&bar[KP_FULL], n & 1)) continue;
-          if (n > 0 && !mbar_try_wait(&bar[O_FREE], (n - 1) & 1)) continue;
+          if (kt == 0 && !mbar_test_wait(&bar[Q_FULL], ni & 1)) continue;
+          if (!mbar_test_wait(&bar[KP_FULL], n & 1)) continue;
+          if (n > 0 && !mbar_test_wait(&bar[O_FREE], (n - 1) & 1)) continue;
           tc_fence_after();
           const uint64_t qu = umma_desc_kmajor_sw128(sbase + kOffQu), qv = umma_desc_kmajor_sw128(sbase + kOffQv);
           const uint64_t kd = umma_desc_kmajor_sw128(sbase + kOffK), pl = umma_desc_kmajor_sw128(sbase + kOffPlo);
@@ -241,7 +241,7 @@ attention_relpos_tc_kernel(const __grid_constant__ CUtensorMap tm_qu, const __gr
           if (g) ph1 = 1; else ph0 = 1;
           progressed = true;
         } else if (ph == 1) {  // B_hi = Qv P_hi^T over the same TMEM columns, once pass A has consumed B_lo
-          if (!mbar_try_wait(&bar[A_DONE], n & 1)) continue;
+          if (!mbar_test_wait(&bar[A_DONE], n & 1)) continue;
           tc_fence_after();
           const uint64_t qv = umma_desc_kmajor_sw128(sbase + kOffQv), phd = umma_desc_kmajor_sw128(sbase + kOffPhi);
 #pragma unroll
@@ -252,8 +252,8 @@ attention_relpos_tc_kernel(const __grid_constant__ CUtensorMap tm_qu, const __gr
           if (g) ph1 = 2; else ph0 = 2;
           progressed = true;
         } else {  // O = P V  (P in TMEM columns B+64.., O into B+0..63)
-          if (!mbar_try_wait(&bar[P_READY], n & 1)) continue;
-          if (!mbar_try_wait(&bar[V_FULL], n & 1)) continue;
+          if (!mbar_test_wait(&bar[P_READY], n & 1)) continue;
+          if (!mbar_test_wait(&bar[V_FULL], n & 1)) continue;
           tc_fence_after();
           const int kv_valid = min(128, len - kt * 128);
           const int ksteps = (kv_valid + 15) >> 4;
@@ -330,13 +330,20 @@ attention_relpos_tc_kernel(const __grid_constant__ CUtensorMap tm_qu, const __gr
         tmem_ld_wait();
         const int lim = kv_valid - c * 32;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          float v = __uint_as_float(sc[k]) + __uint_as_float(in[k]);
-          if (final) {
-            if (k >= lim) v = -CUDART_INF_F;  // keys beyond the utterance: probability exactly 0
-            mx = fmaxf(mx, v);
+        for (int k = 0; k < 32; ++k) sc[k] = __float_as_uint(__uint_as_float(sc[k]) + __uint_as_float(in[k]));
+        if (final) {
+          if (lim < 32) {  // the chunk reaches past the utterance: those keys get probability exactly 0
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (k >= lim) sc[k] = __float_as_uint(-CUDART_INF_F);
           }
-          sc[k] = __float_as_uint(v);
+          float m0 = __uint_as_float(sc[0]), m1 = __uint_as_float(sc[1]);
+#pragma unroll
+          for (int k = 2; k < 32; k += 2) {
+            m0 = fmaxf(m0, __uint_as_float(sc[k]));
+            m1 = fmaxf(m1, __uint_as_float(sc[k + 1]));
+          }
+          mx = fmaxf(mx, fmaxf(m0, m1));
         }
         tmem_st_32x32(tS + c * 32, sc);
       };

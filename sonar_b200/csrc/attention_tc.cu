@@ -214,7 +214,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* c
         const int kv_valid = g1 ? min(128, s1.len - s1.kt * 128) : min(128, s0.len - s0.kt * 128);
         uint8_t* base = smem_qk + sq * 2 * kTile;
         // a P that is already waiting goes to the tensor core before this thread blocks on the next unit's loads
-        if (pend_g >= 0 && mbar_try_wait(&p_ready[pend_g], pend_n & 1)) issue_pv();
+        if (pend_g >= 0 && mbar_test_wait(&p_ready[pend_g], pend_n & 1)) issue_pv();
         // ---- S = Q K^T for this unit ----
         mbar_wait(&full_qk[sq], phq);
         if (ng > 0) {
