@@ -14,13 +14,14 @@
 //       own offset.  TMEM loads are warp-uniform in the column address, so the 32-column window a warp fetches covers its
 //       32 rows' needs (63 columns) and each thread then shifts its row by s = 31 - lane with a 5-stage barrel shifter of
 //       register selects (16, 8, 4, 2, 1) -- no shared-memory round trip, no bank conflicts.
-//     P = exp2((S1 + shift(B) - m) / 8 * log2 e)    one thread per query row, online softmax across key tiles
+//     P = exp2((S1 + shift(B) - m_ref) / 8 * log2 e) one thread per query row; m_ref is a lazily raised reference (see the
+//                                                   softmax section), so the scores are read once and exponentiated at once
 //     O[128 x 64]  = P . V                          P stays in tensor memory (tcgen05.st + A-from-TMEM MMA)
 // Tensor memory holds 256 columns per softmax group: S1 (128) | B half (128).  B is produced in two halves (columns
 // 0-127, then 128-255 into the same TMEM columns): a chunk of 32 keys takes its position term from the low half when
-// jl <= il and from the high half otherwise, so pass A folds the low half into the score chunks c <= warp, pass B the high
-// half into the chunks c >= warp; the combined scores are written back over S1 (tcgen05.st) and P / O later reuse the
-// B columns.  Two softmax warpgroups per CTA (one persistent CTA per SM) work on different items, so one group's
+// jl <= il and from the high half otherwise, so pass A completes the score chunks c < warp, pass B the chunks c >= warp (the
+// diagonal chunk keeps its 32 low-half columns in registers in between); the probabilities overwrite the chunk's own score
+// columns and O later reuses the B columns.  Two softmax warpgroups per CTA (one persistent CTA per SM) work on different items, so one group's
 // exponentials overlap the other's MMAs; each group has its own operand slots and its own TMA producer thread.
 //
 // Warps: 0 = producer of group 0, 3 = producer of group 1, 1 = MMA issuer (event driven over both groups), 2 = TMEM allocator,
@@ -106,19 +107,25 @@ struct RelStream {
   }
 };
 
-// out[k] = in[k + s], k = 0..31, s in [0, 31]: five select stages (16, 8, 4, 2, 1), in place
-__device__ __forceinline__ void barrel_shift(uint32_t (&in)[64], int s) {
-  const bool b16 = s & 16, b8 = s & 8, b4 = s & 4, b2 = s & 2, b1 = s & 1;
+// lo[k] = in[k + s], k = 0..31, s in [0, 31], where in = lo | hi (64 values): five select stages (16, 8, 4, 2, 1), in place.
+// (Two separate 32-register arrays with compile-time indices only: nothing here may end up in local memory.)
+template <int SH>
+__device__ __forceinline__ void barrel_stage(uint32_t (&lo)[32], uint32_t (&hi)[32], bool on) {
+  // after this stage positions [0, 64 - sum of shifts so far) are meaningful; ascending k reads only not-yet-written slots
 #pragma unroll
-  for (int k = 0; k < 48; ++k) in[k] = b16 ? in[k + 16] : in[k];
+  for (int k = 0; k < 32; ++k) {
+    const uint32_t src = (k + SH < 32) ? lo[(k + SH) & 31] : hi[(k + SH - 32) & 31];
+    lo[k] = on ? src : lo[k];
+  }
 #pragma unroll
-  for (int k = 0; k < 40; ++k) in[k] = b8 ? in[k + 8] : in[k];
-#pragma unroll
-  for (int k = 0; k < 36; ++k) in[k] = b4 ? in[k + 4] : in[k];
-#pragma unroll
-  for (int k = 0; k < 34; ++k) in[k] = b2 ? in[k + 2] : in[k];
-#pragma unroll
-  for (int k = 0; k < 32; ++k) in[k] = b1 ? in[k + 1] : in[k];
+  for (int k = 0; k + SH < 32; ++k) hi[k] = on ? hi[k + SH] : hi[k];
+}
+__device__ __forceinline__ void barrel_shift(uint32_t (&lo)[32], uint32_t (&hi)[32], int s) {
+  barrel_stage<16>(lo, hi, s & 16);
+  barrel_stage<8>(lo, hi, s & 8);
+  barrel_stage<4>(lo, hi, s & 4);
+  barrel_stage<2>(lo, hi, s & 2);
+  barrel_stage<1>(lo, hi, s & 1);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -171,7 +178,6 @@ attention_relpos_tc_kernel(const __grid_constant__ CUtensorMap tm_qu, const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-
   if ((warp == 0 || warp == 3) && lane == 0) {
     // ============================ TMA producer of group g ============================
     const int g = (warp == 0) ? 0 : 1;
@@ -251,14 +257,14 @@ attention_relpos_tc_kernel(const __grid_constant__ CUtensorMap tm_qu, const __gr
           if (kt == nt - 1) umma_commit<1>(&bar[Q_EMPTY]);   // last key tile of the item: Qu, Qv are dead too
           if (g) ph1 = 2; else ph0 = 2;
           progressed = true;
-        } else {  // O = P V  (P in TMEM columns B+64.., O into B+0..63)
+        } else {  // O = P V  (P over the score columns, O into B+0..63)
           if (!mbar_test_wait(&bar[P_READY], n & 1)) continue;
           if (!mbar_test_wait(&bar[V_FULL], n & 1)) continue;
           tc_fence_after();
           const int kv_valid = min(128, len - kt * 128);
           const int ksteps = (kv_valid + 15) >> 4;
-          for (int k = 0; k < ksteps; ++k)
-            umma_bf16_ts(tB, tB + 64 + 8 * k, desc_mnmajor_sw128(sbase + kOffV + k * 2048), idesc_o, k != 0);
+          for (int k = 0; k < ksteps; ++k)  // 16 keys per k-step: P of key chunk c lives at S columns 32c .. 32c+15
+            umma_bf16_ts(tB, tS + 32 * (k >> 1) + 8 * (k & 1), desc_mnmajor_sw128(sbase + kOffV + k * 2048), idesc_o, k != 0);
           umma_commit<1>(&bar[O_FULL]);
           umma_commit<1>(&bar[V_EMPTY]);
           if (g) {
@@ -295,105 +301,132 @@ attention_relpos_tc_kernel(const __grid_constant__ CUtensorMap tm_qu, const __gr
     RelStream u;
     u.init(cu, tile_cu, B, H, blockIdx.x + g * gridDim.x, 2 * gridDim.x);
     uint32_t n = 0;
-    float m_run = -CUDART_INF_F, l_run = 0.f;
+    // Softmax state of the query row across the key tiles of an item.  The exponentials are taken against a REFERENCE m_ref
+    // that is only raised when a score exceeds it by more than kTau (then everything accumulated so far is rescaled): the
+    // probabilities stay below 2^8 relative to the reference, well inside bf16 / fp32 range, and the common case needs no
+    // second pass over the scores and no per-tile rescaling of the accumulator.
+    constexpr float kTau = 8.0f / (0.125f * 1.4426950408889634f);
+    float m_ref = -CUDART_INF_F, l_run = 0.f;
     float o_acc[64];
     while (u.valid) {
       const int kv_valid = min(128, u.len - u.kt * 128);
       const int nch = (kv_valid + 31) >> 5;  // 32-key chunks holding valid keys
       if (u.kt == 0) {
-        m_run = -CUDART_INF_F;
+        m_ref = -CUDART_INF_F;
         l_run = 0.f;
 #pragma unroll
         for (int j = 0; j < 64; ++j) o_acc[j] = 0.f;
       }
-      float mx = -CUDART_INF_F;
-      // fold one half of B into score chunk c: window columns [colB, colB + 64) of the resident half, zero where the
-      // other half would be (diagonal chunk); `final` = the chunk's score is complete after this call -> mask + maximum
-      auto fold = [&](int c, int colB, bool lo_missing, bool hi_missing, bool final) {
-        uint32_t in[64];
-        if (lo_missing) {
+      float sum = 0.f;       // this key tile's share of the row sum (relative to m_ref)
+      uint32_t done = 0;     // chunks of this tile whose P is already in tensor memory (warp-uniform)
+
+      // sc = the complete scores of chunk c -> probabilities (bf16 pairs) over the chunk's own S columns
+      auto finalize = [&](int c, uint32_t (&sc)[32]) {
+        const int lim = kv_valid - c * 32;
+        if (lim < 32) {  // the chunk reaches past the utterance: those keys get probability exactly 0
 #pragma unroll
-          for (int k = 0; k < 32; ++k) in[k] = 0u;
-        } else {
-          tmem_ld_32x32(tB + colB, reinterpret_cast<uint32_t(&)[32]>(in[0]));
+          for (int k = 0; k < 32; ++k)
+            if (k >= lim) sc[k] = __float_as_uint(-CUDART_INF_F);
         }
-        if (hi_missing) {
+        float m0 = __uint_as_float(sc[0]), m1 = __uint_as_float(sc[1]);
 #pragma unroll
-          for (int k = 0; k < 32; ++k) in[32 + k] = 0u;
-        } else {
-          tmem_ld_32x32(tB + colB + 32, reinterpret_cast<uint32_t(&)[32]>(in[32]));
+        for (int k = 2; k < 32; k += 2) {
+          m0 = fmaxf(m0, __uint_as_float(sc[k]));
+          m1 = fmaxf(m1, __uint_as_float(sc[k + 1]));
         }
-        tmem_ld_wait();
-        barrel_shift(in, shift);  // in[0..31] = this row's position terms for the chunk's 32 keys
-        uint32_t sc[32];          // (loaded only now: the 64-register window is dead, the accumulator o_acc stays live)
+        const float cm = fmaxf(m0, m1);
+        const bool bump = cm > m_ref + kTau;  // always on the item's first chunk (m_ref = -inf)
+        if (__any_sync(0xffffffffu, bump)) {   // warp-uniform branch; lanes that keep their reference scale by exactly 1
+          const float m_new = bump ? cm : m_ref;
+          const float f = ex2f((m_ref - m_new) * sl2);
+          l_run *= f;
+          sum *= f;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) o_acc[j] *= f;
+          if (done) tmem_st_wait();  // (their tcgen05.st must have landed before they are read back)
+          for (int cc = 0; cc < 4; ++cc) {  // probabilities of this tile already written against the old reference
+            if (!(done & (1u << cc))) continue;
+            uint32_t pk[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(pk[0]), "=r"(pk[1]), "=r"(pk[2]), "=r"(pk[3]), "=r"(pk[4]), "=r"(pk[5]), "=r"(pk[6]), "=r"(pk[7]),
+                  "=r"(pk[8]), "=r"(pk[9]), "=r"(pk[10]), "=r"(pk[11]), "=r"(pk[12]), "=r"(pk[13]), "=r"(pk[14]), "=r"(pk[15])
+                : "r"(tS + cc * 32)
+                : "memory");
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&pk[j]);
+              pk[j] = pack_bf16x2(__low2float(h2) * f, __high2float(h2) * f);
+            }
+            tmem_st_32x16(tS + cc * 32, pk);
+          }
+          m_ref = m_new;
+        }
+        const float mxs = m_ref * sl2;
+        uint32_t pk[16];
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          const float p0 = ex2f(fmaf(__uint_as_float(sc[k]), sl2, -mxs));
+          const float p1 = ex2f(fmaf(__uint_as_float(sc[k + 1]), sl2, -mxs));
+          s0 += p0;
+          s1 += p1;
+          pk[k >> 1] = pack_bf16x2(p0, p1);
+        }
+        sum += s0 + s1;
+        tmem_st_32x16(tS + c * 32, pk);  // over the first 16 of the chunk's 32 score columns (its scores are in registers)
+        done |= 1u << c;
+      };
+      // chunk c gets its position terms from window columns [colB, colB + 64) of the resident half of B
+      auto fold = [&](int c, int colB) {
+        uint32_t lo[32], hi[32], sc[32];
+        tmem_ld_32x32(tB + colB, lo);
+        tmem_ld_32x32(tB + colB + 32, hi);
         tmem_ld_32x32(tS + c * 32, sc);
         tmem_ld_wait();
-        const int lim = kv_valid - c * 32;
+        barrel_shift(lo, hi, shift);
 #pragma unroll
-        for (int k = 0; k < 32; ++k) sc[k] = __float_as_uint(__uint_as_float(sc[k]) + __uint_as_float(in[k]));
-        if (final) {
-          if (lim < 32) {  // the chunk reaches past the utterance: those keys get probability exactly 0
-#pragma unroll
-            for (int k = 0; k < 32; ++k)
-              if (k >= lim) sc[k] = __float_as_uint(-CUDART_INF_F);
-          }
-          float m0 = __uint_as_float(sc[0]), m1 = __uint_as_float(sc[1]);
-#pragma unroll
-          for (int k = 2; k < 32; k += 2) {
-            m0 = fmaxf(m0, __uint_as_float(sc[k]));
-            m1 = fmaxf(m1, __uint_as_float(sc[k + 1]));
-          }
-          mx = fmaxf(mx, fmaxf(m0, m1));
-        }
-        tmem_st_32x32(tS + c * 32, sc);
+        for (int k = 0; k < 32; ++k) sc[k] = __float_as_uint(__uint_as_float(sc[k]) + __uint_as_float(lo[k]));
+        finalize(c, sc);
       };
 
       mbar_wait(&bar[AB_FULL], n & 1);
       tc_fence_after();
-      // ---- pass A: low half of B (window columns 0..127) -> chunks c <= wq ----
-      for (int c = 0; c < nch && c <= wq; ++c) {
-        if (c < wq) fold(c, 96 - 32 * (wq - c), false, false, true);
-        else fold(c, 96, false, true, false);  // diagonal chunk: columns 96..127 now, 128..158 in pass B
+      // ---- pass A: low half of B (window columns 0..127): chunks c < wq complete; the diagonal chunk c == wq needs
+      //      columns 96..127 of this half (kept in registers) and 128..158 of the high half ----
+      for (int c = 0; c < nch && c < wq; ++c) fold(c, 96 - 32 * (wq - c));
+      uint32_t dg[32];
+      const bool has_diag = wq < nch;
+      if (has_diag) {
+        tmem_ld_32x32(tB + 96, dg);
+        tmem_ld_wait();
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[A_DONE]);
-      // ---- pass B: high half of B (window columns 128..255, now in the same TMEM columns) -> chunks c >= wq ----
+      // ---- pass B: high half of B, now in the same TMEM columns: the diagonal chunk and the chunks c > wq ----
       mbar_wait(&bar[BHI_FULL], n & 1);
       tc_fence_after();
-      for (int c = wq; c < nch; ++c) {
-        if (c == wq) fold(c, -32, true, false, true);  // columns 128..159 of the window = 0..31 of the high half
-        else fold(c, 32 * (c - wq) - 32, false, false, true);
-      }
-      tmem_st_wait();
-      // ---- online softmax over this key tile: p = exp2((s - m) / 8 * log2 e) -> bf16 pairs in TMEM (B columns 64..127) ----
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = ex2f((m_run - m_new) * sl2);  // 0 on the first key tile (m_run = -inf)
-      const float mxs = m_new * sl2;
-      float sum0 = 0.f, sum1 = 0.f;
-      for (int c = 0; c < nch; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + c * 32, v);
+      if (has_diag) {
+        uint32_t hi[32], sc[32];
+        tmem_ld_32x32(tB, hi);
+        tmem_ld_32x32(tS + wq * 32, sc);
         tmem_ld_wait();
-        uint32_t pk[16];
+        barrel_shift(dg, hi, shift);
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float p0 = ex2f(fmaf(__uint_as_float(v[j]), sl2, -mxs));
-          const float p1 = ex2f(fmaf(__uint_as_float(v[j + 1]), sl2, -mxs));
-          sum0 += p0;
-          sum1 += p1;
-          pk[j >> 1] = pack_bf16x2(p0, p1);
-        }
-        tmem_st_32x16(tB + 64 + c * 16, pk);
+        for (int k = 0; k < 32; ++k) sc[k] = __float_as_uint(__uint_as_float(sc[k]) + __uint_as_float(dg[k]));
+        finalize(wq, sc);
       }
-      l_run = l_run * alpha + (sum0 + sum1);
-      m_run = m_new;
+      for (int c = wq + 1; c < nch; ++c) fold(c, 32 * (c - wq) - 32);
+      l_run += sum;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[P_READY]);
-      // ---- O tile of this key tile -> register accumulator ----
+      // ---- O tile of this key tile (relative to the same reference) -> register accumulator ----
       mbar_wait(&bar[O_FULL], n & 1);
       tc_fence_after();
       uint32_t o[2][32];
@@ -404,7 +437,7 @@ attention_relpos_tc_kernel(const __grid_constant__ CUtensorMap tm_qu, const __gr
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[O_FREE]);
 #pragma unroll
-      for (int j = 0; j < 64; ++j) o_acc[j] = fmaf(o_acc[j], alpha, __uint_as_float(o[j >> 5][j & 31]));
+      for (int j = 0; j < 64; ++j) o_acc[j] += __uint_as_float(o[j >> 5][j & 31]);
       if (u.kt == u.nt - 1 && u.q0 + row < u.len) {
         const float inv = 1.0f / l_run;
         uint4* dst = reinterpret_cast<uint4*>(out + (long long)(u.tok0 + u.q0 + row) * D + u.h * 64);
