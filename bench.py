@@ -317,6 +317,19 @@ def bench_speech(dev, peaks):
         return model(SequenceBatch(fb, PaddingMask(torch.tensor(fr), fb.shape[1], fr))).sentence_embeddings
 
     ms = _timed_ms(run, iters=3, warm=2)
+    # same-run A/B of the other relative-position attention kernel (tcgen05: attention_relpos_tc.cu)
+    other = "tcgen05" if model.attn_impl == "mma_sync" else "mma_sync"
+    model_b = B200SpeechEncoderModel(sonar_speech_encoder_config("english"), sd, dev, attn_impl=other)
+
+    def run_b():
+        fb, fr = conv(wd)
+        return model_b(SequenceBatch(fb, PaddingMask(torch.tensor(fr), fb.shape[1], fr))).sentence_embeddings
+
+    ms_b = _timed_ms(run_b, iters=3, warm=2)
+    ab_rel = float(((run_b() - run()).norm(dim=1) / run().norm(dim=1)).max())
+    attn_ab = {"default": model.attn_impl, "utterances_per_s": {model.attn_impl: n / ms * 1e3, other: n / ms_b * 1e3},
+               "rel_l2_between_kernels_max": ab_rel}
+    del model_b
     # e2e: pinned host waveforms in, host embeddings out
     wp = [w.pin_memory() for w in waves]
     out_host = torch.empty((n, 1024), dtype=torch.float32).pin_memory()
@@ -345,6 +358,7 @@ def bench_speech(dev, peaks):
             "metric": "utterances/sec->1024-d", "value": val, "unit": "utterances/s", "ms_per_step": ms,
             "e2e": {"value": n / ms_e2e * 1e3, "unit": "utterances/s", "h2d_bytes_per_step": n * 160000 * 4,
                     "d2h_bytes_per_step": n * 1024 * 4},
+            "ab_relpos_attention": attn_ab,
             "roofline": {"bound": "tensor", "achieved": val * flop_per_utt / 1e12, "peak": peak, "unit": "TFLOP/s",
                          "frac": val * flop_per_utt / 1e12 / peak,
                          "algorithmic_flop_per_utterance": flop_per_utt},

@@ -53,7 +53,7 @@ def speech_small(native_lib, cuda_device):
     ocfg = OracleSpeechConfig(num_layers=2, pooler_layers=2)
     sd = make_synthetic_speech_state_dict(ocfg, seed=3)
     cfg = sonar_speech_encoder_config("english", num_encoder_layers=2, num_decoder_layers=2)
-    return OracleSpeechEncoder(ocfg, sd), B200SpeechEncoderModel(cfg, sd, cuda_device)
+    return OracleSpeechEncoder(ocfg, sd), B200SpeechEncoderModel(cfg, sd, cuda_device)  # default attention kernel (mma.sync)
 
 
 def _speech_check(m, what):
