@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(GemmCfg<kCtaGroup, kEpiGroups>::THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                          const __grid_constant__ CUtensorMap tm_c, const float* __restrict__ bias,
                          const OutT* residual, long long ldr, int M, int N, int K, float* __restrict__ cand_val,
-                         int* __restrict__ cand_idx, float* __restrict__ lse_part, int n_chunks, const LnFold lf) {
+                         int* __restrict__ cand_idx, float* __restrict__ lse_part, int n_chunks, const LnFold lf,
+                         const ColFilter cf) {
   constexpr bool kSweep = (kEpi == EPI_TOPK);
   using Cfg = GemmCfg<kCtaGroup, kEpiGroups>;
   extern __shared__ uint8_t smem_raw[];
@@ -367,6 +368,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           const float thr = tv[KC - 1];  // (stale between drains: a few extra pushes, rejected when drained)
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
+            if (cf.thr != nullptr && grow < M) {  // column filter: elements above their COLUMN's threshold (rare)
+              const float4 t0 = __ldg(reinterpret_cast<const float4*>(cf.thr + gcol + g8 * 8));
+              const float4 t1 = __ldg(reinterpret_cast<const float4*>(cf.thr + gcol + g8 * 8 + 4));
+              const float th[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float x = __uint_as_float(v[g8 * 8 + j]);
+                if (x > th[j]) {
+                  const int col = gcol + g8 * 8 + j;
+                  const int slot = atomicAdd(cf.cnt + col, 1);
+                  if (slot < cf.cap) cf.buf[(long long)col * cf.cap + slot] = make_uint2(__float_as_uint(x), uint32_t(grow));
+                }
+              }
+            }
             if (gm[g8] > thr) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -606,7 +621,7 @@ template <int kCtaGroup, int kEpi, typename OutT, int kEpiGroups = 2>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const float* bias,
                        const void* residual, long long ldr, int M, int N, int K, int num_sms, cudaStream_t stream,
                        float* cand_val = nullptr, int* cand_idx = nullptr, float* lse_part = nullptr,
-                       int n_chunks = 1, const LnFold& lf = LnFold()) {
+                       int n_chunks = 1, const LnFold& lf = LnFold(), const ColFilter& cf = ColFilter()) {
   using Cfg = GemmCfg<kCtaGroup, kEpiGroups>;
   auto kern = gemm_bf16_tcgen05_kernel<kCtaGroup, kEpi, OutT, kEpiGroups>;
   static bool attr_set[64] = {};
@@ -633,7 +648,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, bias, reinterpret_cast<const OutT*>(residual), ldr, M, N, K,
-                                   cand_val, cand_idx, lse_part, n_chunks, lf));
+                                   cand_val, cand_idx, lse_part, n_chunks, lf, cf));
   return 0;
 }
 
@@ -656,8 +671,12 @@ int gemm_topk_chunks(int M, int N, int cta_group, int num_sms) {
 // sorted by value descending, and (optional) lse_part [M, lists, 2] = (max, sum exp(v - max)) over the list's columns.
 int gemm_bf16_topk(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
                    float* cand_val, int* cand_idx, float* lse_part, int n_chunks, int cta_group, int num_sms,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, const ColFilter& cf) {
   if (M <= 0 || N <= 0) return 0;
+  if (cf.thr != nullptr && (!cf.cnt || !cf.buf || cf.cap <= 0)) {
+    set_last_error("gemm_bf16_topk: column filter needs cnt, buf and a positive capacity");
+    return -1;
+  }
   if (K % 64 != 0 || K <= 0) {
     set_last_error("gemm_bf16_topk: K must be a positive multiple of 64 (got %d)", K);
     return -1;
@@ -676,9 +695,9 @@ int gemm_bf16_topk(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W
   const int sms = num_sms > 0 ? num_sms : 148;
   if (cg == 2)
     return launch_inst<2, EPI_TOPK, float>(ta, tb, ta /*unused*/, nullptr, nullptr, 0, M, N, K, sms, stream, cand_val,
-                                           cand_idx, lse_part, n_chunks);
+                                           cand_idx, lse_part, n_chunks, LnFold(), cf);
   return launch_inst<1, EPI_TOPK, float>(ta, tb, ta /*unused*/, nullptr, nullptr, 0, M, N, K, sms, stream, cand_val,
-                                         cand_idx, lse_part, n_chunks);
+                                         cand_idx, lse_part, n_chunks, LnFold(), cf);
 }
 
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {

@@ -83,13 +83,24 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
 bool gemm_skinny_eligible(const GemmArgs& g);
 int gemm_skinny(const GemmArgs& g, cudaStream_t stream);
 
+// Column filter of the top-k sweep (xsim: both k-NN directions from ONE pass over x . y^T): next to the per-row lists, every
+// element above its column's threshold is appended to that column's candidate buffer -- entry = (bf16 product as fp32 bits,
+// row index); `cnt[col]` counts every hit (also those beyond `cap`, which are dropped: the caller checks for overflow).
+// `thr` must be readable up to the next multiple of 256 columns (pad with +inf).
+struct ColFilter {
+  const float* thr = nullptr;  // [N padded to 256]; nullptr = no column filter
+  int* cnt = nullptr;          // [N]
+  uint2* buf = nullptr;        // [N, cap]
+  int cap = 0;
+};
+
 int gemm_topk_chunks(int M, int N, int cta_group, int num_sms);
 // candidate lists per row that gemm_bf16_topk writes for a given n_chunks (two epilogue warpgroups per n-chunk)
 constexpr int kTopkListsPerChunk = 2;
 inline int gemm_topk_lists(int n_chunks) { return kTopkListsPerChunk * n_chunks; }
 int gemm_bf16_topk(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
                    float* cand_val, int* cand_idx, float* lse_part, int n_chunks, int cta_group, int num_sms,
-                   cudaStream_t stream);
+                   cudaStream_t stream, const ColFilter& cf = ColFilter());
 
 int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld,
                  int box_rows, int box_cols);

@@ -16,6 +16,7 @@
 #include "sonar_b200_internal.h"
 
 #include <math_constants.h>
+#include <cmath>
 
 namespace sb {
 
@@ -167,6 +168,152 @@ static XsimWs carve_xsim(int n, int m, int d, void* base) {
   return w;
 }
 
+
+// ---- one-pass bidirectional k-NN: the reverse direction (for every y row its best x rows) comes out of the SAME x . y^T GEMM
+// through the sweep epilogue's column filter (ColFilter, sonar_b200_internal.h) ----
+constexpr int kColCap = 256;          // candidate slots per y row (expected hits ~ k * kSampleStride * 2.4 ~ 80)
+constexpr int kSampleStride = 8;      // the thresholds come from every 8th x row: a 1/8-size GEMM instead of a second full one
+constexpr float kBf16DotMargin = 0.008f;  // |bf16 dot - exact dot| <= 2 * 2^-9 * sum |x_k y_k| <= 2^-8 for unit vectors
+
+// one warp per y row: threshold = (k-th best bf16 score among the sampled x rows) - margin.  Every x row whose exact cosine
+// is among the true top-k has a bf16 score above it (the k-th best over a SUBSET cannot exceed the k-th best over all rows).
+__global__ void __launch_bounds__(256)
+col_threshold_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int lists, int m, int k,
+                     float* __restrict__ thr) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= m) return;
+  const int total = lists * kTopkCandidates;  // <= 32
+  float v = -CUDART_INF_F;
+  if (lane < total && cand_idx[(long long)row * total + lane] >= 0) v = cand_val[(long long)row * total + lane];
+  int rank = 0;  // number of strictly better candidates (ties: lower lane first)
+  for (int c = 0; c < 32; ++c) {
+    const float o = __shfl_sync(0xffffffffu, v, c);
+    if (o > v || (o == v && c < lane)) ++rank;
+  }
+  if (rank == k - 1) thr[row] = (v > -CUDART_INF_F) ? v - kBf16DotMargin : -CUDART_INF_F;
+}
+
+__global__ void fill_f32_kernel(float* p, long long n, float v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// one warp per y row j: its candidate x rows (bf16 score above the threshold) -> the 16 best by bf16 score -> exact fp64
+// cosine from the raw fp32 embeddings -> the best k by (score desc, index asc)
+__global__ void __launch_bounds__(256)
+col_rerank_kernel(const float* __restrict__ x, const float* __restrict__ y, const double* __restrict__ nx,
+                  const double* __restrict__ ny, const int* __restrict__ col_cnt, const uint2* __restrict__ col_buf, int n,
+                  int m, int d, int k, double* __restrict__ out_val, int* __restrict__ out_idx, int* __restrict__ overflow) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= m) return;
+  int cnt = col_cnt[j];
+  if (cnt > kColCap) {
+    if (lane == 0) atomicExch(overflow, 1);
+    cnt = kColCap;
+  }
+  constexpr int PER = kColCap / 32;
+  float cv[PER];
+  int ci[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int p = q * 32 + lane;
+    cv[q] = -CUDART_INF_F;
+    ci[q] = 0x7fffffff;
+    if (p < cnt) {
+      const uint2 e = col_buf[(long long)j * kColCap + p];
+      cv[q] = __uint_as_float(e.x);
+      ci[q] = int(e.y);
+    }
+  }
+  // 16 rounds of warp arg-max by (bf16 score desc, row asc): lane r keeps the r-th best candidate
+  int sel = -1;
+  for (int r = 0; r < kTopkCandidates; ++r) {
+    float bv = -CUDART_INF_F;
+    int bi = 0x7fffffff, bq = -1;
+#pragma unroll
+    for (int q = 0; q < PER; ++q)
+      if (ci[q] != 0x7fffffff && (cv[q] > bv || (cv[q] == bv && ci[q] < bi))) { bv = cv[q]; bi = ci[q]; bq = q; }
+    float wv = bv;
+    int wi = bi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+      if (ov > wv || (ov == wv && oi < wi)) { wv = ov; wi = oi; }
+    }
+    if (wi == 0x7fffffff) break;  // fewer than 16 candidates (warp-uniform)
+    if (bq >= 0 && bi == wi) {    // row indices are unique within a column: exactly one lane owns the winner
+#pragma unroll
+      for (int q = 0; q < PER; ++q)
+        if (q == bq) ci[q] = 0x7fffffff;
+    }
+    if (lane == r) sel = wi;
+  }
+  const float4* yr = reinterpret_cast<const float4*>(y + (long long)j * d);
+  double my_score = -CUDART_INF;
+  int my_idx = 0x7fffffff;
+  for (int c = 0; c < kTopkCandidates; ++c) {
+    const int i = __shfl_sync(0xffffffffu, sel, c);
+    if (i < 0 || i >= n) continue;  // warp-uniform
+    const float4* xr = reinterpret_cast<const float4*>(x + (long long)i * d);
+    double dot = 0.0;
+    for (int q = lane; q < d / 4; q += 32) {
+      const float4 a = xr[q], b = yr[q];
+      dot += (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (lane == c) {
+      my_score = dot / fmax(nx[i] * ny[j], 1e-300);
+      my_idx = i;
+    }
+  }
+  int rank = 0;
+  for (int c = 0; c < 32; ++c) {
+    const double sv = __shfl_sync(0xffffffffu, my_score, c);
+    const int iv = __shfl_sync(0xffffffffu, my_idx, c);
+    if (sv > my_score || (sv == my_score && iv < my_idx)) ++rank;
+  }
+  const bool valid = my_idx != 0x7fffffff;
+  if (valid && rank < k) {
+    out_val[(long long)j * k + rank] = my_score;
+    out_idx[(long long)j * k + rank] = my_idx;
+  }
+  const int nvalid = __popc(__ballot_sync(0xffffffffu, valid));
+  if (lane >= nvalid && lane < k) {
+    out_val[(long long)j * k + lane] = -CUDART_INF;
+    out_idx[(long long)j * k + lane] = -1;
+  }
+}
+
+struct XsimBidirWs {
+  XsimWs base;
+  float* s_val;   // [m, 32] sample-pass candidates of the y rows
+  int* s_idx;
+  float* thr;     // [m padded to 256]
+  int* cnt;       // [m]
+  int* overflow;  // [1]
+  uint2* buf;     // [m, kColCap]
+  size_t bytes;
+};
+
+static XsimBidirWs carve_xsim_bidir(int n, int m, int d, void* base) {
+  XsimBidirWs w;
+  w.base = carve_xsim(n, m, d, base);
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  size_t off = w.base.bytes;
+  const size_t mp = ((size_t)m + 255) / 256 * 256;
+  w.s_val = reinterpret_cast<float*>(p + off); off = align_up_sz(off + (size_t)m * kXsimCands * 4, 1024);
+  w.s_idx = reinterpret_cast<int*>(p + off); off = align_up_sz(off + (size_t)m * kXsimCands * 4, 1024);
+  w.thr = reinterpret_cast<float*>(p + off); off = align_up_sz(off + mp * 4, 1024);
+  w.cnt = reinterpret_cast<int*>(p + off); off = align_up_sz(off + (size_t)m * 4, 1024);
+  w.overflow = reinterpret_cast<int*>(p + off); off = align_up_sz(off + 256, 1024);
+  w.buf = reinterpret_cast<uint2*>(p + off); off = align_up_sz(off + (size_t)m * kColCap * 8, 1024);
+  w.bytes = off;
+  return w;
+}
 }  // namespace sb
 
 using namespace sb;
@@ -203,6 +350,62 @@ int sb_xsim_knn(const float* x, const float* y, int32_t n, int32_t m, int32_t d,
   rerank_kernel<kXsimCands, kTopkCandidates><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(x, y, w.nx, w.ny, w.cand_val, w.cand_idx, n, m, d, k,
                                                                              out_val, out_idx);
   SB_CUDA_CHECK(cudaGetLastError());
+  return SB_OK;
+}
+
+
+int sb_xsim_bidir_workspace_bytes(int32_t n, int32_t m, int32_t d, size_t* bytes) {
+  if (n <= 0 || m <= 0 || d <= 0 || !bytes) { set_last_error("sb_xsim_bidir_workspace_bytes: bad argument"); return SB_ERR_INVALID; }
+  *bytes = carve_xsim_bidir(n, m, d, nullptr).bytes + 1024;
+  return SB_OK;
+}
+
+int sb_xsim_knn_bidir(const float* x, const float* y, int32_t n, int32_t m, int32_t d, int32_t k, double* val_xy,
+                      int32_t* idx_xy, double* val_yx, int32_t* idx_yx, int32_t* overflow_flag, void* workspace,
+                      size_t workspace_bytes, void* stream_v) {
+  if (!x || !y || !val_xy || !idx_xy || !val_yx || !idx_yx || !overflow_flag || !workspace) {
+    set_last_error("sb_xsim_knn_bidir: null pointer");
+    return SB_ERR_INVALID;
+  }
+  if (n <= 0 || m <= 0) { set_last_error("sb_xsim_knn_bidir: empty input"); return SB_ERR_INVALID; }
+  if (d <= 0 || d % 64 != 0) { set_last_error("sb_xsim_knn_bidir: embedding dim must be a multiple of 64 (got %d)", d); return SB_ERR_INVALID; }
+  if (k <= 0 || k > kTopkCandidates) { set_last_error("sb_xsim_knn_bidir: k must be in [1, %d]", kTopkCandidates); return SB_ERR_INVALID; }
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023);
+  XsimBidirWs w = carve_xsim_bidir(n, m, d, reinterpret_cast<void*>(base));
+  if (base - reinterpret_cast<uintptr_t>(workspace) + w.bytes > workspace_bytes) {
+    set_last_error("sb_xsim_knn_bidir: workspace too small");
+    return SB_ERR_INVALID;
+  }
+  int dev = 0, sms = 0;
+  SB_CUDA_CHECK(cudaGetDevice(&dev));
+  SB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  l2_normalize_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(x, w.base.xn, w.base.nx, n, d);
+  l2_normalize_kernel<<<(unsigned)((m + 7) / 8), 256, 0, stream>>>(y, w.base.yn, w.base.ny, m, d);
+  SB_CUDA_CHECK(cudaGetLastError());
+  // (1) thresholds of the y rows from a strided sample of the x rows: y^ . xs^T with the usual running top-16 per row
+  const int stride = n >= 512 * kSampleStride ? kSampleStride : (n >= 1024 ? n / 512 : 1);
+  const int ns = (n + stride - 1) / stride;
+  int rc = gemm_bf16_topk(w.base.yn, d, w.base.xn, (long long)stride * d, m, ns, d, w.s_val, w.s_idx, nullptr, 1, 2, sms,
+                          stream);
+  if (rc) return rc;
+  const long long mp = ((long long)m + 255) / 256 * 256;
+  fill_f32_kernel<<<(unsigned)((mp + 255) / 256), 256, 0, stream>>>(w.thr, mp, INFINITY);  // padding columns: never hit
+  col_threshold_kernel<<<(unsigned)((m + 7) / 8), 256, 0, stream>>>(w.s_val, w.s_idx, gemm_topk_lists(1), m, k, w.thr);
+  SB_CUDA_CHECK(cudaGetLastError());
+  SB_CUDA_CHECK(cudaMemsetAsync(w.cnt, 0, sizeof(int) * (size_t)m, stream));
+  SB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, sizeof(int), stream));
+  // (2) ONE pass over x^ . y^T: per-row top-16 lists (forward direction) + per-column candidates above the thresholds
+  ColFilter cf;
+  cf.thr = w.thr; cf.cnt = w.cnt; cf.buf = w.buf; cf.cap = kColCap;
+  rc = gemm_bf16_topk(w.base.xn, d, w.base.yn, d, n, m, d, w.base.cand_val, w.base.cand_idx, nullptr, 1, 2, sms, stream, cf);
+  if (rc) return rc;
+  rerank_kernel<kXsimCands, kTopkCandidates><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(
+      x, y, w.base.nx, w.base.ny, w.base.cand_val, w.base.cand_idx, n, m, d, k, val_xy, idx_xy);
+  col_rerank_kernel<<<(unsigned)((m + 7) / 8), 256, 0, stream>>>(x, y, w.base.nx, w.base.ny, w.cnt, w.buf, n, m, d, k, val_yx,
+                                                                 idx_yx, w.overflow);
+  SB_CUDA_CHECK(cudaGetLastError());
+  SB_CUDA_CHECK(cudaMemcpyAsync(overflow_flag, w.overflow, sizeof(int), cudaMemcpyDeviceToDevice, stream));
   return SB_OK;
 }
 

@@ -63,6 +63,11 @@ def _worker(rank, world, port, results):
             v, i = ox.knn(a.numpy(), b.numpy(), k)
             return torch.from_numpy(v), torch.from_numpy(i.astype(np.int32))
 
+        def knn_bidir_cpu(a, b, k):
+            v1, i1 = knn_cpu(a, b, k)
+            v2, i2 = knn_cpu(b, a, k)
+            return v1, i1, v2, i2
+
         def margin_cpu(val_xy, idx_xy, val_yx, m, margin):
             v, i = val_xy.numpy(), idx_xy.numpy()
             if margin == "absolute":
@@ -74,7 +79,7 @@ def _worker(rank, world, port, results):
         ns = 64 // world
         sl = slice(rank * ns, (rank + 1) * ns)
         for margin in ("ratio", "distance", "absolute"):
-            err, n_tot, pred = _xsim_distributed_impl(x[sl], y[sl], margin, 4, None, knn_cpu, margin_cpu)
+            err, n_tot, pred = _xsim_distributed_impl(x[sl], y[sl], margin, 4, None, knn_cpu, margin_cpu, knn_bidir_cpu)
             ref_err, ref_n, ref_pred = ox.xsim(x.numpy(), y.numpy(), margin=margin, k=4)
             assert n_tot == ref_n and err == ref_err, (margin, err, ref_err)
             assert np.array_equal(pred.numpy(), ref_pred[sl])

@@ -82,3 +82,43 @@ def test_xsim_rejects_bad_args(native_lib, cuda_device):
         xsim.knn(torch.zeros((4, 64), device=cuda_device), torch.zeros((4, 64), device=cuda_device), 17)
     with pytest.raises(RuntimeError):
         xsim.knn(torch.zeros((4, 64)), torch.zeros((4, 64)), 2)
+
+
+@pytest.mark.parametrize("n,m,d,k", [(300, 1000, 1024, 4), (1000, 777, 1024, 4), (64, 20, 256, 4), (5, 3, 64, 2),
+                                     (4096, 8192, 1024, 8), (9000, 5000, 1024, 4), (16384, 16384, 1024, 4)])
+def test_knn_bidir_matches_oracle_in_both_directions(native_lib, cuda_device, n, m, d, k):
+    """One pass over x . y^T gives the forward k-NN (per-row running top-16) AND the reverse k-NN (column filter against
+    thresholds from a 1/8 sample of the x rows, then exact re-rank): both must equal the float64 oracle's `knn(x, y)` and
+    `knn(y, x)` index for index, cosine to 1e-12.  Sizes below 4096 x rows take the degenerate sample (stride < 8)."""
+    from sonar_b200 import xsim
+
+    x, y = _data(n, m, d, seed=3 * n + m, noise=0.5)
+    vxy, ixy, vyx, iyx = xsim.knn_bidir(x.to(cuda_device), y.to(cuda_device), k)
+    torch.cuda.synchronize()
+    rvxy, rixy = oracle_xsim.knn(x.numpy(), y.numpy(), k)
+    rvyx, riyx = oracle_xsim.knn(y.numpy(), x.numpy(), k)
+    kk = min(k, m)
+    assert np.array_equal(ixy.cpu().numpy()[:, :kk], rixy[:, :kk])
+    np.testing.assert_allclose(vxy.cpu().numpy()[:, :kk], rvxy[:, :kk], rtol=0, atol=1e-12)
+    kr = min(k, n)
+    assert np.array_equal(iyx.cpu().numpy()[:, :kr], riyx[:, :kr])
+    np.testing.assert_allclose(vyx.cpu().numpy()[:, :kr], rvyx[:, :kr], rtol=0, atol=1e-12)
+    if kr < k:
+        assert (iyx.cpu().numpy()[:, kr:] == -1).all()
+
+
+def test_knn_bidir_near_ties_and_dense_columns(native_lib, cuda_device):
+    """Clustered data: a y row has dozens of x rows within the bf16 margin of its k-th best -- the column buffers fill far
+    beyond the typical load (and overflow for the tightest clusters, which must take the exact fallback): still the oracle's
+    neighbours."""
+    from sonar_b200 import xsim
+
+    g = torch.Generator().manual_seed(17)
+    centers = torch.randn((16, 1024), generator=g)
+    y = centers.repeat_interleave(512, 0) + 0.01 * torch.randn((8192, 1024), generator=g)  # clusters of 512 near-duplicates
+    x = y + 0.005 * torch.randn(y.shape, generator=g)
+    vxy, ixy, vyx, iyx = xsim.knn_bidir(x.to(cuda_device), y.to(cuda_device), 4)
+    rvxy, rixy = oracle_xsim.knn(x.numpy(), y.numpy(), 4)
+    rvyx, riyx = oracle_xsim.knn(y.numpy(), x.numpy(), 4)
+    assert np.array_equal(ixy.cpu().numpy(), rixy)
+    assert np.array_equal(iyx.cpu().numpy(), riyx)
