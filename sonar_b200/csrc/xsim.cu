@@ -209,9 +209,13 @@ col_rerank_kernel(const float* __restrict__ x, const float* __restrict__ y, cons
   const int lane = threadIdx.x & 31;
   if (j >= m) return;
   int cnt = col_cnt[j];
-  if (cnt > kColCap) {
-    if (lane == 0) atomicExch(overflow, 1);
-    cnt = kColCap;
+  if (cnt > kColCap) {  // more hits than slots (the threshold of this y row came out low): the caller redoes this row exactly
+    if (lane == 0) atomicAdd(overflow, 1);
+    if (lane < k) {
+      out_val[(long long)j * k + lane] = -CUDART_INF;
+      out_idx[(long long)j * k + lane] = -2;
+    }
+    return;
   }
   constexpr int PER = kColCap / 32;
   float cv[PER];

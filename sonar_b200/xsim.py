@@ -51,8 +51,8 @@ def knn_bidir(x: Tensor, y: Tensor, k: int = 4) -> Tuple[Tensor, Tensor, Tensor,
     """Both k-NN directions from ONE pass over the similarity matrix (``sb_xsim_knn_bidir``):
     -> (cos_xy fp64 [n,k], idx_xy int32 [n,k], cos_yx fp64 [m,k], idx_yx int32 [m,k]); ``idx_yx`` indexes rows of ``x``.
     The reverse direction's candidates are the products above per-column thresholds taken from a 1/8 sample of the x rows;
-    in the (unobserved) case that a column collects more candidates than its buffer holds, the reverse direction is
-    recomputed with a second pass so the result is always exact."""
+    the few y rows whose threshold came out so low that they collect more candidates than their buffer holds (marked
+    ``idx = -2`` by the kernel) are redone with the plain one-direction search against all of x."""
     x, y = _need_cuda_f32(x), _need_cuda_f32(y)
     n, d = x.shape
     m = y.shape[0]
@@ -72,8 +72,11 @@ def knn_bidir(x: Tensor, y: Tensor, k: int = 4) -> Tuple[Tensor, Tensor, Tensor,
                                    torch.cuda.current_stream(x.device).cuda_stream)
     _lib.check(rc, "sb_xsim_knn_bidir")
     del ws
-    if int(overflow.item()) != 0:  # a column's candidate buffer overflowed: exact fallback for the reverse direction
-        val_yx, idx_yx = knn(y, x, k)
+    if int(overflow.item()) != 0:  # rows of y whose candidate buffer overflowed: one-direction search for just those rows
+        rows = (idx_yx[:, 0] == -2).nonzero(as_tuple=True)[0]
+        v2, i2 = knn(y[rows].contiguous(), x, k)
+        val_yx[rows] = v2
+        idx_yx[rows] = i2
     return val_xy, idx_xy, val_yx, idx_yx
 
 

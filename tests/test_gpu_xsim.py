@@ -107,18 +107,38 @@ def test_knn_bidir_matches_oracle_in_both_directions(native_lib, cuda_device, n,
         assert (iyx.cpu().numpy()[:, kr:] == -1).all()
 
 
-def test_knn_bidir_near_ties_and_dense_columns(native_lib, cuda_device):
-    """Clustered data: a y row has dozens of x rows within the bf16 margin of its k-th best -- the column buffers fill far
-    beyond the typical load (and overflow for the tightest clusters, which must take the exact fallback): still the oracle's
-    neighbours."""
+def test_knn_bidir_reverse_near_ties_are_ranked_exactly(native_lib, cuda_device):
+    """Every y row has 8 x rows whose cosines differ by less than the bf16 resolution of the GEMM (8 noisy copies): all of them
+    clear the column threshold, and the exact fp64 re-rank must order them like the oracle."""
     from sonar_b200 import xsim
 
     g = torch.Generator().manual_seed(17)
-    centers = torch.randn((16, 1024), generator=g)
-    y = centers.repeat_interleave(512, 0) + 0.01 * torch.randn((8192, 1024), generator=g)  # clusters of 512 near-duplicates
-    x = y + 0.005 * torch.randn(y.shape, generator=g)
+    y = torch.randn((1024, 1024), generator=g)
+    x = y.repeat_interleave(8, 0)
+    x = x + 0.05 * torch.randn(x.shape, generator=g) * x.norm(dim=1, keepdim=True) / 32.0
     vxy, ixy, vyx, iyx = xsim.knn_bidir(x.to(cuda_device), y.to(cuda_device), 4)
     rvxy, rixy = oracle_xsim.knn(x.numpy(), y.numpy(), 4)
     rvyx, riyx = oracle_xsim.knn(y.numpy(), x.numpy(), 4)
     assert np.array_equal(ixy.cpu().numpy(), rixy)
     assert np.array_equal(iyx.cpu().numpy(), riyx)
+    np.testing.assert_allclose(vyx.cpu().numpy(), rvyx, rtol=0, atol=1e-12)
+
+
+def test_knn_bidir_column_overflow_takes_the_second_pass(native_lib, cuda_device):
+    """600 near-duplicates of one y row: that row collects more candidates than its buffer holds, is marked by the kernel and
+    redone with the plain one-direction search -- the result must then equal `knn(y, x)` exactly (beyond 16 ties inside the
+    bf16 resolution neither path can promise the oracle's order, so the comparison is with the one-direction kernel, not
+    with the oracle)."""
+    from sonar_b200 import xsim
+
+    g = torch.Generator().manual_seed(19)
+    y = torch.randn((512, 1024), generator=g)
+    x = torch.randn((4096, 1024), generator=g)
+    x[:600] = y[7] + 0.002 * torch.randn((600, 1024), generator=g)
+    xd, yd = x.to(cuda_device), y.to(cuda_device)
+    vxy, ixy, vyx, iyx = xsim.knn_bidir(xd, yd, 4)
+    v2, i2 = xsim.knn(yd, xd, 4)
+    assert torch.equal(iyx, i2) and torch.equal(vyx, v2)
+    v1, i1 = xsim.knn(xd, yd, 4)
+    assert torch.equal(ixy, i1) and torch.equal(vxy, v1)
+    assert int(iyx[7, 0]) < 600  # the duplicates are row 7's neighbours
