@@ -93,5 +93,12 @@ elif which in ("decoder", "decoder_small"):  # a few decoder steps (512 x beam 5
     tk = torch.randint(4, 256000, (r,), device=dev)
     for t in (0, 1, 64, 120):
         model.step(tk, table, t)
+elif which == "xsim_bidir":  # both k-NN directions from one sweep, at the bench size (config 5)
+    from sonar_b200 import xsim
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
+    y = torch.randn((n, 1024), device=dev, generator=g)
+    x = y + 0.1 * torch.randn((n, 1024), device=dev, generator=g)
+    for _ in range(2):
+        xsim.knn_bidir(x, y, 4)
 torch.cuda.synchronize()
 print("done", which)

@@ -319,6 +319,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         // qualifies (32 rows with independent insertion events -> ~2500 instructions per tile per warp on random logits);
         // drained together, a round of insertions serves every lane that has one pending.  Same elements, same order per
         // row, same result bit for bit.
+        const bool cf_on = cf.thr != nullptr && grow < M;
         constexpr int kQ = 16;  // queue entries per thread; drained once any lane holds more than kQ - 8
         uint2* queue = reinterpret_cast<uint2*>(smem_cd_wg) + row_in_tile;  // entry e of this thread at queue[e * 128]
         auto drain = [&]() {
@@ -366,9 +367,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             }
           }
           const float thr = tv[KC - 1];  // (stale between drains: a few extra pushes, rejected when drained)
+          float t8[4] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};  // column filter off / rows beyond M: never hit
+          if (cf_on) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(cf.thr8 + (gcol >> 3)));
+            t8[0] = t.x; t8[1] = t.y; t8[2] = t.z; t8[3] = t.w;
+          }
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
-            if (cf.thr != nullptr && grow < M) {  // column filter: elements above their COLUMN's threshold (rare)
+            if (gm[g8] > t8[g8]) {  // column filter: some element of these 8 is above its COLUMN's threshold (rare)
               const float4 t0 = __ldg(reinterpret_cast<const float4*>(cf.thr + gcol + g8 * 8));
               const float4 t1 = __ldg(reinterpret_cast<const float4*>(cf.thr + gcol + g8 * 8 + 4));
               const float th[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
@@ -673,7 +679,7 @@ int gemm_bf16_topk(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W
                    float* cand_val, int* cand_idx, float* lse_part, int n_chunks, int cta_group, int num_sms,
                    cudaStream_t stream, const ColFilter& cf) {
   if (M <= 0 || N <= 0) return 0;
-  if (cf.thr != nullptr && (!cf.cnt || !cf.buf || cf.cap <= 0)) {
+  if (cf.thr != nullptr && (!cf.thr8 || !cf.cnt || !cf.buf || cf.cap <= 0)) {
     set_last_error("gemm_bf16_topk: column filter needs cnt, buf and a positive capacity");
     return -1;
   }

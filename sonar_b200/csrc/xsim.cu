@@ -144,7 +144,51 @@ __global__ void margin_predict_kernel(const double* __restrict__ val_xy, const i
 constexpr int kXsimCands = kTopkListsPerChunk * kTopkCandidates;
 static_assert(kXsimCands <= 32, "rerank_kernel maps one candidate to one lane");
 
+// Few query rows (fewer 256-row tile pairs than SM pairs): the key rows are split into up to 16 chunks swept by different
+// clusters, each writing its own two candidate lists; merge_lists_kernel then keeps the 32 best of them per row.
+static int xsim_chunks(int n, int m) {
+  int c = gemm_topk_chunks(n, m, 2, 148);
+  if (c > 16) {
+    const int tiles = (m + 255) / 256, tpc = (tiles + 15) / 16;
+    c = (tiles + tpc - 1) / tpc;
+  }
+  return c;
+}
+
+// one warp per row: the 32 best of `total` (<= 512) candidates by (bf16 score desc, index asc) -> out [n, 32]
+__global__ void __launch_bounds__(256)
+merge_lists_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int total, int n, int m,
+                   float* __restrict__ out_val, int* __restrict__ out_idx) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* cv = cand_val + (long long)row * total;
+  const int* ci = cand_idx + (long long)row * total;
+  out_val[(long long)row * 32 + lane] = -CUDART_INF_F;
+  out_idx[(long long)row * 32 + lane] = -1;
+  __syncwarp();
+  for (int a = lane; a < total; a += 32) {
+    const int ia = ci[a];
+    if (ia < 0 || ia >= m) continue;
+    const float va = cv[a];
+    int rank = 0;
+    for (int b = 0; b < total && rank < 32; ++b) {
+      const int ib = ci[b];
+      if (ib < 0 || ib >= m) continue;
+      const float vb = cv[b];
+      if (vb > va || (vb == va && ib < ia)) ++rank;
+    }
+    if (rank < 32) {
+      out_val[(long long)row * 32 + rank] = va;
+      out_idx[(long long)row * 32 + rank] = ia;
+    }
+  }
+}
+
 struct XsimWs {
+  int chunks;
+  float* merged_val;  // [n, 32], only when chunks > 1
+  int* merged_idx;
   __nv_bfloat16* xn;
   __nv_bfloat16* yn;
   double* nx;
@@ -162,8 +206,16 @@ static XsimWs carve_xsim(int n, int m, int d, void* base) {
   w.yn = reinterpret_cast<__nv_bfloat16*>(p + off); off = align_up_sz(off + (size_t)m * d * 2, 1024);
   w.nx = reinterpret_cast<double*>(p + off); off = align_up_sz(off + (size_t)n * 8, 1024);
   w.ny = reinterpret_cast<double*>(p + off); off = align_up_sz(off + (size_t)m * 8, 1024);
-  w.cand_val = reinterpret_cast<float*>(p + off); off = align_up_sz(off + (size_t)n * kXsimCands * 4, 1024);
-  w.cand_idx = reinterpret_cast<int*>(p + off); off = align_up_sz(off + (size_t)n * kXsimCands * 4, 1024);
+  w.chunks = xsim_chunks(n, m);
+  const size_t per_row = (size_t)gemm_topk_lists(w.chunks) * kTopkCandidates;
+  w.cand_val = reinterpret_cast<float*>(p + off); off = align_up_sz(off + (size_t)n * per_row * 4, 1024);
+  w.cand_idx = reinterpret_cast<int*>(p + off); off = align_up_sz(off + (size_t)n * per_row * 4, 1024);
+  w.merged_val = nullptr;
+  w.merged_idx = nullptr;
+  if (w.chunks > 1) {
+    w.merged_val = reinterpret_cast<float*>(p + off); off = align_up_sz(off + (size_t)n * 32 * 4, 1024);
+    w.merged_idx = reinterpret_cast<int*>(p + off); off = align_up_sz(off + (size_t)n * 32 * 4, 1024);
+  }
   w.bytes = off;
   return w;
 }
@@ -192,6 +244,14 @@ col_threshold_kernel(const float* __restrict__ cand_val, const int* __restrict__
     if (o > v || (o == v && c < lane)) ++rank;
   }
   if (rank == k - 1) thr[row] = (v > -CUDART_INF_F) ? v - kBf16DotMargin : -CUDART_INF_F;
+}
+
+// thr8[g] = min of the thresholds of columns 8g .. 8g+7: the sweep epilogue tests a row's 8-column maximum against it first
+__global__ void group_min8_kernel(const float* __restrict__ thr, float* __restrict__ thr8, long long groups) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= groups) return;
+  const float4 a = *reinterpret_cast<const float4*>(thr + g * 8), b = *reinterpret_cast<const float4*>(thr + g * 8 + 4);
+  thr8[g] = fminf(fminf(fminf(a.x, a.y), fminf(a.z, a.w)), fminf(fminf(b.x, b.y), fminf(b.z, b.w)));
 }
 
 __global__ void fill_f32_kernel(float* p, long long n, float v) {
@@ -297,6 +357,7 @@ struct XsimBidirWs {
   float* s_val;   // [m, 32] sample-pass candidates of the y rows
   int* s_idx;
   float* thr;     // [m padded to 256]
+  float* thr8;    // [m padded to 256, / 8] minimum over each 8 adjacent y rows
   int* cnt;       // [m]
   int* overflow;  // [1]
   uint2* buf;     // [m, kColCap]
@@ -312,6 +373,7 @@ static XsimBidirWs carve_xsim_bidir(int n, int m, int d, void* base) {
   w.s_val = reinterpret_cast<float*>(p + off); off = align_up_sz(off + (size_t)m * kXsimCands * 4, 1024);
   w.s_idx = reinterpret_cast<int*>(p + off); off = align_up_sz(off + (size_t)m * kXsimCands * 4, 1024);
   w.thr = reinterpret_cast<float*>(p + off); off = align_up_sz(off + mp * 4, 1024);
+  w.thr8 = reinterpret_cast<float*>(p + off); off = align_up_sz(off + mp / 8 * 4, 1024);
   w.cnt = reinterpret_cast<int*>(p + off); off = align_up_sz(off + (size_t)m * 4, 1024);
   w.overflow = reinterpret_cast<int*>(p + off); off = align_up_sz(off + 256, 1024);
   w.buf = reinterpret_cast<uint2*>(p + off); off = align_up_sz(off + (size_t)m * kColCap * 8, 1024);
@@ -349,10 +411,19 @@ int sb_xsim_knn(const float* x, const float* y, int32_t n, int32_t m, int32_t d,
   l2_normalize_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(x, w.xn, w.nx, n, d);
   l2_normalize_kernel<<<(unsigned)((m + 7) / 8), 256, 0, stream>>>(y, w.yn, w.ny, m, d);
   SB_CUDA_CHECK(cudaGetLastError());
-  int rc = gemm_bf16_topk(w.xn, d, w.yn, d, n, m, d, w.cand_val, w.cand_idx, nullptr, 1, 2, sms, stream);
+  int rc = gemm_bf16_topk(w.xn, d, w.yn, d, n, m, d, w.cand_val, w.cand_idx, nullptr, w.chunks, 2, sms, stream);
   if (rc) return rc;
-  rerank_kernel<kXsimCands, kTopkCandidates><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(x, y, w.nx, w.ny, w.cand_val, w.cand_idx, n, m, d, k,
-                                                                             out_val, out_idx);
+  const float* cv = w.cand_val;
+  const int* ci = w.cand_idx;
+  if (w.chunks > 1) {
+    merge_lists_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(w.cand_val, w.cand_idx,
+                                                                    gemm_topk_lists(w.chunks) * kTopkCandidates, n, m,
+                                                                    w.merged_val, w.merged_idx);
+    cv = w.merged_val;
+    ci = w.merged_idx;
+  }
+  rerank_kernel<kXsimCands, kTopkCandidates><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(x, y, w.nx, w.ny, cv, ci, n, m, d, k,
+                                                                                          out_val, out_idx);
   SB_CUDA_CHECK(cudaGetLastError());
   return SB_OK;
 }
@@ -396,12 +467,13 @@ int sb_xsim_knn_bidir(const float* x, const float* y, int32_t n, int32_t m, int3
   const long long mp = ((long long)m + 255) / 256 * 256;
   fill_f32_kernel<<<(unsigned)((mp + 255) / 256), 256, 0, stream>>>(w.thr, mp, INFINITY);  // padding columns: never hit
   col_threshold_kernel<<<(unsigned)((m + 7) / 8), 256, 0, stream>>>(w.s_val, w.s_idx, gemm_topk_lists(1), m, k, w.thr);
+  group_min8_kernel<<<(unsigned)((mp / 8 + 255) / 256), 256, 0, stream>>>(w.thr, w.thr8, mp / 8);
   SB_CUDA_CHECK(cudaGetLastError());
   SB_CUDA_CHECK(cudaMemsetAsync(w.cnt, 0, sizeof(int) * (size_t)m, stream));
   SB_CUDA_CHECK(cudaMemsetAsync(w.overflow, 0, sizeof(int), stream));
   // (2) ONE pass over x^ . y^T: per-row top-16 lists (forward direction) + per-column candidates above the thresholds
   ColFilter cf;
-  cf.thr = w.thr; cf.cnt = w.cnt; cf.buf = w.buf; cf.cap = kColCap;
+  cf.thr = w.thr; cf.thr8 = w.thr8; cf.cnt = w.cnt; cf.buf = w.buf; cf.cap = kColCap;
   rc = gemm_bf16_topk(w.base.xn, d, w.base.yn, d, n, m, d, w.base.cand_val, w.base.cand_idx, nullptr, 1, 2, sms, stream, cf);
   if (rc) return rc;
   rerank_kernel<kXsimCands, kTopkCandidates><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(

@@ -47,12 +47,13 @@ def knn(x: Tensor, y: Tensor, k: int = 4) -> Tuple[Tensor, Tensor]:
     return val, idx
 
 
-def knn_bidir(x: Tensor, y: Tensor, k: int = 4) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+def knn_bidir(x: Tensor, y: Tensor, k: int = 4, stats: Optional[dict] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """Both k-NN directions from ONE pass over the similarity matrix (``sb_xsim_knn_bidir``):
     -> (cos_xy fp64 [n,k], idx_xy int32 [n,k], cos_yx fp64 [m,k], idx_yx int32 [m,k]); ``idx_yx`` indexes rows of ``x``.
     The reverse direction's candidates are the products above per-column thresholds taken from a 1/8 sample of the x rows;
     the few y rows whose threshold came out so low that they collect more candidates than their buffer holds (marked
-    ``idx = -2`` by the kernel) are redone with the plain one-direction search against all of x."""
+    ``idx = -2`` by the kernel) are redone with the plain one-direction search against all of x (``stats["overflow_rows"]``
+    reports how many, when a dict is passed)."""
     x, y = _need_cuda_f32(x), _need_cuda_f32(y)
     n, d = x.shape
     m = y.shape[0]
@@ -72,7 +73,10 @@ def knn_bidir(x: Tensor, y: Tensor, k: int = 4) -> Tuple[Tensor, Tensor, Tensor,
                                    torch.cuda.current_stream(x.device).cuda_stream)
     _lib.check(rc, "sb_xsim_knn_bidir")
     del ws
-    if int(overflow.item()) != 0:  # rows of y whose candidate buffer overflowed: one-direction search for just those rows
+    n_over = int(overflow.item())
+    if stats is not None:
+        stats["overflow_rows"] = n_over
+    if n_over != 0:  # rows of y whose candidate buffer overflowed: one-direction search for just those rows
         rows = (idx_yx[:, 0] == -2).nonzero(as_tuple=True)[0]
         v2, i2 = knn(y[rows].contiguous(), x, k)
         val_yx[rows] = v2
