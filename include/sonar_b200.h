@@ -162,6 +162,15 @@ int sb_gemm_ln_consumer(const void* A, int64_t lda, const void* Wf, int64_t ldw,
 int sb_gemm_residual_stats(const void* A, int64_t lda, const void* W, int64_t ldw, float* x, int64_t ldx, const float* bias,
                            void* h_out, int64_t ldh, float* stats_out, int32_t M, int32_t N, int32_t K, void* stream);
 
+/* x += A . W^T + bias (fp32, in place) as the decoder step issues it (the residual additions of
+ * fairseq2's StandardTransformerDecoderLayer, reached from sonar/models/sonar_text/factory.py:263-301): when the
+ * [M/256, N/256] tile pairs leave SM pairs idle (2 560 hypothesis rows x 1 024 columns = 40 tiles on 74 pairs) the K
+ * dimension is split into up to 4 slices run by different SM pairs, which add into x ONE AFTER THE OTHER (hand-over through
+ * `counters`, >= 4 * tiles zero-initialised device ints that the call leaves zero): x + p0, + p1, + p2 -- the same bits on
+ * every run.  With enough tiles it is the plain accumulate epilogue. */
+int sb_gemm_residual_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, float* x, int64_t ldx, const float* bias,
+                            int32_t M, int32_t N, int32_t K, int32_t* counters, int64_t n_counters, void* stream);
+
 /* C[M,N] = epi(A[M,K] * W[N,K]^T + bias[N]) ; A, W bf16 row-major; C bf16 (out_fp32=0) or fp32;
  * residual (SB_EPI_BIAS_RESIDUAL) has C's dtype and may alias C.  N % 256 == 0, K % 64 == 0.
  * cta_group: 2 = paired-CTA tcgen05 tiles, 1 = single-CTA tiles, 0 = automatic (paired tiles, except that M <= 64 with

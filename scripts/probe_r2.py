@@ -105,3 +105,22 @@ if "predict" in which:
               f"-> {8 * t_gpu / 1e3:.2f} s for 8 batches", flush=True)
         del model, pipe, sd
         torch.cuda.empty_cache()
+
+if "decstep" in which:
+    # decoder step time against the position, with every hypothesis on its own KV-cache rows (identity ancestry) and with
+    # the five hypotheses of a sentence sharing one ancestor chain (what beam search converges to): how much of the step
+    # is KV-cache traffic, and how much of it L2 already removes when the rows are shared
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from bench import synthetic_decoder_state_dict  # noqa: E402
+    from sonar_b200 import B200TextDecoderModel, sonar_text_decoder_config  # noqa: E402
+    model = B200TextDecoderModel(sonar_text_decoder_config("basic"), synthetic_decoder_state_dict(dev), dev)
+    n, beam, tmax = 512, 5, 130
+    model.begin(torch.randn((n, 1024), device=dev) * 0.25, beam, tmax)
+    r = n * beam
+    ident = torch.arange(r, dtype=torch.int32, device=dev)[:, None].expand(r, tmax).contiguous()
+    shared = ((torch.arange(r, dtype=torch.int32, device=dev) // beam) * beam)[:, None].expand(r, tmax).contiguous()
+    tk = torch.randint(4, 256000, (r,), device=dev)
+    for t in (8, 64, 120):
+        a = timed(lambda: model.step(tk, ident, t), iters=8, warm=3)
+        b = timed(lambda: model.step(tk, shared, t), iters=8, warm=3)
+        print(f"decoder step 2560 rows, t={t:3d}: own rows {a:.3f} ms   shared ancestors {b:.3f} ms")

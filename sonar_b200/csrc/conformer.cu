@@ -420,10 +420,12 @@ glu_dwconv_kernel(const __nv_bfloat16* __restrict__ g, const int32_t* __restrict
                   __nv_bfloat16* __restrict__ out) {
   constexpr int TP = 64, HALO = KS / 2, ROWS = TP + KS - 1;
   __shared__ __align__(16) float tile[ROWS][64];
+  __shared__ float taps[64 * KS];  // this block's 64 channels x KS taps, read from dw [D, KS] with coalesced loads
   const int b = blockIdx.z, c0 = blockIdx.y * 64, t0 = blockIdx.x * TP;
   const int start = cu[b], len = cu[b + 1] - start;
   if (t0 >= len) return;
   const int tid = threadIdx.x;
+  for (int i = tid; i < 64 * KS; i += 256) taps[i] = __ldg(dw + (long long)c0 * KS + i);
   // 16-byte loads, 8 channels of value and gate per thread; every load of the block is in flight before the first use
   constexpr int kIt = (ROWS * 8 + 255) / 256;
   uint4 a4[kIt], g4[kIt];
@@ -460,7 +462,7 @@ glu_dwconv_kernel(const __nv_bfloat16* __restrict__ g, const int32_t* __restrict
   const int c = tid & 63, pg = tid >> 6;  // 4 groups of 16 positions; each thread slides a register window down one channel
   float w[KS];
 #pragma unroll
-  for (int k = 0; k < KS; ++k) w[k] = dw[(long long)(c0 + c) * KS + k];
+  for (int k = 0; k < KS; ++k) w[k] = taps[c * KS + k];  // stride KS (odd) words across the lanes: conflict-free
   const float sc = bn_scale[c0 + c], sh = bn_shift[c0 + c];
   constexpr int PP = 16;
   float win[PP + KS - 1];

@@ -331,8 +331,11 @@ struct SbDecoder {
 
 namespace {
 
+constexpr long long kSplitkFlags = 4096;  // >= 4 * (tile pairs of an [R, D] residual GEMM) whenever splitting can pay
+
 struct DecWs {
   int32_t* err_flag;
+  int* splitk_flags;      // [kSplitkFlags] hand-over counters of the split-K residual GEMMs (zeroed by sb_decoder_begin)
   float* x;               // [R, D] fp32 residual stream of the current step
   __nv_bfloat16* h;       // [R, D]
   __nv_bfloat16* qkv;     // [R, 3D]
@@ -358,6 +361,7 @@ DecWs carve_dec(const SbDecoder* d, int N, int beam, int Tmax, void* base) {
   auto take = [&](size_t bytes) { uint8_t* q = p + off; off = align_up_d(off + bytes, 1024); return q; };
   w.n_chunks = gemm_topk_chunks((int)R, (int)d->cfg.vocab_size, 2, d->num_sms);
   w.err_flag = reinterpret_cast<int32_t*>(take(256));
+  w.splitk_flags = reinterpret_cast<int*>(take(kSplitkFlags * sizeof(int)));
   w.x = reinterpret_cast<float*>(take(R * D * 4));
   w.h = reinterpret_cast<__nv_bfloat16*>(take(R * D * 2));
   w.qkv = reinterpret_cast<__nv_bfloat16*>(take(R * 3 * D * 2));
@@ -473,6 +477,7 @@ int sb_decoder_begin(SbDecoder* d, const float* embeddings, int32_t N, int32_t b
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   const int D = d->cfg.model_dim;
   SB_CUDA_CHECK(cudaMemsetAsync(w.err_flag, 0, sizeof(int32_t), stream));
+  SB_CUDA_CHECK(cudaMemsetAsync(w.splitk_flags, 0, kSplitkFlags * sizeof(int), stream));
   const long long n = (long long)N * D;
   cast_bf16_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, stream>>>(embeddings, w.ebf, n);
   SB_CUDA_CHECK(cudaGetLastError());
@@ -529,6 +534,8 @@ int sb_decoder_step(SbDecoder* d, const int64_t* tokens, const int32_t* table, i
   g.cta_group = 2;
   g.num_sms = d->num_sms;
   g.M = R;
+  g.splitk_flags = w.splitk_flags;  // the residual GEMMs may split K when their tiles leave SM pairs idle (2 560 rows)
+  g.splitk_flags_len = kSplitkFlags;
   const size_t layer_stride = (size_t)R * max_len * D;
   for (int li = 0; li < d->cfg.num_layers; ++li) {
     const SbDecoderLayerWeights& L = d->layers[li];

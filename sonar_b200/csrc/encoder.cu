@@ -115,7 +115,7 @@ static Workspace carve(const SbEncoder* e, int32_t max_batch, int64_t max_tokens
 extern "C" {
 
 const char* sb_last_error(void) { return g_err; }
-int sb_version(void) { return 101; }
+int sb_version(void) { return 102; }
 
 int sb_encoder_create(const SbEncoderConfig* cfg, const SbEncoderWeights* w, SbEncoder** out) {
   if (!cfg || !w || !out) { set_last_error("sb_encoder_create: null argument"); return SB_ERR_INVALID; }
@@ -481,6 +481,24 @@ int sb_gemm_residual_stats(const void* A, int64_t lda, const void* W, int64_t ld
   g.M = M; g.N = N; g.K = K; g.epi = EPI_BIAS_RESIDUAL_STATS;
   g.cta_group = 2;
   g.lf.h_out = reinterpret_cast<__nv_bfloat16*>(h_out); g.lf.ldh = ldh; g.lf.stats_out = stats_out;
+  int dev = 0, sms = 0;
+  SB_CUDA_CHECK(cudaGetDevice(&dev));
+  SB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  g.num_sms = sms;
+  return gemm_bf16(g, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sb_gemm_residual_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, float* x, int64_t ldx, const float* bias,
+                            int32_t M, int32_t N, int32_t K, int32_t* counters, int64_t n_counters, void* stream) {
+  if (!A || !W || !x || !bias || !counters) { set_last_error("sb_gemm_residual_splitk: null pointer"); return SB_ERR_INVALID; }
+  GemmArgs g;
+  g.A = reinterpret_cast<const __nv_bfloat16*>(A); g.lda = lda;
+  g.W = reinterpret_cast<const __nv_bfloat16*>(W); g.ldw = ldw;
+  g.C = x; g.ldc = ldx; g.out_fp32 = 1; g.bias = bias; g.residual = x; g.ldr = ldx;
+  g.M = M; g.N = N; g.K = K; g.epi = EPI_BIAS_RESIDUAL;
+  g.cta_group = 2;
+  g.splitk_flags = counters;
+  g.splitk_flags_len = n_counters;
   int dev = 0, sms = 0;
   SB_CUDA_CHECK(cudaGetDevice(&dev));
   SB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -57,15 +57,18 @@ struct GemmCfg {
 template <bool kSweep>
 struct TileSched {
   int num_m_tiles, num_n_tiles, cluster_id, num_clusters, n_chunks, tiles_per_chunk;
+  int k_splits = 1;  // split-K (accumulate epilogue, few tiles): item = split * tiles + tile, `chunk` returns the split
   int i = 0, j = 0;
   __device__ __forceinline__ bool next(int& m_blk, int& n_blk, int& chunk, bool& first, bool& last) {
     if constexpr (!kSweep) {
-      const int tile = cluster_id + i * num_clusters;
+      const int item = cluster_id + i * num_clusters;
       ++i;
-      if (tile >= num_m_tiles * num_n_tiles) return false;
+      const int tiles = num_m_tiles * num_n_tiles;
+      if (item >= tiles * k_splits) return false;
+      const int tile = (k_splits == 1) ? item : item % tiles;
+      chunk = (k_splits == 1) ? 0 : item / tiles;
       m_blk = tile / num_n_tiles;
       n_blk = tile % num_n_tiles;
-      chunk = 0;
       first = last = true;
       return true;
     } else {
@@ -113,7 +116,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                          const __grid_constant__ CUtensorMap tm_c, const float* __restrict__ bias,
                          const OutT* residual, long long ldr, int M, int N, int K, float* __restrict__ cand_val,
                          int* __restrict__ cand_idx, float* __restrict__ lse_part, int n_chunks, const LnFold lf,
-                         const ColFilter cf) {
+                         const ColFilter cf, int k_splits, int* __restrict__ splitk_flags) {
   constexpr bool kSweep = (kEpi == EPI_TOPK);
   using Cfg = GemmCfg<kCtaGroup, kEpiGroups>;
   extern __shared__ uint8_t smem_raw[];
@@ -163,7 +166,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   const int cluster_id = blockIdx.x / kCtaGroup;
   const int num_clusters = gridDim.x / kCtaGroup;
   TileSched<kSweep> sched{num_m_tiles, num_n_tiles, cluster_id, num_clusters, n_chunks,
-                          (num_n_tiles + n_chunks - 1) / n_chunks};
+                          (num_n_tiles + n_chunks - 1) / n_chunks, (kEpi == EPI_BIAS_ACCUM) ? k_splits : 1};
+  // split-K: split s of a tile runs k-blocks [s * num_kb / k_splits, (s + 1) * num_kb / k_splits)
+  auto kb_begin = [&](int split) { return (kEpi == EPI_BIAS_ACCUM && k_splits > 1) ? split * num_kb / k_splits : 0; };
+  auto kb_end = [&](int split) { return (kEpi == EPI_BIAS_ACCUM && k_splits > 1) ? (split + 1) * num_kb / k_splits : num_kb; };
   int m_blk, n_blk, chunk;
   bool first_in_item, last_in_item;
 
@@ -175,7 +181,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       while (sched.next(m_blk, n_blk, chunk, first_in_item, last_in_item)) {
         const int m0 = m_blk * tile_m + int(cta_rank) * Cfg::BLOCK_M;
         const int n0 = n_blk * Cfg::BLOCK_N + int(cta_rank) * Cfg::LOAD_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb1 = kb_end(chunk);
+        for (int kb = kb_begin(chunk); kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], (Cfg::A_BYTES + Cfg::B_BYTES) * kCtaGroup);
           if (kCtaGroup == 2) {
@@ -206,7 +213,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = kb_begin(chunk), kb1 = kb_end(chunk);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);  // TMA bytes of both CTAs have landed
           tc_fence_after();
           if (elect_one()) {
@@ -217,10 +225,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
               // +32 bytes (= 16 bf16) along K inside the 128B swizzle atom -> +2 in the >>4 address field
               const uint64_t a_desc = (uint64_t(desc_hi) << 32) | uint64_t(a_lo + 2 * k);
               const uint64_t b_desc = (uint64_t(desc_hi) << 32) | uint64_t(b_lo + 2 * k);
-              umma_bf16<kCtaGroup>(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16<kCtaGroup>(d_tmem, a_desc, b_desc, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
             }
             umma_commit<kCtaGroup>(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-            if (kb == num_kb - 1) umma_commit<kCtaGroup>(&tmem_full_bar[acc]);
+            if (kb == kb1 - 1) umma_commit<kCtaGroup>(&tmem_full_bar[acc]);
           }
           __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -446,9 +454,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
               f[j + 3] = fmaf(ln_rstd, fmaf(-ln_mean, c4.w, __uint_as_float(v[j + 3])), b4.w);
             }
           } else {
+            // split-K: the bias belongs to split 0, the later splits add their bare partial products
+            const bool with_bias = !(kEpi == EPI_BIAS_ACCUM && chunk > 0);
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + gcol + j));
+              const float4 b4 = with_bias ? __ldg(reinterpret_cast<const float4*>(bias + gcol + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
               f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
               f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
               f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
@@ -556,11 +566,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
         if (ew == 0 && lane == 0) {
-          if constexpr (kEpi == EPI_BIAS_ACCUM)
+          if constexpr (kEpi == EPI_BIAS_ACCUM) {
+            // Ordered split-K: the splits of a tile add into C one after the other (x + p0, + p1, + p2 -- the same sum on
+            // every run).  Split s waits for the counter its predecessor leaves after ITS adds have completed; the
+            // predecessor is a lower-numbered item, so it is already running on another resident cluster or finished.
+            int* flag = nullptr;
+            if (k_splits > 1) {
+              flag = splitk_flags + ((long long)(m_blk * num_n_tiles + n_blk) * kCtaGroup + int(cta_rank)) * Cfg::EPI_GROUPS + wg;
+              if (c == wg && chunk > 0) {
+                while (ld_acquire_gpu(flag) != chunk) __nanosleep(64);
+                fence_proxy_async_all();
+              }
+            }
             tma_reduce_add_2d(&tm_c, smem_cd_wg + cd_stage * Cfg::CD_STAGE_BYTES, n0 + c * CHUNK_COLS, m0);
-          else
+            tma_store_commit();
+            if (k_splits > 1 && c + Cfg::EPI_GROUPS >= NUM_CHUNKS) {
+              tma_store_wait_all<0>();  // this split's adds have been performed
+              fence_proxy_async_all();
+              __threadfence();
+              st_release_gpu(flag, chunk == k_splits - 1 ? 0 : chunk + 1);  // the last split re-arms the counter
+            }
+          } else {
             tma_store_2d(&tm_c, smem_cd_wg + cd_stage * Cfg::CD_STAGE_BYTES, n0 + c * CHUNK_COLS, m0);
-          tma_store_commit();
+            tma_store_commit();
+          }
         }
         cd_stage ^= 1;
       }
@@ -627,7 +656,8 @@ template <int kCtaGroup, int kEpi, typename OutT, int kEpiGroups = 2>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const float* bias,
                        const void* residual, long long ldr, int M, int N, int K, int num_sms, cudaStream_t stream,
                        float* cand_val = nullptr, int* cand_idx = nullptr, float* lse_part = nullptr,
-                       int n_chunks = 1, const LnFold& lf = LnFold(), const ColFilter& cf = ColFilter()) {
+                       int n_chunks = 1, const LnFold& lf = LnFold(), const ColFilter& cf = ColFilter(), int k_splits = 1,
+                       int* splitk_flags = nullptr) {
   using Cfg = GemmCfg<kCtaGroup, kEpiGroups>;
   auto kern = gemm_bf16_tcgen05_kernel<kCtaGroup, kEpi, OutT, kEpiGroups>;
   static bool attr_set[64] = {};
@@ -638,7 +668,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   const long long num_m_tiles = (M + tile_m - 1) / tile_m;
   const long long num_tiles = num_m_tiles * ((N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N);
   long long clusters = num_sms / kCtaGroup;
-  if (clusters > num_tiles) clusters = num_tiles;
+  if (clusters > num_tiles * k_splits) clusters = num_tiles * k_splits;
   if (kEpi == EPI_TOPK && clusters > num_m_tiles * n_chunks) clusters = num_m_tiles * n_chunks;  // whole items
   if (clusters < 1) clusters = 1;
   cudaLaunchConfig_t cfg = {};
@@ -654,7 +684,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   SB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, bias, reinterpret_cast<const OutT*>(residual), ldr, M, N, K,
-                                   cand_val, cand_idx, lse_part, n_chunks, lf, cf));
+                                   cand_val, cand_idx, lse_part, n_chunks, lf, cf, k_splits, splitk_flags));
   return 0;
 }
 
@@ -768,6 +798,25 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     if (epi == EPI_BIAS)
       return launch_inst<2, EPI_BIAS, __nv_bfloat16, 1>(ta, tb, tc, g.bias, g.residual, g.ldr, g.M, g.N, g.K, sms, stream);
     return launch_inst<2, EPI_BIAS_RELU, __nv_bfloat16, 1>(ta, tb, tc, g.bias, g.residual, g.ldr, g.M, g.N, g.K, sms, stream);
+  }
+
+  // Ordered split-K for the accumulate epilogue when the tiles do not fill the machine (the decoder's FFN output
+  // projection at 2 560 rows: 40 tile pairs on 74 SM pairs): pick the split count with the fewest k-blocks on the
+  // critical path, ~8 k-blocks charged per item for its epilogue and hand-over.
+  if (epi == EPI_BIAS_ACCUM && cg == 2 && g.splitk_flags != nullptr) {
+    const long long tiles = (long long)((g.M + 255) / 256) * (g.N / 256);
+    const long long clusters = sms / 2;
+    const int num_kb = g.K / 64;
+    int best = 1;
+    double best_cost = 1e30;
+    for (int ks = 1; ks <= 4; ++ks) {
+      if (num_kb / ks < 8) break;
+      const double cost = double((tiles * ks + clusters - 1) / clusters) * (double(num_kb) / ks + 8.0);
+      if (cost < best_cost * 0.95) { best_cost = cost; best = ks; }  // a later candidate must win by 5 %
+    }
+    if (best > 1 && tiles * 2 * 2 <= g.splitk_flags_len)
+      return launch_inst<2, EPI_BIAS_ACCUM, float>(ta, tb, tc, g.bias, g.residual, g.ldr, g.M, g.N, g.K, sms, stream, nullptr,
+                                                   nullptr, nullptr, 1, LnFold(), ColFilter(), best, g.splitk_flags);
   }
 
 #define SB_DISPATCH(CG, EPI, T)                                                                                   \

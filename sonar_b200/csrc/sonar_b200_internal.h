@@ -75,6 +75,11 @@ struct GemmArgs {
   // 2 (default) = two epilogue warpgroups / 5 mainloop stages; 1 = one epilogue warpgroup / 6 stages (A/B variant, only
   // for the text encoder's bias, bias+ReLU and accumulate epilogues with paired CTAs)
   int epi_groups = 2;
+  // Ordered split-K of the accumulate epilogue (x += A.W^T + b with few tiles): zero-initialised device counters, one per
+  // (tile, CTA of the pair, epilogue warpgroup); the kernel leaves them zero.  nullptr = never split.  Changes the
+  // summation order (deterministically), so only callers that do not promise batch-size-independent bits pass it.
+  int* splitk_flags = nullptr;
+  long long splitk_flags_len = 0;
 };
 
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);

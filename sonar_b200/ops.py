@@ -104,6 +104,19 @@ def gemm_residual_stats(a: Tensor, w: Tensor, bias: Tensor, x: Tensor):
     return h, stats
 
 
+def gemm_residual_splitk(a: Tensor, w: Tensor, bias: Tensor, x: Tensor, counters: Tensor) -> Tensor:
+    """x += a . w^T + bias in place (fp32) with the decoder step's ordered split-K (``sb_gemm_residual_splitk``);
+    ``counters``: zero-initialised int32 device tensor with >= 4 * (M/256 * N/256) entries, left zero."""
+    _need_cuda(a, w, bias, x, counters)
+    m, k = a.shape
+    n = w.shape[0]
+    assert x.shape == (m, n) and x.dtype == torch.float32 and x.is_contiguous() and counters.dtype == torch.int32
+    rc = _lib.load().sb_gemm_residual_splitk(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), x.data_ptr(), n,
+                                             bias.data_ptr(), m, n, k, counters.data_ptr(), counters.numel(), _stream())
+    _lib.check(rc, "sb_gemm_residual_splitk")
+    return x
+
+
 def gemm_ln_consumer(a: Tensor, wf: Tensor, bias_f: Tensor, colsum: Tensor, stats: Tensor, eps: float = 1e-5,
                      relu: bool = False) -> Tensor:
     """bf16 [M,N] = [relu](rstd * (a . wf^T - mean * colsum) + bias_f), (mean, rstd) merged from stats [M, K/128, 2]

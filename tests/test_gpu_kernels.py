@@ -282,6 +282,39 @@ def test_gemm_residual_stats(ops, cuda_device, m, k):
     torch.testing.assert_close(stats[..., 1].double(), m2, rtol=2e-5, atol=1e-4)
 
 
+# ------------------------------------------------------------------------------------------------
+# ordered split-K of the accumulate epilogue (the decoder's residual GEMMs at 2 560 hypothesis rows)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,n,k", [(2560, 1024, 8192),   # config 4: 40 tile pairs -> 3 K slices
+                                   (2560, 1024, 1024),   # too little K per slice: not split
+                                   (2500, 512, 4096),    # ragged last row tile, 20 tile pairs
+                                   (700, 256, 2048),     # 3 tile pairs -> 4 slices
+                                   (40000, 1024, 8192)])  # plenty of tiles: plain accumulate epilogue
+def test_gemm_residual_splitk(ops, cuda_device, m, n, k):
+    """x += a.W^T + b through the split-K path: right value, the SAME bits on every run (the slices add in a fixed order),
+    hand-over counters back at zero, and x rows beyond M untouched."""
+    a = _rand((m, k), 1.0, 51, cuda_device, torch.bfloat16)
+    w = _rand((n, k), 1.0 / math.sqrt(k), 52, cuda_device, torch.bfloat16)
+    bias = _rand((n,), 0.5, 53, cuda_device)
+    x0 = _rand((m + 3, n), 1.0, 54, cuda_device)
+    counters = torch.zeros(4 * ((m + 255) // 256) * (n // 256) + 8, dtype=torch.int32, device=cuda_device)
+    ref = x0[:m].double() + a.double() @ w.double().T + bias.double()
+    runs = []
+    for _ in range(4):
+        x = x0.clone()
+        ops.gemm_residual_splitk(a, w, bias, x[:m], counters)
+        torch.cuda.synchronize()
+        assert int(counters.abs().sum()) == 0
+        assert torch.equal(x[m:], x0[m:])
+        torch.testing.assert_close(x[:m].double(), ref, rtol=1e-5, atol=2e-3)
+        runs.append(x)
+    assert all(torch.equal(runs[0], r) for r in runs[1:])
+    # against the unsplit accumulate epilogue: same products, another summation order
+    y = x0[:m].clone()
+    ops.gemm_bf16(a, w, bias, epilogue="residual", residual=y, out=y)
+    torch.testing.assert_close(runs[0][:m], y, rtol=1e-5, atol=1e-4)
+
+
 @pytest.mark.parametrize("relu", [False, True])
 @pytest.mark.parametrize("m,n,k", [(1000, 3072, 1024), (2048, 8192, 1024), (130, 512, 512)])
 def test_gemm_ln_consumer_equals_layernorm_then_linear(ops, cuda_device, relu, m, n, k):
