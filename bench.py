@@ -453,6 +453,11 @@ def bench_decoder(dev, peaks):
         worst = max(worst, float((got_lp - torch.gather(ref, 1, got_tk)).abs().max()))
     hyp_tokens = n * beam * steps
     peak = float(peaks["bf16_tflops_sustained"])
+    # the step is a SERIES of kernels with different bounds: the GEMMs against the tensor peak, the KV-cache attention against
+    # HBM (every hypothesis row reads K and V of all earlier positions in all 24 layers: 2 * 2 B * D per position and layer)
+    hbm = float(peaks.get("hbm_gbs", FALLBACK_PEAKS.get("hbm_gbs", 6572.2)))
+    kv_bytes = n * beam * D * 4.0 * 24 * steps * (steps + 1) / 2.0
+    floor_s = hyp_tokens * 1.63e9 / (peak * 1e12) + kv_bytes / (hbm * 1e9)
     del model, oracle, sd_cpu
     return {"workload": f"text_sonar_basic_decoder arch (random init): {n} embeddings, beam {beam}, max_seq_len {max_seq_len} "
                         f"({steps} steps ran: random-weight hypotheses rarely emit EOS early)",
@@ -464,7 +469,10 @@ def bench_decoder(dev, peaks):
             "batch5_beam5": {"wall_s": d5, "steps": st5, "ms_per_step": d5 / st5 * 1e3},
             "roofline": {"bound": "tensor", "achieved": hyp_tokens * 1.63e9 / dt / 1e12, "peak": peak, "unit": "TFLOP/s",
                          "frac": hyp_tokens * 1.63e9 / dt / 1e12 / peak,
-                         "algorithmic_flop_per_hypothesis_token": 1.63e9},
+                         "algorithmic_flop_per_hypothesis_token": 1.63e9,
+                         "serial_floor": {"frac": floor_s / dt, "floor_s": floor_s, "kv_cache_bytes": kv_bytes,
+                                          "note": "GEMM flops / sustained bf16 peak + KV-cache bytes / measured HBM bandwidth: "
+                                                  "the kernels run one after the other, so their floors add"}},
             "parity_vs_oracle": {"rows": 64, "of_rows": R, "steps": 3, "max_abs_lprob_err": worst,
                                  "tolerance": "2e-2 + 2e-3*|lprob| (tests/test_gpu_decoder.py)"}}
 

@@ -93,6 +93,13 @@ elif which in ("decoder", "decoder_small"):  # a few decoder steps (512 x beam 5
     tk = torch.randint(4, 256000, (r,), device=dev)
     for t in (0, 1, 64, 120):
         model.step(tk, table, t)
+elif which == "text_step":  # three forwards of the benched text encoder (4096 x 128): 170 kernels per forward
+    from bench import BATCH, SEQ, VOCAB, synthetic_state_dict
+    from sonar_b200 import B200TextEncoderModel, SequenceBatch, sonar_text_encoder_config
+    model = B200TextEncoderModel(sonar_text_encoder_config("basic"), synthetic_state_dict(dev), dev)
+    ids = torch.randint(4, VOCAB, (BATCH, SEQ), device=dev, dtype=torch.int64)
+    for _ in range(3):
+        model(SequenceBatch(ids, None))
 elif which == "xsim_bidir":  # both k-NN directions from one sweep, at the bench size (config 5)
     from sonar_b200 import xsim
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
