@@ -165,13 +165,17 @@ class TextToEmbeddingModelPipeline(torch.nn.Module):
 
         out_device = torch.device(target_device) if target_device is not None else self.device
 
+        n_known = None if isinstance(input, (str, Path)) else len(input)
+        sink = _HostSink(self, n_known) if (on_cuda and out_device.type == "cpu") else None
+
         def run_model() -> Iterable[Tensor]:
             # One batch of lag between launching a batch and collecting its embeddings: batch k+1 is already queued on the
             # GPU when the host blocks on the device->host copy of batch k, so the GPU never idles between batches (the
             # reference's `.map(self.model)` + `.to(target_device)` per batch leaves that gap).
             pending = None
             for b in prefetch(batches(), 2):
-                cur = _PendingEmbeddings(self.model(b).sentence_embeddings, out_device)
+                emb = self.model(b).sentence_embeddings
+                cur = sink.push(emb) if sink is not None and emb.is_cuda else _Ready(emb.to(out_device, non_blocking=True))
                 if pending is not None:
                     yield pending.get()
                 pending = cur
@@ -196,7 +200,8 @@ class TextToEmbeddingModelPipeline(torch.nn.Module):
                 f"For {n_truncated} input tensors for SONAR text encoder, "
                 f"the length was truncated to {max_seq_len} elements.")
 
-        sentence_embeddings = torch.cat(results, dim=0)
+        whole = sink.result(results) if sink is not None else None
+        sentence_embeddings = whole if whole is not None else torch.cat(results, dim=0)
         if self.dtype is not None:
             sentence_embeddings = sentence_embeddings.to(self.dtype)
 
@@ -206,24 +211,64 @@ class TextToEmbeddingModelPipeline(torch.nn.Module):
         return sentence_embeddings
 
 
-class _PendingEmbeddings:
-    """Embeddings of one batch on their way to `device`: a device->host copy goes through pinned memory without blocking the
-    launching thread; `get()` waits for it."""
-
-    def __init__(self, emb: Tensor, device: torch.device) -> None:
-        self._event = None
-        if emb.is_cuda and device.type == "cpu":
-            self._out = torch.empty(emb.shape, dtype=emb.dtype, pin_memory=True)
-            self._out.copy_(emb, non_blocking=True)
-            self._event = torch.cuda.Event()
-            self._event.record(torch.cuda.current_stream(emb.device))
-        else:
-            self._out = emb.to(device, non_blocking=True)
+class _Ready:
+    def __init__(self, t: Tensor) -> None:
+        self._t = t
 
     def get(self) -> Tensor:
-        if self._event is not None:
+        return self._t
+
+
+class _HostSink:
+    """Device -> host path of `predict(target_device="cpu")`.  Every batch is copied (asynchronously, on the launching
+    stream, right behind its kernels) into one of TWO pinned staging buffers that live as long as the pipeline -- no pinned
+    allocation per batch (`cudaHostAlloc` takes milliseconds to hundreds of milliseconds depending on the host's memory
+    state) -- and from there into its slice of ONE result tensor allocated up front when the number of sentences is known,
+    so there is no final `torch.cat` either.  With one batch of lag (see `predict`) slot k % 2 is free again when batch k + 2
+    arrives."""
+
+    def __init__(self, owner, n_total: Optional[int]) -> None:
+        self._owner = owner
+        self._n_total = n_total
+        self._out: Optional[Tensor] = None
+        self._pos = 0
+        self._k = 0
+
+    def push(self, emb: Tensor) -> "_HostSink._Slot":
+        n, d = emb.shape
+        ring = getattr(self._owner, "_d2h_ring", None)
+        if ring is None or ring[0].shape[0] < n or ring[0].shape[1] != d or ring[0].dtype != emb.dtype:
+            ring = [torch.empty((n, d), dtype=emb.dtype, pin_memory=True) for _ in range(2)]
+            self._owner._d2h_ring = ring
+        stage = ring[self._k % 2][:n]
+        self._k += 1
+        stage.copy_(emb, non_blocking=True)
+        event = torch.cuda.Event()
+        event.record(torch.cuda.current_stream(emb.device))
+        if self._n_total is not None and self._out is None:
+            self._out = torch.empty((self._n_total, d), dtype=emb.dtype)
+        dst = None
+        if self._out is not None and self._pos + n <= self._out.shape[0]:
+            dst = self._out[self._pos:self._pos + n]
+            self._pos += n
+        return _HostSink._Slot(stage, event, dst)
+
+    def result(self, parts: List[Tensor]) -> Optional[Tensor]:
+        """The preallocated result when every batch landed in it, else None (the caller concatenates)."""
+        if self._out is not None and self._pos == self._out.shape[0] and sum(p.shape[0] for p in parts) == self._pos:
+            return self._out
+        return None
+
+    class _Slot:
+        def __init__(self, stage: Tensor, event, dst: Optional[Tensor]) -> None:
+            self._stage, self._event, self._dst = stage, event, dst
+
+        def get(self) -> Tensor:
             self._event.synchronize()
-        return self._out
+            if self._dst is None:
+                return self._stage.clone()
+            self._dst.copy_(self._stage)
+            return self._dst
 
 
 def _load_decoder_card(name: str, device: Device) -> B200TextDecoderModel:

@@ -139,13 +139,17 @@ class B200TextEncoderModel(torch.nn.Module):
     """SONAR text encoder (24-layer pre-LN Transformer + final LN + pooling) on sm_100a kernels."""
 
     def __init__(self, config: SonarTextEncoderConfig, state_dict: Dict[str, Tensor],
-                 device: Union[str, torch.device] = "cuda", *, cta_group: int = 2, ln_fold: Union[bool, int] = False, epi_groups: int = 1) -> None:
+                 device: Union[str, torch.device] = "cuda", *, cta_group: int = 2, ln_fold: Union[bool, int] = False,
+                 epi_groups: Optional[int] = None) -> None:
         """``ln_fold=True``: the engine folds every encoder-layer LayerNorm into the GEMMs around it (see
         ``SbEncoderConfig.ln_fold`` in ``include/sonar_b200.h``); the default runs the separate LayerNorm kernels, which is
         the faster schedule as measured.  ``epi_groups``: epilogue warpgroups per GEMM CTA -- 1 (six mainloop stages) is the
         default here: inside the power-capped 24-layer step it is 2 % faster than 2 (five stages), although 2 wins by 9-33 %
-        when a GEMM is timed alone at boost clocks (``bench.py`` A/Bs all of these in every run, ``ab_schedule_variants``)."""
+        when a GEMM is timed alone at boost clocks (``bench.py`` A/Bs all of these in every run, ``ab_schedule_variants``).
+        The folded schedules exist with two warpgroups only, so ``None`` means 1 without and 2 with ``ln_fold``."""
         super().__init__()
+        if epi_groups is None:
+            epi_groups = 2 if int(ln_fold) else 1
         self.ln_fold = int(ln_fold)  # 0 = separate LayerNorm kernels, 1 = both folded, 2 = only the attention-block one
         self.epi_groups = int(epi_groups)
         _check_supported(config)
