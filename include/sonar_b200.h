@@ -371,10 +371,13 @@ int sb_xsim_knn(const float* x, const float* y, int32_t n, int32_t m, int32_t d,
 
 /* Both k-NN directions from ONE pass over x^ . y^T ("row top-k and simultaneously per-column partial top-k"):
  * val_xy / idx_xy [n,k] as sb_xsim_knn; val_yx / idx_yx [m,k] = for every y row its k nearest x rows (exact fp64 cosines,
- * int32 row indices).  The reverse direction's candidates are the elements of the product above a per-column threshold
- * taken from a 1/8 sample of the x rows (a 1/8-size GEMM); a y row that collects more candidates than its 256 slots is
- * marked idx_yx[j, :] = -2 and counted in *overflow_flag (DEVICE int): the caller recomputes those rows with
- * sb_xsim_knn(y[rows], x) (sonar_b200/xsim.py::knn_bidir does; a fraction of a percent of the rows on random data). */
+ * int32 row indices).  The reverse direction's candidates are the elements of the product above a per-column threshold:
+ * the 16th best bf16 score of that y row against every 8th x row (a 1/8-size GEMM).  sb_xsim_knn keeps the 16 best bf16
+ * scores of a row and re-scores them exactly, and a subset's 16th best never exceeds the 16th best over all rows, so the
+ * result equals sb_xsim_knn(y, x) for any data; about 16 * 8 = 128 rows pass per column whatever the score distribution.
+ * A y row that collects more than its 256 slots (heavy ties / duplicates) is marked idx_yx[j, :] = -2 and counted in
+ * *overflow_flag (DEVICE int): the caller recomputes those rows with sb_xsim_knn(y[rows], x) (sonar_b200/xsim.py::knn_bidir
+ * does). */
 int sb_xsim_bidir_workspace_bytes(int32_t n, int32_t m, int32_t d, size_t* bytes);
 int sb_xsim_knn_bidir(const float* x, const float* y, int32_t n, int32_t m, int32_t d, int32_t k, double* val_xy,
                       int32_t* idx_xy, double* val_yx, int32_t* idx_yx, int32_t* overflow_flag, void* workspace,

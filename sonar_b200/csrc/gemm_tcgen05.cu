@@ -383,8 +383,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
             if (gm[g8] > t8[g8]) {  // column filter: some element of these 8 is above its COLUMN's threshold (rare)
-              const float4 t0 = __ldg(reinterpret_cast<const float4*>(cf.thr + gcol + g8 * 8));
-              const float4 t1 = __ldg(reinterpret_cast<const float4*>(cf.thr + gcol + g8 * 8 + 4));
+              const float4 t0 = *reinterpret_cast<const float4*>(cf.thr + gcol + g8 * 8);  // (not __ldg: columns get closed)
+              const float4 t1 = *reinterpret_cast<const float4*>(cf.thr + gcol + g8 * 8 + 4);
               const float th[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -393,6 +393,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                   const int col = gcol + g8 * 8 + j;
                   const int slot = atomicAdd(cf.cnt + col, 1);
                   if (slot < cf.cap) cf.buf[(long long)col * cf.cap + slot] = make_uint2(__float_as_uint(x), uint32_t(grow));
+                  else cf.thr[col] = CUDART_INF_F;  // full: the caller redoes this column; stop collecting for it
                 }
               }
             }

@@ -90,11 +90,13 @@ int gemm_skinny(const GemmArgs& g, cudaStream_t stream);
 
 // Column filter of the top-k sweep (xsim: both k-NN directions from ONE pass over x . y^T): next to the per-row lists, every
 // element above its column's threshold is appended to that column's candidate buffer -- entry = (bf16 product as fp32 bits,
-// row index); `cnt[col]` counts every hit (also those beyond `cap`, which are dropped: the caller checks for overflow).
+// row index); `cnt[col]` counts the hits (beyond `cap` they are dropped and the column's threshold is raised to +inf so that
+// degenerate inputs -- every product above its threshold -- cannot turn the sweep into a stream of atomics: the caller checks
+// cnt > cap).
 // `thr` must be readable up to the next multiple of 256 columns (pad with +inf); `thr8[g]` = min(thr[8g .. 8g+7]) lets the
 // epilogue reject 8 columns of a row with one compare against the maximum it already has.
 struct ColFilter {
-  const float* thr = nullptr;  // [N padded to 256]; nullptr = no column filter
+  float* thr = nullptr;        // [N padded to 256]; nullptr = no column filter.  A column that fills up is closed (+inf)
   const float* thr8 = nullptr; // [N padded to 256, / 8]
   int* cnt = nullptr;          // [N]
   uint2* buf = nullptr;        // [N, cap]

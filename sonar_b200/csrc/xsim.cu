@@ -223,14 +223,16 @@ static XsimWs carve_xsim(int n, int m, int d, void* base) {
 
 // ---- one-pass bidirectional k-NN: the reverse direction (for every y row its best x rows) comes out of the SAME x . y^T GEMM
 // through the sweep epilogue's column filter (ColFilter, sonar_b200_internal.h) ----
-constexpr int kColCap = 256;          // candidate slots per y row (expected hits ~ k * kSampleStride * 2.4 ~ 80)
+constexpr int kColCap = 256;          // candidate slots per y row (expected hits = 16 * kSampleStride = 128, see below)
 constexpr int kSampleStride = 8;      // the thresholds come from every 8th x row: a 1/8-size GEMM instead of a second full one
-constexpr float kBf16DotMargin = 0.008f;  // |bf16 dot - exact dot| <= 2 * 2^-9 * sum |x_k y_k| <= 2^-8 for unit vectors
+constexpr float kThrSlack = 1e-5f;    // the sampled rows themselves must pass (>) their own score again in the full sweep
 
-// one warp per y row: threshold = (k-th best bf16 score among the sampled x rows) - margin.  Every x row whose exact cosine
-// is among the true top-k has a bf16 score above it (the k-th best over a SUBSET cannot exceed the k-th best over all rows).
+// one warp per y row: threshold = the 16th best bf16 score among the SAMPLED x rows.  The plain search keeps a row's 16 best
+// candidates by bf16 score and re-scores those exactly; a subset's 16th best cannot exceed the 16th best over all rows, so
+// everything the plain search would keep passes the threshold: the one-pass result is the two-pass result by construction,
+// for any data.  How many rows pass is distribution-free as well: about 16 x kSampleStride (order statistics of a 1/8 sample).
 __global__ void __launch_bounds__(256)
-col_threshold_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int lists, int m, int k,
+col_threshold_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int lists, int m,
                      float* __restrict__ thr) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -243,7 +245,7 @@ col_threshold_kernel(const float* __restrict__ cand_val, const int* __restrict__
     const float o = __shfl_sync(0xffffffffu, v, c);
     if (o > v || (o == v && c < lane)) ++rank;
   }
-  if (rank == k - 1) thr[row] = (v > -CUDART_INF_F) ? v - kBf16DotMargin : -CUDART_INF_F;
+  if (rank == kTopkCandidates - 1) thr[row] = (v > -CUDART_INF_F) ? v - kThrSlack : -CUDART_INF_F;  // < 16 sampled rows: all pass
 }
 
 // thr8[g] = min of the thresholds of columns 8g .. 8g+7: the sweep epilogue tests a row's 8-column maximum against it first
@@ -466,7 +468,7 @@ int sb_xsim_knn_bidir(const float* x, const float* y, int32_t n, int32_t m, int3
   if (rc) return rc;
   const long long mp = ((long long)m + 255) / 256 * 256;
   fill_f32_kernel<<<(unsigned)((mp + 255) / 256), 256, 0, stream>>>(w.thr, mp, INFINITY);  // padding columns: never hit
-  col_threshold_kernel<<<(unsigned)((m + 7) / 8), 256, 0, stream>>>(w.s_val, w.s_idx, gemm_topk_lists(1), m, k, w.thr);
+  col_threshold_kernel<<<(unsigned)((m + 7) / 8), 256, 0, stream>>>(w.s_val, w.s_idx, gemm_topk_lists(1), m, w.thr);
   group_min8_kernel<<<(unsigned)((mp / 8 + 255) / 256), 256, 0, stream>>>(w.thr, w.thr8, mp / 8);
   SB_CUDA_CHECK(cudaGetLastError());
   SB_CUDA_CHECK(cudaMemsetAsync(w.cnt, 0, sizeof(int) * (size_t)m, stream));

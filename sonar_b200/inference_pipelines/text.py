@@ -149,7 +149,7 @@ class TextToEmbeddingModelPipeline(torch.nn.Module):
             source: Iterable[str] = _read_text(Path(input))
             sorting_index = None
         else:
-            # so it should a list
+            # a list of sentences: encode in order of character length, restore the order at the end
             sorting_index = torch.argsort(torch.tensor(list(map(len, input))))
             source = (input[int(i)] for i in sorting_index.tolist())
 

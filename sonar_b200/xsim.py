@@ -50,8 +50,9 @@ def knn(x: Tensor, y: Tensor, k: int = 4) -> Tuple[Tensor, Tensor]:
 def knn_bidir(x: Tensor, y: Tensor, k: int = 4, stats: Optional[dict] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """Both k-NN directions from ONE pass over the similarity matrix (``sb_xsim_knn_bidir``):
     -> (cos_xy fp64 [n,k], idx_xy int32 [n,k], cos_yx fp64 [m,k], idx_yx int32 [m,k]); ``idx_yx`` indexes rows of ``x``.
-    The reverse direction's candidates are the products above per-column thresholds taken from a 1/8 sample of the x rows;
-    the few y rows whose threshold came out so low that they collect more candidates than their buffer holds (marked
+    The reverse direction's candidates are the products above per-column thresholds -- a y row's 16th best bf16 score
+    against every 8th x row, which cannot exceed its 16th best over all of them, so the result equals ``knn(y, x)`` for any
+    data; the few y rows that collect more candidates than their buffer holds (ties, duplicates; marked
     ``idx = -2`` by the kernel) are redone with the plain one-direction search against all of x (``stats["overflow_rows"]``
     reports how many, when a dict is passed)."""
     x, y = _need_cuda_f32(x), _need_cuda_f32(y)

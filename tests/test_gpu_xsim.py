@@ -142,3 +142,26 @@ def test_knn_bidir_column_overflow_takes_the_second_pass(native_lib, cuda_device
     v1, i1 = xsim.knn(xd, yd, 4)
     assert torch.equal(ixy, i1) and torch.equal(vxy, v1)
     assert int(iyx[7, 0]) < 600  # the duplicates are row 7's neighbours
+
+
+def test_knn_bidir_narrow_score_spread_equals_two_passes(native_lib, cuda_device):
+    """Embeddings with a large common component (what a random-init encoder produces): all cosines lie within ~0.01 of each
+    other, far inside the bf16 resolution of a dot product.  The column thresholds are order statistics of a sample, so the
+    number of candidates per y row does not depend on that spread: the one-pass result must equal the two one-direction
+    searches bit for bit, with (almost) no y row redone."""
+    from sonar_b200 import xsim
+
+    g = torch.Generator().manual_seed(23)
+    n = 20000
+    common = torch.randn((1, 1024), generator=g)
+    y = common + 0.1 * torch.randn((n, 1024), generator=g)
+    x = y + 0.03 * torch.randn((n, 1024), generator=g)
+    xd, yd = x.to(cuda_device), y.to(cuda_device)
+    stats = {}
+    vxy, ixy, vyx, iyx = xsim.knn_bidir(xd, yd, 4, stats)
+    v1, i1 = xsim.knn(xd, yd, 4)
+    v2, i2 = xsim.knn(yd, xd, 4)
+    assert torch.equal(ixy, i1) and torch.equal(vxy, v1)
+    assert torch.equal(iyx, i2) and torch.equal(vyx, v2)
+    assert stats["overflow_rows"] <= n // 100, stats
+    assert float((iyx[:, 0] == torch.arange(n, device=cuda_device)).float().mean()) > 0.99
