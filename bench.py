@@ -595,12 +595,16 @@ def bench_config5(model, dev, dist, rank, world, local, peaks, per_gpu, S=SEQ, B
     del x_all
     torch.cuda.synchronize()
     dist.barrier()
+    xsim_distributed(x_shard, y_shard, margin="ratio", k=4)  # warm-up: workspace allocation, communicator at these sizes
+    torch.cuda.synchronize()
+    dist.barrier()
     e0, e1 = ev(), ev()
     e0.record()
-    err, n_tot, _ = xsim_distributed(x_shard, y_shard, margin="ratio", k=4)
+    for _ in range(2):
+        err, n_tot, _ = xsim_distributed(x_shard, y_shard, margin="ratio", k=4)
     e1.record()
     torch.cuda.synchronize()
-    xs_ms = max_ms(e0, e1)
+    xs_ms = max_ms(e0, e1) / 2.0
     if rank != 0:
         return None
     peak = float(peaks["bf16_tflops_sustained"])
