@@ -264,3 +264,68 @@ def beam_search(lprob_fn, prompt: Tensor, n: int, cfg: BeamSearchConfig,
         # stable sort: score desc, earlier-finished first on ties
         out.append(sorted(finished[i], key=lambda h: -h[0])[:beam])
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Sampling (fairseq2 SamplingSeq2SeqGenerator + TopKSampler / TopPSampler [fs2], restated from the documented behaviour;
+# PARITY UNPINNED: fairseq2 is not installable and HuggingFace's samplers draw from another random stream).  The subset the
+# sampler keeps is taken over the WHOLE vocabulary here -- sonar_b200/sampling.py sees 16 candidates per row and must agree
+# whenever the subset lies inside them.
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class SamplingConfig:
+    top_k: Optional[int] = None   # exactly one of top_k / top_p
+    top_p: Optional[float] = None
+    num_gens: int = 1
+    min_gen_len: int = 1
+    max_gen_len: int = 128
+    normalize_scores: bool = True
+    len_penalty: float = 1.0
+    pad_idx: int = 0
+    eos_idx: int = 3
+
+
+def sampling_search(lprob_fn, prompt: Tensor, n: int, cfg: SamplingConfig, uniforms: Tensor
+                    ) -> List[List[Tuple[float, List[int]]]]:
+    """``lprob_fn(tokens [R,S]) -> [R,V]`` for R = n * num_gens rows (input-major); ``uniforms`` fp32 [max_gen_len, R]: the
+    number in [0, 1) row r consumes at generation step g.  -> per input its ``num_gens`` hypotheses in generation order as
+    (score, generated tokens incl. the final EOS); score = sum of the sampled tokens' log-probs, / step_nr ** len_penalty
+    when normalised."""
+    G = cfg.num_gens
+    R = n * G
+    P = prompt.numel()
+    seqs = [[int(v) for v in prompt] for _ in range(R)]
+    cum = [torch.zeros((), dtype=torch.float32) for _ in range(R)]
+    out: List[Optional[Tuple[float, List[int]]]] = [None] * R
+    for g in range(cfg.max_gen_len):
+        live = [r for r in range(R) if out[r] is None]
+        if not live:
+            break
+        lp = lprob_fn(torch.tensor([seqs[r] for r in live], dtype=torch.int64)).float()
+        for row, r in enumerate(live):
+            if g >= cfg.max_gen_len - 1:
+                t, l = cfg.eos_idx, lp[row, cfg.eos_idx]
+            else:
+                probs = lp[row].exp()
+                probs[cfg.pad_idx] = 0.0
+                if g < cfg.min_gen_len - 1:
+                    probs[cfg.eos_idx] = 0.0
+                order = torch.argsort(probs, descending=True, stable=True)  # probability desc, token asc
+                ps = probs[order]
+                if cfg.top_k is not None:
+                    w = ps.clone()
+                    w[cfg.top_k:] = 0.0
+                else:
+                    w = ps.masked_fill((ps.cumsum(0) - ps) > cfg.top_p, 0.0)
+                kept = int((w > 0).sum())
+                cdf = w[:kept].cumsum(0)
+                u = uniforms[g, r].float() * cdf[-1]
+                pick = min(int((cdf <= u).sum()), kept - 1)
+                t = int(order[pick])
+                l = lp[row, t]
+            seqs[r].append(t)
+            cum[r] = cum[r] + l
+            if t == cfg.eos_idx:
+                s = cum[r] / torch.tensor(float(P + g) ** cfg.len_penalty, dtype=torch.float32) if cfg.normalize_scores else cum[r]
+                out[r] = (float(s), seqs[r][P:])
+    return [[out[i * G + j] for j in range(G)] for i in range(n)]

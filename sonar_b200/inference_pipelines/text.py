@@ -18,6 +18,7 @@ from torch import Tensor
 from ..batching import collate, dynamic_bucket, prefetch, to_sequence_batch
 from ..batching import bucket
 from ..generation import BeamSearchSeq2SeqGenerator, SequenceToTextConverter
+from ..sampling import SamplingSeq2SeqGenerator
 from ..text_decoder import B200TextDecoderModel, sonar_text_decoder_config
 from ..text_encoder import B200TextEncoderModel, sonar_text_encoder_config
 from .utils import add_progress_bar
@@ -302,10 +303,11 @@ class EmbeddingToTextModelPipeline(torch.nn.Module):
     @torch.inference_mode()
     def predict(self, inputs: Tensor, target_lang: str, batch_size: int = 5, progress_bar: bool = False,
                 sampler=None, **generator_kwargs) -> List[str]:
-        if sampler is not None:
-            raise NotImplementedError("SamplingSeq2SeqGenerator is not part of the B200 path; use beam search")
         generator_kwargs.setdefault("pad_idx", self.tokenizer.vocab_info.pad_idx)
-        generator = BeamSearchSeq2SeqGenerator(self.model, **generator_kwargs)
+        if sampler is not None:  # text.py:313-316
+            generator = SamplingSeq2SeqGenerator(self.model, sampler, **generator_kwargs)
+        else:
+            generator = BeamSearchSeq2SeqGenerator(self.model, **generator_kwargs)
         converter = SequenceToTextConverter(generator, self.tokenizer, task="translation", target_lang=target_lang)
 
         def _do_translate(src_tensors: List[Tensor]) -> List[str]:

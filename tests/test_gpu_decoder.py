@@ -128,6 +128,51 @@ def test_embedding_to_text_pipeline(small, cuda_device):
         pipe.predict(emb, target_lang="fra_Latn", max_seq_len=2)  # no room after the 2-token prompt
 
 
+def test_sampling_generator_on_the_cuda_decoder(small, cuda_device):
+    """`predict(sampler=...)` (text.py:313-316): top-1 sampling is greedy search (= beam search with one beam); a seeded
+    generator reproduces its draws; the sampled tokens' scores are the oracle's log-probs of those very tokens; a nucleus
+    that needs more than the 16 returned candidates is refused."""
+    from oracle.text_decoder import OracleTextDecoder  # noqa: F401  (fixture type)
+    from sonar_b200.generation import BeamSearchSeq2SeqGenerator
+    from sonar_b200.inference_pipelines import EmbeddingToTextModelPipeline
+    from sonar_b200.sampling import SamplingSeq2SeqGenerator, TopKSampler, TopPSampler
+    from sonar_b200.tokenizer import SyntheticTokenizer
+
+    oracle, model = small
+    emb = _emb(6, seed=4).to(cuda_device)
+    prompt = torch.tensor([3, 77])
+    greedy = BeamSearchSeq2SeqGenerator(model, beam_size=1, max_gen_len=(0, 12), pad_idx=0)(emb, None, prompt, None)
+    top1 = SamplingSeq2SeqGenerator(model, TopKSampler(1), max_gen_len=(0, 12), pad_idx=0)(emb, None, prompt, None)
+    for a, b in zip(greedy.hypotheses, top1.hypotheses):
+        assert a[0].seq.tolist() == b[0].seq.tolist()
+
+    def run(seed):
+        gen = SamplingSeq2SeqGenerator(model, TopKSampler(8), num_gens=3, max_gen_len=(0, 10), compute_scores=True,
+                                       normalize_scores=False, pad_idx=0,
+                                       generator=torch.Generator(device=cuda_device).manual_seed(seed))
+        return gen(emb, None, prompt, None)
+
+    o1, o2, o3 = run(5), run(5), run(6)
+    seqs = lambda o: [[h.seq.tolist() for h in hs] for hs in o.hypotheses]  # noqa: E731
+    assert seqs(o1) == seqs(o2) and seqs(o1) != seqs(o3)
+    assert all(len(hs) == 3 and hs[0].score >= hs[1].score >= hs[2].score for hs in o1.hypotheses)
+    # raw score = sum of the fp32-oracle log-probs of the sampled tokens (teacher-forced), to the step's tolerance
+    for i, hs in enumerate(o1.hypotheses):
+        for h in hs:
+            toks = torch.cat([prompt, h.seq])[None]
+            want = 0.0
+            for t in range(len(h.seq)):
+                lp = oracle.step_lprobs(toks[:, : 2 + t], emb[i].cpu()[None, None, :])
+                want += float(lp[0, int(h.seq[t])])
+            assert abs(h.score - want) <= 2e-2 * len(h.seq) + 2e-3 * abs(want), (i, h.score, want)
+    pipe = EmbeddingToTextModelPipeline(model, SyntheticTokenizer(vocab_size=VOCAB), device=cuda_device)
+    texts = pipe.predict(emb, target_lang="fra_Latn", batch_size=4, sampler=TopKSampler(4), max_seq_len=12,
+                         generator=torch.Generator(device=cuda_device).manual_seed(1))
+    assert len(texts) == 6 and all(isinstance(t, str) for t in texts)
+    with pytest.raises(ValueError, match="nucleus"):  # 4096 near-uniform tokens: 0.999 of the mass is not in 16 of them
+        pipe.predict(emb, target_lang="fra_Latn", sampler=TopPSampler(0.999), max_seq_len=12)
+
+
 def test_cuda_graph_replay_equals_eager_generation(small, cuda_device):
     """The per-step CUDA graphs (engine launches + beam bookkeeping, captured once per step index) reproduce the eager
     search token for token, also when the cached graphs are replayed for a second batch of the same shape."""

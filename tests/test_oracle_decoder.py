@@ -152,3 +152,104 @@ def test_beam_search_follows_fairseq2_scoring_rules():
     cfg2 = BeamSearchConfig(beam_size=2, min_gen_len=2, max_gen_len=6, pad_idx=0, unk_idx=1, eos_idx=eos)
     (h2,) = beam_search(lprob_fn, torch.tensor([3, 4]), 1, cfg2)
     assert all(len(t) >= 2 for _, t in h2) and h2[0][1] == [5, eos]
+
+
+# ------------------------------------------------------------------------------------------------
+# sampling generator (the `sampler=` branch of EmbeddingToTextModelPipeline.predict, text.py:313-316)
+# ------------------------------------------------------------------------------------------------
+def _peaky_decoder(v=40):
+    cfg = OracleDecoderConfig(model_dim=32, vocab_size=v, num_layers=1, num_heads=2, ffn_inner_dim=64, max_seq_len=32)
+    sd = make_synthetic_decoder_state_dict(cfg, seed=5, weight_std=0.4)
+    sd["decoder_frontend.embed.weight"] *= 6.0
+    sd["final_proj.weight"] = sd["decoder_frontend.embed.weight"]
+    return OracleTextDecoder(cfg, sd), VocabularyInfo(size=v, unk_idx=1, bos_idx=2, eos_idx=3, pad_idx=1)
+
+
+@pytest.mark.parametrize("kind,arg,num_gens,min_len,max_len", [("k", 1, 1, 1, 8), ("k", 5, 3, 2, 9), ("k", 14, 2, 1, 6),
+                                                               ("p", 0.5, 2, 1, 9), ("p", 0.8, 1, 3, 7)])
+def test_product_sampling_equals_oracle_given_the_same_uniform_numbers(kind, arg, num_gens, min_len, max_len):
+    """The product draws by inverse CDF over the 16 candidates the step returns; the oracle over the whole vocabulary.  Fed
+    the same uniform numbers they must produce the same tokens and the same (normalised) scores."""
+    from oracle.text_decoder import SamplingConfig, sampling_search
+    from sonar_b200.sampling import SamplingSeq2SeqGenerator, TopKSampler, TopPSampler
+
+    torch.manual_seed(1)
+    dec, vocab = _peaky_decoder()
+    n = 4
+    emb = torch.randn(n, 32)
+    prompt = torch.tensor([3, 17])
+    R = n * num_gens
+    uni = torch.rand((max_len, R), generator=torch.Generator().manual_seed(7))
+    sampler = TopKSampler(arg) if kind == "k" else TopPSampler(arg)
+    gen = SamplingSeq2SeqGenerator(_OracleBackedModel(dec, vocab, 32), sampler, num_gens=num_gens, min_gen_len=min_len,
+                                   max_gen_len=(0, max_len), compute_scores=True, pad_idx=0, sync_every=2,
+                                   uniform_fn=lambda g, rows: uni[g])
+    try:
+        out = gen(emb, None, prompt, None)
+    except ValueError as e:  # a nucleus wider than 16 tokens is refused, never truncated
+        assert kind == "p" and "nucleus" in str(e)
+        pytest.skip("nucleus wider than the step's 16 candidates for this seed")
+    scfg = SamplingConfig(top_k=arg if kind == "k" else None, top_p=arg if kind == "p" else None, num_gens=num_gens,
+                          min_gen_len=min_len, max_gen_len=max_len, pad_idx=0, eos_idx=3)
+    enc = emb[:, None, :].repeat_interleave(num_gens, 0)
+    # the oracle steps only the still-live rows, so it is run one hypothesis row at a time (row r consumes column r of `uni`)
+    ref = []
+    for i in range(n):
+        per_gen = []
+        for j in range(num_gens):
+            r = i * num_gens + j
+            one = sampling_search(lambda toks, _r=r: dec.step_lprobs(toks, enc[_r:_r + 1]), prompt, 1,
+                                  SamplingConfig(top_k=scfg.top_k, top_p=scfg.top_p, num_gens=1, min_gen_len=min_len,
+                                                 max_gen_len=max_len, pad_idx=0, eos_idx=3), uni[:, r:r + 1])
+            per_gen.append(one[0][0])
+        ref.append(per_gen)
+    for i in range(n):
+        want = sorted(ref[i], key=lambda h: -h[0])  # compute_scores: best first (stable)
+        got = out.hypotheses[i]
+        assert [h.seq.tolist() for h in got] == [w[1] for w in want], i
+        for h, w in zip(got, want):
+            assert abs(h.score - w[0]) <= 1e-6 * max(1.0, abs(w[0]))
+        for h in got:
+            assert h.seq[-1] == 3 and len(h.seq) >= min(min_len, max_len) and len(h.seq) <= max_len
+
+
+def test_top1_sampling_is_greedy_search():
+    """TopKSampler(1) has one token to draw from: the result is beam search with a beam of one."""
+    from sonar_b200.sampling import SamplingSeq2SeqGenerator, TopKSampler
+
+    torch.manual_seed(2)
+    dec, vocab = _peaky_decoder()
+    emb = torch.randn(5, 32)
+    prompt = torch.tensor([3, 9])
+    beam = BeamSearchSeq2SeqGenerator(_OracleBackedModel(dec, vocab, 32), beam_size=1, max_gen_len=(0, 10), pad_idx=0)
+    samp = SamplingSeq2SeqGenerator(_OracleBackedModel(dec, vocab, 32), TopKSampler(1), max_gen_len=(0, 10), pad_idx=0,
+                                    generator=torch.Generator().manual_seed(3))
+    a, b = beam(emb, None, prompt, None), samp(emb, None, prompt, None)
+    for ha, hb in zip(a.hypotheses, b.hypotheses):
+        assert ha[0].seq.tolist() == hb[0].seq.tolist()
+        assert hb[0].score is None  # compute_scores=False
+
+
+def test_sampling_argument_errors():
+    from sonar_b200.sampling import SamplingSeq2SeqGenerator, TopKSampler, TopPSampler
+
+    dec, vocab = _peaky_decoder()
+    m = _OracleBackedModel(dec, vocab, 32)
+    with pytest.raises(ValueError):
+        TopKSampler(0)
+    with pytest.raises(ValueError):
+        TopKSampler(15)
+    with pytest.raises(ValueError):
+        TopPSampler(0.0)
+    with pytest.raises(ValueError):
+        SamplingSeq2SeqGenerator(m, TopKSampler(2), num_gens=0)
+    with pytest.raises(NotImplementedError):
+        SamplingSeq2SeqGenerator(m, TopKSampler(2), temperature=0.7)
+    # a flat distribution: the 0.99 nucleus cannot fit into 16 of 40 tokens -> refused after the call
+    cfg = OracleDecoderConfig(model_dim=32, vocab_size=40, num_layers=1, num_heads=2, ffn_inner_dim=64, max_seq_len=32)
+    sd = make_synthetic_decoder_state_dict(cfg, seed=5, weight_std=0.02)
+    sd["final_proj.weight"] = sd["decoder_frontend.embed.weight"]
+    flat = _OracleBackedModel(OracleTextDecoder(cfg, sd), vocab, 32)
+    with pytest.raises(ValueError, match="nucleus"):
+        SamplingSeq2SeqGenerator(flat, TopPSampler(0.99), max_gen_len=(0, 4), pad_idx=0)(torch.randn(2, 32), None,
+                                                                                          torch.tensor([3, 9]), None)
