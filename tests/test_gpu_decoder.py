@@ -146,6 +146,19 @@ def test_sampling_generator_on_the_cuda_decoder(small, cuda_device):
     for a, b in zip(greedy.hypotheses, top1.hypotheses):
         assert a[0].seq.tolist() == b[0].seq.tolist()
 
+    # a random decoder with tied embeddings predicts its own input token with probability ~1 (the residual stream carries
+    # that token's embedding straight into the output projection): shrink the embeddings so that 8 candidates leave something
+    # to draw
+    from sonar_b200 import B200TextDecoderModel, VocabularyInfo, sonar_text_decoder_config
+    ocfg = OracleDecoderConfig(vocab_size=VOCAB, num_layers=2, max_seq_len=64)
+    sd = make_synthetic_decoder_state_dict(ocfg, seed=3)
+    sd["decoder_frontend.embed.weight"] *= 0.15
+    sd["final_proj.weight"] = sd["decoder_frontend.embed.weight"]
+    oracle = OracleTextDecoder(ocfg, sd)
+    model = B200TextDecoderModel(sonar_text_decoder_config(
+        "basic", num_decoder_layers=2, max_seq_len=64,
+        vocab_info=VocabularyInfo(size=VOCAB, unk_idx=1, bos_idx=2, eos_idx=3, pad_idx=1)), sd, cuda_device)
+
     def run(seed):
         gen = SamplingSeq2SeqGenerator(model, TopKSampler(8), num_gens=3, max_gen_len=(0, 10), compute_scores=True,
                                        normalize_scores=False, pad_idx=0,
