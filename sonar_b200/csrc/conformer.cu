@@ -413,25 +413,36 @@ attention_relpos_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 // conv module middle: GLU -> depthwise conv (k taps, "same", zero outside the utterance) -> BN(scale,shift) -> SiLU
 //   g bf16 [T, 2D] (pointwise_conv1 output: value | gate), out bf16 [T, D]
 // ---------------------------------------------------------------------------------------------
+// Two adjacent channels per thread: value pairs come out of shared memory as 64-bit loads and every tap is ONE packed
+// fma.rn.f32x2 (FFMA2) for both channels -- the kernel is issue-bound (31 taps per output next to the GLU, BatchNorm and SiLU
+// arithmetic), and the packed form halves the FMA issue slots.  Per output the taps are applied in the order k = 0..KS-1
+// with IEEE fma, exactly as a scalar loop would.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 template <int KS>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(128, 5)
 glu_dwconv_kernel(const __nv_bfloat16* __restrict__ g, const int32_t* __restrict__ cu, int D,
                   const float* __restrict__ dw, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
                   __nv_bfloat16* __restrict__ out) {
-  constexpr int TP = 64, HALO = KS / 2, ROWS = TP + KS - 1;
+  constexpr int TP = 64, HALO = KS / 2, ROWS = TP + KS - 1, PP = 16, TAPLD = 66;
   __shared__ __align__(16) float tile[ROWS][64];
-  __shared__ float taps[64 * KS];  // this block's 64 channels x KS taps, read from dw [D, KS] with coalesced loads
+  __shared__ __align__(8) float taps[KS][TAPLD];  // this block's 64 channels, transposed to [tap][channel] (row pad: 2-way banks)
   const int b = blockIdx.z, c0 = blockIdx.y * 64, t0 = blockIdx.x * TP;
   const int start = cu[b], len = cu[b + 1] - start;
   if (t0 >= len) return;
   const int tid = threadIdx.x;
-  for (int i = tid; i < 64 * KS; i += 256) taps[i] = __ldg(dw + (long long)c0 * KS + i);
+  for (int i = tid; i < 64 * KS; i += 128) taps[i % KS][i / KS] = __ldg(dw + (long long)c0 * KS + i);  // coalesced read of dw [D, KS]
   // 16-byte loads, 8 channels of value and gate per thread; every load of the block is in flight before the first use
-  constexpr int kIt = (ROWS * 8 + 255) / 256;
+  constexpr int kIt = (ROWS * 8 + 127) / 128;
   uint4 a4[kIt], g4[kIt];
 #pragma unroll
   for (int it = 0; it < kIt; ++it) {
-    const int i = tid + it * 256;
+    const int i = tid + it * 128;
     const int pos = t0 - HALO + (i >> 3);
     a4[it] = g4[it] = make_uint4(0u, 0u, 0u, 0u);  // bf16 zeros: 0 * sigmoid(0) = 0 outside the utterance
     if (i < ROWS * 8 && pos >= 0 && pos < len) {
@@ -442,7 +453,7 @@ glu_dwconv_kernel(const __nv_bfloat16* __restrict__ g, const int32_t* __restrict
   }
 #pragma unroll
   for (int it = 0; it < kIt; ++it) {
-    const int i = tid + it * 256;
+    const int i = tid + it * 128;
     if (i < ROWS * 8) {
       const int p = i >> 3, c8 = (i & 7) * 8;
       const uint32_t aw[4] = {a4[it].x, a4[it].y, a4[it].z, a4[it].w}, gw[4] = {g4[it].x, g4[it].y, g4[it].z, g4[it].w};
@@ -459,26 +470,26 @@ glu_dwconv_kernel(const __nv_bfloat16* __restrict__ g, const int32_t* __restrict
     }
   }
   __syncthreads();
-  const int c = tid & 63, pg = tid >> 6;  // 4 groups of 16 positions; each thread slides a register window down one channel
-  float w[KS];
+  const int cp = (tid & 31) * 2, pg = tid >> 5;  // channel pair; 4 groups of 16 positions, a register window slides down them
+  float2 win[PP + KS - 1];
 #pragma unroll
-  for (int k = 0; k < KS; ++k) w[k] = taps[c * KS + k];  // stride KS (odd) words across the lanes: conflict-free
-  const float sc = bn_scale[c0 + c], sh = bn_shift[c0 + c];
-  constexpr int PP = 16;
-  float win[PP + KS - 1];
+  for (int i = 0; i < PP + KS - 1; ++i) win[i] = *reinterpret_cast<const float2*>(&tile[pg * PP + i][cp]);
+  float2 acc[PP];
 #pragma unroll
-  for (int i = 0; i < PP + KS - 1; ++i) win[i] = tile[pg * PP + i][c];
-  float acc[PP];
+  for (int pp = 0; pp < PP; ++pp) acc[pp] = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int pp = 0; pp < PP; ++pp) acc[pp] = 0.f;
+  for (int k = 0; k < KS; ++k) {  // tap-major: PP independent chains in flight
+    const float2 w = *reinterpret_cast<const float2*>(&taps[k][cp]);
 #pragma unroll
-  for (int k = 0; k < KS; ++k)  // tap-major: PP independent FMA chains in flight
-#pragma unroll
-    for (int pp = 0; pp < PP; ++pp) acc[pp] = fmaf(w[k], win[pp + k], acc[pp]);
+    for (int pp = 0; pp < PP; ++pp) acc[pp] = fma2(w, win[pp + k], acc[pp]);
+  }
+  const float2 sc = *reinterpret_cast<const float2*>(bn_scale + c0 + cp), sh = *reinterpret_cast<const float2*>(bn_shift + c0 + cp);
 #pragma unroll
   for (int pp = 0; pp < PP; ++pp) {
     const int pos = t0 + pg * PP + pp;
-    if (pos < len) out[(long long)(start + pos) * D + c0 + c] = __float2bfloat16_rn(silu_fast(acc[pp] * sc + sh));
+    if (pos < len)
+      *reinterpret_cast<uint32_t*>(out + (long long)(start + pos) * D + c0 + cp) =
+          pack_bf16x2(silu_fast(acc[pp].x * sc.x + sh.x), silu_fast(acc[pp].y * sc.y + sh.y));
   }
 }
 
@@ -763,7 +774,13 @@ int sb_speech_encoder_forward(SbSpeechEncoder* e, const float* fbank, int32_t pa
     // (c) convolution module
     if ((rc = layernorm_bf16(w.x, L.conv_ln_g, L.conv_ln_b, eps, w.h, T, D, stream))) return rc;
     if ((rc = gemm(w.h, D, L.pw1, D, w.big, 2 * D, 0, e->w.zeros, (int)T, 2 * D, D, EPI_BIAS))) return rc;
-    glu_dwconv_kernel<31><<<dim3((unsigned)((smax + 63) / 64), (unsigned)(D / 64), (unsigned)B), 256, 0, stream>>>(
+    {
+      static bool carve_set[64] = {};
+      if (first_use_on_device(carve_set))  // 5 CTAs x 32 KB of static shared memory per SM: ask for the large carve-out
+        SB_CUDA_CHECK(cudaFuncSetAttribute(glu_dwconv_kernel<31>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           cudaSharedmemCarveoutMaxShared));
+    }
+    glu_dwconv_kernel<31><<<dim3((unsigned)((smax + 63) / 64), (unsigned)(D / 64), (unsigned)B), 128, 0, stream>>>(
         w.big, cu_dev, D, L.dw, L.bn_scale, L.bn_shift, w.h);
     SB_CUDA_CHECK(cudaGetLastError());
     if ((rc = gemm(w.h, D, L.pw2, D, w.x, D, 1, e->w.zeros, (int)T, D, D, EPI_BIAS_RESIDUAL))) return rc;
