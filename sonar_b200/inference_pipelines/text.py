@@ -7,6 +7,7 @@ B200 engine (``sonar_b200.text_encoder.B200TextEncoderModel``).
 
 from __future__ import annotations
 
+import contextlib
 import os
 import warnings
 from pathlib import Path
@@ -27,28 +28,21 @@ Device = Union[str, torch.device]
 CPU = torch.device("cpu")
 
 
-class precision_context:
-    """Same behaviour as the reference context manager (``text.py:36-54``): maps the model
-    dtype to ``torch.set_float32_matmul_precision``.  It has no effect on the sm_100a
-    kernels (bf16 operands, fp32 accumulate) and is kept for API fidelity."""
+_MATMUL_PRECISION = {torch.bfloat16: "medium", torch.float16: "medium", torch.float32: "high", torch.float64: "highest"}
 
-    dtype_to_precision: Dict[torch.dtype, str] = {
-        torch.bfloat16: "medium",
-        torch.float16: "medium",
-        torch.float32: "high",
-        torch.float64: "highest",
-    }
 
-    def __init__(self, dtype: torch.dtype):
-        self.precision = self.dtype_to_precision.get(dtype, "high")
-
-    def __enter__(self):
-        self.original_precision = torch.get_float32_matmul_precision()
-        if self.precision:
-            torch.set_float32_matmul_precision(self.precision)
-
-    def __exit__(self, exc_type, exc_value, traceback):
-        torch.set_float32_matmul_precision(self.original_precision)
+@contextlib.contextmanager
+def precision_context(dtype: torch.dtype):
+    """What the reference wraps every pipeline run in (``text.py:36-54``): torch's float32 matmul precision follows the model
+    dtype for the duration of the call and is put back afterwards.  The sm_100a kernels are not affected by that switch
+    (bf16 operands, fp32 accumulate, always); it is honoured so that torch code a caller runs inside the same ``with`` block
+    behaves as it would around the reference."""
+    before = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision(_MATMUL_PRECISION.get(dtype, "high"))
+    try:
+        yield
+    finally:
+        torch.set_float32_matmul_precision(before)
 
 
 def _load_encoder_card(name: str, device: Device) -> B200TextEncoderModel:
