@@ -1,7 +1,9 @@
 """CPU oracle for xsim cosine-margin mining.  TEST INFRASTRUCTURE ONLY (see oracle/text_encoder.py).
 
-PARITY UNPINNED: the reference repository contains no xsim code, fixture or golden -- only the word
-in README.md:5 and result tables (README.md:19-22).  This file restates the public LASER
+PARITY UNPINNED against the reference: the repository contains no xsim code, fixture or golden -- only the word
+in README.md:5 and result tables (README.md:19-22).  Pinned instead against an independent implementation
+(tests/test_oracle_xsim.py: scikit-learn's brute-force cosine k-NN for the search, a dense evaluation of the margin
+formula for the scoring).  This file restates the public LASER
 ``xsim.py`` algorithm in float64 NumPy: L2-normalise, cosine = inner
 product, k-NN in both directions, ratio/distance margin over the forward k candidates, prediction
 = candidate with the best margin score, ties broken by the lowest candidate rank (first maximum),
