@@ -12,11 +12,13 @@ the encoder output, then a bias-free 1024->1024 projection (``sonar_speech/facto
 
 The Conformer internals live in fairseq2's w2v-BERT ``600m`` config, which is not on disk: the block is
 restated from the identical-by-parameter-name HuggingFace ``SeamlessM4TConformerEncoderLayer`` and PINNED against it
-through ``tests/golden/conformer_layer_small.pt`` (``tests/golden/make_conformer_golden.py``).  The pooler's POST-LN
+through ``tests/golden/conformer_layer_small.pt`` (``tests/golden/make_conformer_golden.py``); the whole stack before the
+pooler (2-frame stacking, LayerNorm + projection frontend, block composition, final LayerNorm) is PINNED against HuggingFace's
+feature projection + ``SeamlessM4TConformerEncoder`` (``tests/golden/conformer_encoder_small.pt``).  The pooler's POST-LN
 decoder-layer stack is PINNED against HuggingFace ``BartDecoderLayer`` (``tests/golden/pooler_layers_small.pt``,
 ``make_pooler_golden.py``); the fbank features are pinned against torchaudio on the reference's own audio clips
 (``tests/test_reference_audio.py``).  What stays unpinned offline: the w2v-BERT ``600m`` hyper-parameters, the
-frame-stacking frontend and the pooler's one-token input (the reference's golden ``speech_embedding.pt`` needs the downloaded
+pooler's one-token input (the reference's golden ``speech_embedding.pt`` needs the downloaded
 checkpoint; ``tests/test_reference_audio.py`` runs it when ``SONAR_B200_CHECKPOINT_DIR`` is set).
 """
 
@@ -208,9 +210,10 @@ class OracleSpeechEncoder:
         return F.linear(x, self.sd["encoder_pooler.projection_out.weight"]).squeeze(1)  # bias-free (factory.py:146-152)
 
     @torch.no_grad()
-    def forward(self, fbank: Tensor, frame_lens: List[int]) -> Tuple[Tensor, Tensor, List[int]]:
-        """fbank [B, T, 80] zero-padded, T even; frame_lens = true frame counts.
-        -> (sentence_embeddings [B, D], encoder_output [B, T/2, D] after model.layer_norm, positions per utterance)."""
+    def encode(self, fbank: Tensor, frame_lens: List[int]) -> Tuple[Tensor, Tensor, List[int]]:
+        """Everything before the pooler: fbank [B, T, 80] zero-padded, T even -> (encoder output [B, T/2, D] after
+        model.layer_norm, key mask [B, T/2], positions per utterance).  Pinned against HuggingFace's SeamlessM4T Conformer
+        encoder (tests/golden/conformer_encoder_small.pt)."""
         cfg, sd = self.cfg, self.sd
         b, t, nm = fbank.shape
         x = fbank.float().reshape(b, t // 2, nm * 2)  # stack 2 frames; seq_len // 2 (App. B.2)
@@ -223,6 +226,13 @@ class OracleSpeechEncoder:
         for i in range(cfg.num_layers):
             x = self.conformer_block(i, x, key_ok)
         x = F.layer_norm(x, (cfg.model_dim,), sd["layer_norm.weight"], sd["layer_norm.bias"], cfg.ln_eps)
+        return x, key_ok, lens
+
+    @torch.no_grad()
+    def forward(self, fbank: Tensor, frame_lens: List[int]) -> Tuple[Tensor, Tensor, List[int]]:
+        """fbank [B, T, 80] zero-padded, T even; frame_lens = true frame counts.
+        -> (sentence_embeddings [B, D], encoder_output [B, T/2, D] after model.layer_norm, positions per utterance)."""
+        x, key_ok, lens = self.encode(fbank, frame_lens)
         return self.pooler(x, key_ok), x, lens
 
     __call__ = forward

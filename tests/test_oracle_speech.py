@@ -55,6 +55,19 @@ def test_oracle_conformer_block_matches_hf_golden():
     torch.testing.assert_close(out * ok[:, :, None], g["out"] * ok[:, :, None], rtol=1e-5, atol=1e-5)
 
 
+def test_oracle_frontend_and_block_stack_match_hf_conformer_encoder_golden():
+    """The whole stack before the pooler -- 2-frame stacking, LayerNorm(160) + projection, two Conformer blocks, the final
+    LayerNorm -- against HuggingFace's SeamlessM4T (w2v-BERT) feature projection + Conformer encoder on shared random
+    weights (golden made by tests/golden/make_conformer_encoder_golden.py), ragged batch, valid positions compared."""
+    from oracle.speech_encoder import OracleSpeechConfig, OracleSpeechEncoder
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "conformer_encoder_small.pt"), weights_only=True)
+    enc = OracleSpeechEncoder(OracleSpeechConfig(**g["config"]), g["state_dict"])
+    out, ok, lens = enc.encode(g["fbank"], g["frame_lens"])
+    assert lens == [n // 2 for n in g["frame_lens"]]
+    torch.testing.assert_close(out * ok[:, :, None], g["out"] * ok[:, :, None], rtol=1e-5, atol=2e-5)
+
+
 def test_oracle_speech_padding_invariance():
     """An utterance's embedding must not depend on its batch neighbours / padding (key masks, zeroed conv inputs)."""
     from oracle.speech_encoder import OracleSpeechConfig, OracleSpeechEncoder, make_synthetic_speech_state_dict
