@@ -1,8 +1,9 @@
 """Sampling generation over the B200 decoder -- the ``sampler=`` branch of ``EmbeddingToTextModelPipeline.predict``
 (``sonar/inference_pipelines/text.py:313-320``): fairseq2's ``SamplingSeq2SeqGenerator`` with a ``TopKSampler`` or
 ``TopPSampler`` [fs2].  fairseq2 is not installable here, so the semantics below are restated from its documented
-behaviour and are **parity unpinned** (``oracle/text_decoder.py::sampling_search`` is the CPU restatement the tests hold
-this file to):
+behaviour and are **parity unpinned** against it (``oracle/text_decoder.py::sampling_search`` is the CPU restatement the
+tests hold this file to; the token subsets the two samplers keep are pinned against HuggingFace's ``TopKLogitsWarper`` /
+``TopPLogitsWarper``, ``tests/test_oracle_decoder.py``):
 
 * every step turns the next-token distribution into probabilities, zeroes PAD, zeroes EOS while the hypothesis is shorter
   than ``min_gen_len``, lets the sampler keep a subset (the ``k`` most probable tokens / the smallest prefix of the
